@@ -1,0 +1,228 @@
+/*
+ * smcrt.h — C ABI of libsmcrt_gpu.so, the B200 (sm_100a) photon-packet transport engine that
+ * replaces the body of signedMCRT/RSMCRT's `run_MCRT` (reference: src/kernelsMod.f90:1790-1898).
+ *
+ * The reference has no FFI for this path: its hot path is reached through ordinary Fortran module
+ * calls and communicates through module-global state.  The de-facto operator boundary is the
+ * `run_MCRT` dummy-argument list + the module globals it touches; every entry point
+ * below cites the reference state it carries across.  All signatures are plain pointers / sizes so a
+ * Fortran 2018 host binds them with ISO_C_BINDING (see INTEGRATION.md for the `bind(C)` interface
+ * block and the `select type` flattener a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; `smcrt_last_error()` gives the message.
+ *     (the reference's convention is `error stop`; the Fortran shim maps non-zero to `error stop`).
+ *   - all host arrays are owned by the caller; the library copies during the call and never retains
+ *     pointers.  Host precision is real64 (reference `wp`, src/constants.f90:18); the f64 -> f32 drop
+ *     happens inside smcrt_set_*.
+ *   - indices that name a top-level SDF ("layer") are 1-based like the reference; 0 = "outside all".
+ *   - single-threaded entry is assumed (the reference calls run_MCRT from serial context).
+ */
+#ifndef SMCRT_H
+#define SMCRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smcrt_ctx smcrt_ctx; /* opaque */
+
+/* ---- SDF node kinds (reference: src/sdfs/sdfs.f90:494-735, sdfModifiers.f90:286-491) -------- */
+enum smcrt_node_kind {
+    SMCRT_SPHERE = 1,     /* params: r                                  sdfs.f90:494-508 */
+    SMCRT_BOX = 2,        /* params: hx,hy,hz (HALF lengths as stored)   sdfs.f90:510-525 */
+    SMCRT_TORUS = 3,      /* params: oradius, iradius                    sdfs.f90:527-542 */
+    SMCRT_CYLINDER = 4,   /* params: a(3), b(3), radius                  sdfs.f90:544-581 */
+    SMCRT_TRIPRISM = 5,   /* params: h1, h2                              sdfs.f90:583-597 */
+    SMCRT_SEGMENT = 6,    /* params: a(3), b(3)   (radius fixed 0.1)     sdfs.f90:599-626 */
+    SMCRT_CAPSULE = 7,    /* params: a(3), b(3), r                       sdfs.f90:628-648 */
+    SMCRT_CONE = 8,       /* params: a(3), b(3), ra, rb                  sdfs.f90:650-686 */
+    SMCRT_EGG = 9,        /* params: r1, r2, h                           sdfs.f90:688-718 */
+    SMCRT_PLANE = 10,     /* params: a(3) unit normal                    sdfs.f90:720-735 */
+    /* CSG `model`: left fold of op over children (sdf_base.f90:146-161); params: k */
+    SMCRT_MODEL_UNION = 20,        /* sdfModifiers.f90:428-441 */
+    SMCRT_MODEL_SMOOTHUNION = 21,  /* sdfModifiers.f90:443-459 */
+    SMCRT_MODEL_SUBTRACTION = 22,  /* sdfModifiers.f90:461-476 */
+    SMCRT_MODEL_INTERSECTION = 23, /* sdfModifiers.f90:478-491 */
+    /* single-child modifiers; their own transform is identity and unused (sdfModifiers.f90:180-280) */
+    SMCRT_MOD_REVOLUTION = 30, /* params: o, cx,cy,cz    :303-321 */
+    SMCRT_MOD_EXTRUDE = 31,    /* params: h              :286-301 */
+    SMCRT_MOD_ONION = 32,      /* params: thickness      :323-333 */
+    SMCRT_MOD_TWIST = 33,      /* params: k              :353-371 */
+    SMCRT_MOD_BEND = 34,       /* params: k              :373-391 */
+    SMCRT_MOD_ELONGATE = 35    /* params: sx,sy,sz       :335-351 */
+    /* `displacement` carries a Fortran procedure pointer and `repeat` is `error stop` in the
+       reference (:393-426); neither can cross a C ABI and no shipped scene uses them. */
+};
+#define SMCRT_NODE_PARAMS 8
+
+/* ---- photon sources (reference: src/photon.f90:214-1043) ---------------------------------- */
+enum smcrt_source_kind {
+    SMCRT_SRC_POINT = 1,    /* photon.f90:311-359 */
+    SMCRT_SRC_PENCIL = 2,   /* photon.f90:652-710 */
+    SMCRT_SRC_UNIFORM = 3,  /* photon.f90:566-649 */
+    SMCRT_SRC_CIRCULAR = 4, /* photon.f90:214-308 */
+    SMCRT_SRC_FOCUS = 5,    /* photon.f90:361-563 */
+    SMCRT_SRC_ANNULUS = 6   /* photon.f90:850-1043 */
+};
+/* source parameter block, 24 doubles (what `photon_origin` + the emitters' dict keys hold) */
+enum smcrt_source_slot {
+    SMCRT_SP_POS = 0,       /* [0..2]  photon_origin%pos            photon.f90:88-97 */
+    SMCRT_SP_DIR = 3,       /* [3..5]  photon_origin%n{x,y,z}p */
+    SMCRT_SP_P1 = 6,        /* [6..8]  dict pos1%x..z  (uniform)    photon.f90:596-606 */
+    SMCRT_SP_P2 = 9,        /* [9..11] dict pos2 */
+    SMCRT_SP_P3 = 12,       /* [12..14] dict pos3 */
+    SMCRT_SP_RADIUS = 15,   /* dict radius (circular) */
+    SMCRT_SP_FOCAL = 16,    /* dict focalLength */
+    SMCRT_SP_BEAM = 17,     /* dict beam_size */
+    SMCRT_SP_RLO = 18,      /* dict rlo */
+    SMCRT_SP_RHI = 19,      /* dict rhi */
+    SMCRT_SP_SIGMA = 20,    /* dict sigma */
+    SMCRT_SP_ROT = 21       /* [21..23] dict rotation%x..z (already normalised by the parser) */
+};
+#define SMCRT_SOURCE_PARAMS 24
+/* `subtype` of smcrt_set_source: focus_type / annulus_type strings of the reference */
+enum smcrt_source_subtype {
+    SMCRT_FOCUS_SQUARE = 1, SMCRT_FOCUS_CIRCLE = 2, SMCRT_FOCUS_GAUSSIAN = 3,
+    SMCRT_ANNULUS_TOPHAT = 1, SMCRT_ANNULUS_BESSEL = 2, SMCRT_ANNULUS_GAUSSIAN = 3
+};
+
+/* ---- detectors (reference: src/detectors/detectors.f90) ------------------------------------ */
+enum smcrt_detector_kind {
+    SMCRT_DET_CIRCLE = 1,  /* p: pos(3) dir(3) radius                                   :107-164 */
+    SMCRT_DET_ANNULUS = 2, /* p: pos(3) dir(3) r1 r2                                    :166-244 */
+    SMCRT_DET_FIBRE = 3,   /* p: pos(3) dir(3) f1 f2 f1Ap f2Ap frontOff backOff frontToPin
+                                 pinToBack pinAp acceptAngle coreDiameter               :246-393 */
+    SMCRT_DET_CAMERA = 4   /* p: p1(3) p2(3) p3(3) maxval                               :395-469 */
+};
+#define SMCRT_DET_PARAMS 20
+
+/* ---- tally selection: the reference's compile-time flags become run-time bits -------------- */
+enum smcrt_tally_mode {
+    SMCRT_TALLY_ABSORB = 1,     /* recordWeight, kernelsMod.f90:2202-2220 (always on in the reference) */
+    SMCRT_TALLY_PATHLENGTH = 2, /* -Dpathlength: update_grids DDA, inttau2.f90:408-445 */
+    SMCRT_TALLY_EMISSION = 4    /* state%render_source: recordEmissionLocation, kernelsMod.f90:2184-2200 */
+};
+
+/* per-run counters the reference keeps on the packet but never prints (photon.f90:48) plus engine health */
+typedef struct smcrt_counters {
+    double nscatt;        /* Σ scatter events            (kernelsMod.f90:1965, reduction(+:nscatt)) */
+    double sdf_evals;     /* Σ packet%cnts               (inttau2.f90:67,83,138,183,219,232) */
+    double bounces;       /* Σ packet%bounces            (inttau2.f90:311) */
+    double launched;      /* packets launched (== nphotons) */
+    double emit_retries;  /* re-emissions of the start-voxel rejection loop (kernelsMod.f90:1939-1943) */
+    double lost;          /* packets killed by an engine guard (step cap / bounces>1000 / layer 0) */
+    double sweeps;        /* eval-all sweeps executed (engine instrumentation; == sdf_evals / n_top) */
+    double det_hits;      /* detector hits recorded */
+} smcrt_counters;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* n_gpus devices driven from this one process (the reference's OpenMP thread count becomes a GPU count,
+   kernelsMod.f90:1833-1836).  device_ids may be NULL (= 0..n_gpus-1); n_gpus==0 means "all visible". */
+int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids);
+void smcrt_destroy(smcrt_ctx* ctx);
+const char* smcrt_last_error(void);
+/* returns e.g. "smcrt-b200 0.1 sm_100a" */
+const char* smcrt_version(void);
+
+/* state%grid = init_grid_cart(n*, *max)  (src/grid.f90:119-159, parse.f90:110).  Allocates (and zeroes)
+   the tally grids like alloc_array/zarray (src/setup.f90:29-30, :170-190). */
+int smcrt_set_grid(smcrt_ctx* ctx, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax);
+
+/* array(:) of type(sdf), flattened.  Node i: kind[i]; children (models: n_child>=1,
+   modifiers: exactly 1) are the CONTIGUOUS nodes first_child[i] .. first_child[i]+n_child[i]-1;
+   xform = n_nodes x 16, each 4x4 in Fortran column-major order exactly as `sdf_base%transform` is stored
+   (row-vector convention p' = p.M, translation in row 4: vector_class.f90:292-304);
+   params = n_nodes x SMCRT_NODE_PARAMS.  top_node[t] is the root node of top-level SDF t+1 ("layer" t+1,
+   order matters: maxloc(ds, mask=ds<0), inttau2.f90:84,220);  optics per top-level SDF as `mono(mus,mua,hgg,n)`
+   (opticalProperties.f90:107-125; kappa/albedo/g2 are derived inside with the same rule). */
+int smcrt_set_scene(smcrt_ctx* ctx, int n_nodes, const int32_t* kind, const int32_t* first_child,
+                    const int32_t* n_child, const double* xform, const double* params, int n_top,
+                    const int32_t* top_node, const double* mus, const double* mua, const double* hgg,
+                    const double* n_ref);
+/* sdf%updateOptProp (sdf_base.f90:244-255), used by inverse_MCRT between runs. top_index is 1-based. */
+int smcrt_set_optprops(smcrt_ctx* ctx, int top_index, double mus, double mua, double hgg, double n_ref);
+
+/* packet = photon(name) + set_photon + dict keys (parse_source.f90:17-264).  p: SMCRT_SOURCE_PARAMS doubles. */
+int smcrt_set_source(smcrt_ctx* ctx, int kind, int subtype, const double* p);
+
+/* dects(:)  (parse_detectors.f90:17-141).  p = n x SMCRT_DET_PARAMS, nbins = the USER nbins (the stored
+   count is nbins+1, detectors.f90:133; cameras (nbins+1)^2).  Tallies are zeroed. */
+int smcrt_set_detectors(smcrt_ctx* ctx, int n, const int32_t* kind, const double* p, const int32_t* nbins);
+/* number of doubles smcrt_fetch writes to det_bins (Σ stored bins, detector order) */
+int64_t smcrt_det_bins_total(const smcrt_ctx* ctx);
+
+/* engine knobs without a reference counterpart.  eps0: absolute floor of the boundary tolerance
+   (reference eps = 1e-8, inttau2.f90:56); the engine uses max(eps0, eps_rel*|pos|_inf) because the
+   arithmetic is FP32.  <=0 keeps the default.  max_steps: per-packet sweep cap. */
+int smcrt_set_tolerances(smcrt_ctx* ctx, double eps0, double eps_rel, int64_t max_steps);
+
+/* ---- run: the photon loop of run_MCRT (kernelsMod.f90:1861-1888) ---------------------------- */
+/* Launches packets with global ids [id_offset, id_offset+nphotons); the Philox stream of a packet depends
+   only on (seed, global id), so a job split over ranks/GPUs is the same job.  tally_mode: OR of
+   smcrt_tally_mode.  survival_bias!=0 selects survivalBiasPropagation (kernelsMod.f90:1979-2067) with
+   THRESHOLD/CHANCE (constants.f90:28-30; pass <=0 for the reference values 0.01 / 0.1).
+   Tallies ACCUMULATE across calls, like the module arrays do across run_MCRT calls. Blocking. */
+int smcrt_run(smcrt_ctx* ctx, int64_t nphotons, uint64_t seed, int64_t id_offset, int tally_mode,
+              int survival_bias, double threshold, double chance);
+/* non-blocking variant + wait, so a host can overlap (used by the benchmark to time on the device) */
+int smcrt_run_async(smcrt_ctx* ctx, int64_t nphotons, uint64_t seed, int64_t id_offset, int tally_mode,
+                    int survival_bias, double threshold, double chance);
+int smcrt_wait(smcrt_ctx* ctx);
+/* device time of the last completed run in ms (CUDA events on the launch stream; max over this ctx's GPUs) */
+double smcrt_last_run_ms(const smcrt_ctx* ctx);
+/* kernels launched by this ctx since creation (the benchmark's gpu_launches claim) */
+int64_t smcrt_launch_count(const smcrt_ctx* ctx);
+
+/* ---- results -------------------------------------------------------------------------------- */
+/* Sums the tallies of all GPUs of this ctx (NCCL reduce to the first device when n_gpus>1; the intent of the
+   dead mpi_reduce block, kernelsMod.f90:2351-2357) and copies them out.  Grids: nxg*nyg*nzg floats, x fastest
+   (Fortran (nxg,nyg,nzg) order, setup.f90:180-183); any pointer may be NULL.  accumulate!=0: host += device
+   (the reference's `jmeanGLOBAL = jmean` after in-place accumulation), else overwrite. */
+int smcrt_fetch(smcrt_ctx* ctx, float* jmean, float* absorb, float* emission, double* det_bins,
+                smcrt_counters* counters, int accumulate);
+/* zarray + detector reset (setup.f90:192-205, kernelsMod.f90:2418-2439) */
+int smcrt_reset_tallies(smcrt_ctx* ctx);
+
+/* ---- multi-process (one rank per GPU) reduce, NCCL over NVLink ------------------------------ */
+/* rank 0 calls smcrt_comm_unique_id (128 bytes), the host broadcasts it (MPI / torch.distributed / file),
+   every rank calls smcrt_comm_init.  smcrt_comm_reduce then sums the tally grids, detector bins and
+   counters of all ranks onto rank `root` with ONE grouped ncclReduce per buffer. */
+int smcrt_comm_unique_id(char id_out[128]);
+int smcrt_comm_init(smcrt_ctx* ctx, int nranks, int rank, const char id[128]);
+int smcrt_comm_reduce(smcrt_ctx* ctx, int root);
+
+/* ---- deterministic-component probes (parity tests) ------------------------ */
+/* Evaluate top-level SDF `top_index` (1-based; 0 = all: out has n*n_top values, SDF fastest) at n points
+   (pos = n x 3 doubles) with the engine's FP32 device code.  normal (n x 3, may be NULL) is only written
+   for a single SDF (replaces calcNormal, sdf_base.f90:166-190). */
+int smcrt_probe_sdf(smcrt_ctx* ctx, int top_index, int64_t n, const double* pos, double* dist, double* normal);
+/* reflect_refract with a supplied uniform (surfaces.f90:14-127): in dir/nrm n x 3, n1,n2,xi n; out new dir,
+   R (Fresnel coefficient), rflag. */
+int smcrt_probe_fresnel(smcrt_ctx* ctx, int64_t n, const double* dir, const double* nrm, const double* n1,
+                        const double* n2, const double* xi, double* dir_out, double* refl_coeff, int32_t* rflag);
+/* photon%scatter with supplied uniforms (photon.f90:1045-1103): xi = n x 2 (cos-theta draw, phi draw). */
+int smcrt_probe_scatter(smcrt_ctx* ctx, int64_t n, const double* dir, const double* hgg, const double* xi,
+                        double* dir_out);
+/* emit with supplied uniforms (4 per packet) using the source set by smcrt_set_source; out pos/dir n x 3,
+   cell n x 3 (1-based voxel, -1 outside: grid.f90:51-78). */
+int smcrt_probe_emit(smcrt_ctx* ctx, int64_t n, const double* xi4, double* pos, double* dir, int32_t* cell);
+/* record_hit on one straight segment per entry against detector det_index (1-based), tallies untouched:
+   out hit flag and the bin index (1-based; cameras: idx + (idy-1)*nbinsX). */
+int smcrt_probe_detector(smcrt_ctx* ctx, int det_index, int64_t n, const double* start, const double* dir,
+                         const double* seg_len, int32_t* hit, int32_t* bin);
+/* Trace packets [id_offset, id_offset+n) exactly like smcrt_run (tallies ARE updated) and also return, per
+   packet: fate (0 absorbed, 1 left geometry/grid, 2 roulette, 3 lost), scatter count, final position.
+   Any out pointer may be NULL. */
+int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode,
+                        int survival_bias, int32_t* fate, int32_t* nscatt, double* final_pos,
+                        int32_t* n_events);
+/* The engine's Philox4x32-10 block for (seed, packet id, event index): 4 words. */
+int smcrt_probe_philox(uint64_t seed, uint64_t packet_id, uint32_t event, uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCRT_H */

@@ -1,0 +1,71 @@
+/*
+ * smcrt_host.h — C ABI of the host-side mirror of the reference's config / scene-setup / output layer.
+ *
+ * The reference's host is Fortran 2018 (src/parse/*.f90, src/setup.f90, src/setupGeometry.f90,
+ * src/writer.f90, src/kernelsMod.f90 setup/finalise/default_MCRT).  No Fortran toolchain exists in this
+ * image, so the same interface is provided in C++ above the engine's C ABI (include/smcrt.h): same TOML
+ * keys and defaults, same geom_name dispatch and scene contents (App. E), same output
+ * bytes (App. D / §8f N1).  It lives in the same shared object as the engine (libsmcrt_gpu.so).
+ */
+#ifndef SMCRT_HOST_H
+#define SMCRT_HOST_H
+
+#include <stdint.h>
+#include "smcrt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smcrt_config smcrt_config; /* opaque: `state` + `dict` + dects + flattened array(:) */
+
+/* parse_params (src/parse/parse.f90:20-72).  res_dir is where geometry side files live (the reference
+   hard-codes "res/": setupGeometry.f90:586-627); may be NULL (= directory of the toml file). */
+int smcrt_config_load(const char* toml_path, const char* res_dir, smcrt_config** out);
+int smcrt_config_loads(const char* toml_text, const char* res_dir, smcrt_config** out);
+void smcrt_config_free(smcrt_config* cfg);
+
+/* parsed values (state%..., src/sim_state.f90:10-58) */
+int smcrt_config_grid(const smcrt_config* cfg, int32_t n[3], double half_extent[3]);
+int64_t smcrt_config_nphotons(const smcrt_config* cfg);
+int64_t smcrt_config_iseed(const smcrt_config* cfg);
+const char* smcrt_config_geom_name(const smcrt_config* cfg);
+const char* smcrt_config_source_name(const smcrt_config* cfg);
+int smcrt_config_render_source(const smcrt_config* cfg);
+/* source block as smcrt_set_source wants it */
+int smcrt_config_source(const smcrt_config* cfg, int32_t* kind, int32_t* subtype, double p[SMCRT_SOURCE_PARAMS]);
+/* detectors in the reference's dects(:) order: circles, annuli, fibres, cameras (parse_detectors.f90:119-137) */
+int smcrt_config_n_detectors(const smcrt_config* cfg);
+int smcrt_config_detectors(const smcrt_config* cfg, int32_t* kind, double* p /* n x SMCRT_DET_PARAMS */, int32_t* nbins);
+const char* smcrt_config_detector_id(const smcrt_config* cfg, int i /*0-based, dects order*/);
+
+/* setup_simulation's geom_name dispatch (src/setup.f90:33-60) -> flattened array(:) */
+int smcrt_config_scene_sizes(const smcrt_config* cfg, int32_t* n_nodes, int32_t* n_top);
+int smcrt_config_scene(const smcrt_config* cfg, int32_t* kind, int32_t* first_child, int32_t* n_child, double* xform,
+                       double* params, int32_t* top_node, double* mus, double* mua, double* hgg, double* n_ref);
+
+/* push grid + scene + source + detectors into an engine context (what setup() leaves in module state) */
+int smcrt_config_apply(const smcrt_config* cfg, smcrt_ctx* ctx);
+
+/* ---- output layer (src/writer.f90) ---------------------------------------------------------- */
+/* normalise_fluence (writer.f90:25-52): array *= nx*ny*nz / nphotons, evaluated like the reference */
+int smcrt_normalise_fluence(float* array, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, int64_t nphotons);
+/* write_3d_r4_nrrd (writer.f90:382-424, header :304-337).  meta (may be NULL) is dumped between header and
+   data like toml_dump(dict). */
+int smcrt_write_nrrd_f32(const char* path, const float* data, int nxg, int nyg, int nzg, const char* meta);
+/* write_detected_photons (writer.f90:55-134): out_dir/detector_<i>.dat for every non-camera detector */
+int smcrt_write_detectors(const smcrt_config* cfg, const double* det_bins, const char* out_dir);
+/* metadata text written into NRRD headers (the `dict` toml dump, kernelsMod.f90:2378-2382) */
+const char* smcrt_config_metadata(const smcrt_config* cfg);
+
+/* default_MCRT (src/kernelsMod.f90:29-83): setup -> run_MCRT -> finalise.  Writes out_dir/{jmean,absorb,emission,
+   detectors}/... with the reference's names.  tally_mode<0: default build semantics (absorb [+emission when
+   render_source]); nphotons<=0: the toml's.  photons_per_s (may be NULL) receives what the reference prints
+   (kernelsMod.f90:1897). */
+int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* out_dir, int n_gpus, int tally_mode,
+                       int survival_bias, int64_t nphotons, double* photons_per_s, smcrt_counters* counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,262 @@
+// device_scene.cuh — flattened struct-of-records scene as the sm_100a kernel sees it, and the SDF evaluators.
+//
+// Layout in HBM / shared memory: one blob per context, copied once per kernel into shared
+// memory by every CTA (a few KB; all lanes of a warp read the same primitive in the same iteration, so the
+// reads are shared-memory broadcasts):
+//     DevPrim  prims[n_prims]      96 B each: kind, transform class, 3x4 affine (row-vector convention of
+//                                  src/vector_class.f90:292-304 folded into columns), 8 parameters
+//     DevTop   tops[n_top]         32 B each: how to evaluate top-level SDF i + its optical properties
+//     DevInstr prog[n_instr]       16 B each: postfix program for `model`/modifier trees
+//     DevDet   dets[n_det]         96 B each
+// The evaluators are templated on the scalar so the same formulas run in FP32 (transport) and FP64
+// (4-tap surface normal with the reference's h = 1e-6, src/sdfs/sdf_base.f90:166-190).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace smcrt_dev {
+
+enum : int { XF_IDENTITY = 0, XF_TRANSLATE = 1, XF_AFFINE = 2 };
+
+template <typename T>
+struct PrimT {
+    int32_t kind;
+    int32_t xf;
+    T m[12];  // p'.x = m[0] x + m[1] y + m[2] z + m[3]; p'.y = m[4..7]; p'.z = m[8..11]
+    T p[8];
+    int32_t pad_[2];
+};
+using DevPrim = PrimT<float>;    // 96 B
+using DevPrimD = PrimT<double>;  // 176 B
+static_assert(sizeof(DevPrim) == 96, "DevPrim must be 96 bytes");
+
+struct DevTop {
+    int32_t mode;   // 0: single primitive `first`; 1: program prog[first .. first+count)
+    int32_t first;
+    int32_t count;
+    float kappa, albedo, hgg, n, mua;
+};
+static_assert(sizeof(DevTop) == 32, "DevTop must be 32 bytes");
+
+// postfix program (compiled from the node tree in smcrt_set_scene)
+enum : int {
+    I_PRIM = 1,        // a = prim index            push d = prim(P)
+    I_CSG = 2,         // a = model kind, f[0] = k   d2=pop, d1=pop, push op(d1,d2,k)
+    I_PUSH_REV = 3,    // f = o, cx, cy              (cz in the next word via `g`)  push P' (revolution)
+    I_PUSH_ELONG = 4,  // f = sx, sy, sz             push P' = max(|P|-s,0)
+    I_PUSH_TWIST = 5,  // f[0] = k
+    I_PUSH_BEND = 6,   // f[0] = k
+    I_POP_P = 7,
+    I_EXTRUDE = 8,     // f[0] = h                   d = pop; push extrude(d, P.z)
+    I_ONION = 9,       // f[0] = thickness
+    I_ELONG_ADD = 10   // f = sx, sy, sz             d += min(max(q),0), q = |P|-s
+};
+struct DevInstr {
+    int32_t op;
+    int32_t a;
+    float f[3];
+    float g;
+    int32_t pad_[2];
+};
+static_assert(sizeof(DevInstr) == 32, "DevInstr must be 32 bytes");
+struct DevInstrD {
+    int32_t op, a;
+    double f[3];
+    double g;
+};
+
+struct DevDet {
+    int32_t kind;
+    int32_t nbins;     // stored count (user + 1); cameras: per axis
+    int32_t offset;    // into the concatenated bin array
+    int32_t pad_;
+    float pos[3];      // circle/annulus/fibre: centre (fibre: already pos + dir*frontOffset); camera: p1
+    float dir[3];      // plane normal (camera: n = normalised e2 x e1)
+    float q[14];       // kind-specific, see engine.cu:pack_detector
+};
+static_assert(sizeof(DevDet) == 96, "DevDet must be 96 bytes");
+
+// -------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ T t_abs(T x);
+template <> __device__ __forceinline__ float t_abs<float>(float x) { return fabsf(x); }
+template <> __device__ __forceinline__ double t_abs<double>(double x) { return fabs(x); }
+template <typename T> __device__ __forceinline__ T t_min(T a, T b);
+template <> __device__ __forceinline__ float t_min<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double t_min<double>(double a, double b) { return fmin(a, b); }
+template <typename T> __device__ __forceinline__ T t_max(T a, T b);
+template <> __device__ __forceinline__ float t_max<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double t_max<double>(double a, double b) { return fmax(a, b); }
+template <typename T> __device__ __forceinline__ void t_sincos(T x, T* s, T* c);
+template <> __device__ __forceinline__ void t_sincos<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void t_sincos<double>(double x, double* s, double* c) { sincos(x, s, c); }
+template <typename T> __device__ __forceinline__ T t_clamp01(T v) { return t_min(t_max(v, T(0)), T(1)); }
+
+// One primitive, reference formulas of src/sdfs/sdfs.f90:494-735
+template <typename T>
+__device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
+    T px, py, pz;
+    if (P.xf == XF_IDENTITY) {
+        px = x; py = y; pz = z;
+    } else if (P.xf == XF_TRANSLATE) {
+        px = x + P.m[3]; py = y + P.m[7]; pz = z + P.m[11];
+    } else {
+        px = P.m[0] * x + P.m[1] * y + P.m[2] * z + P.m[3];
+        py = P.m[4] * x + P.m[5] * y + P.m[6] * z + P.m[7];
+        pz = P.m[8] * x + P.m[9] * y + P.m[10] * z + P.m[11];
+    }
+    const T* q = P.p;
+    switch (P.kind) {
+        case 1:  // sphere :494-508
+            return t_sqrt(px * px + py * py + pz * pz) - q[0];
+        case 2: {  // box :510-525
+            T dx = t_abs(px) - q[0], dy = t_abs(py) - q[1], dz = t_abs(pz) - q[2];
+            T ox = t_max(dx, T(0)), oy = t_max(dy, T(0)), oz = t_max(dz, T(0));
+            return t_sqrt(ox * ox + oy * oy + oz * oz) + t_min(t_max(dx, t_max(dy, dz)), T(0));
+        }
+        case 3: {  // torus :527-542 (axis = y)
+            T tx = t_sqrt(px * px + pz * pz) - q[0];
+            return t_sqrt(tx * tx + py * py) - q[1];
+        }
+        case 4: {  // capped cylinder a->b :544-581
+            T bax = q[3] - q[0], bay = q[4] - q[1], baz = q[5] - q[2];
+            T pax = px - q[0], pay = py - q[1], paz = pz - q[2];
+            T baba = bax * bax + bay * bay + baz * baz;
+            T paba = pax * bax + pay * bay + paz * baz;
+            T vx = pax * baba - bax * paba, vy = pay * baba - bay * paba, vz = paz * baba - baz * paba;
+            T xx = t_sqrt(vx * vx + vy * vy + vz * vz) - q[6] * baba;
+            T yy = t_abs(paba - baba * T(0.5)) - baba * T(0.5);
+            T x2 = xx * xx, y2 = (yy * yy) * baba, d;
+            if (t_max(xx, yy) < T(0)) d = -t_min(x2, y2);
+            else d = (xx > T(0) ? x2 : T(0)) + (yy > T(0) ? y2 : T(0));
+            T r = t_sqrt(t_abs(d)) / baba;
+            return d >= T(0) ? r : -r;
+        }
+        case 5: {  // triprism :583-597
+            T ax = t_abs(px), az = t_abs(pz);
+            return t_max(az - q[1], t_max(ax * T(0.866025) + py * T(0.5), -py) - q[0] * T(0.5));
+        }
+        case 6:    // segment :599-626 (radius 0.1)
+        case 7: {  // capsule :628-648
+            T pax = px - q[0], pay = py - q[1], paz = pz - q[2];
+            T bax = q[3] - q[0], bay = q[4] - q[1], baz = q[5] - q[2];
+            T h = t_clamp01((pax * bax + pay * bay + paz * baz) / (bax * bax + bay * bay + baz * baz));
+            T ex = pax - bax * h, ey = pay - bay * h, ez = paz - baz * h;
+            return t_sqrt(ex * ex + ey * ey + ez * ez) - (P.kind == 6 ? T(0.1) : q[6]);
+        }
+        case 8: {  // capped cone :650-686
+            T ra = q[6], rb = q[7], rba = rb - ra;
+            T bax = q[3] - q[0], bay = q[4] - q[1], baz = q[5] - q[2];
+            T pax = px - q[0], pay = py - q[1], paz = pz - q[2];
+            T baba = bax * bax + bay * bay + baz * baz;
+            T papa = pax * pax + pay * pay + paz * paz;
+            T paba = (pax * bax + pay * bay + paz * baz) / baba;
+            T xx = t_sqrt(papa - baba * paba * paba);
+            T cax = t_max(T(0), xx - (paba < T(0.5) ? ra : rb));
+            T cay = t_abs(paba - T(0.5)) - T(0.5);
+            T k = rba * rba + baba;
+            T f = t_clamp01((rba * (xx - ra) + paba * baba) / k);
+            T cbx = xx - ra - f * rba, cby = paba - f;
+            T s = (cbx < T(0) && cay < T(0)) ? T(-1) : T(1);
+            return s * t_sqrt(t_min(cax * cax + baba * cay * cay, cbx * cbx + baba * cby * cby));
+        }
+        case 9: {  // egg :688-718
+            T r1 = q[0], r2 = q[1], h = q[2];
+            T ax = t_abs(px);
+            T r = r1 - r2, hin = h + r;
+            T l = (hin * hin - r * r) / (T(2) * r);
+            if (py <= T(0)) return t_sqrt(ax * ax + py * py + pz * pz) - r1;
+            if ((py - hin) * l > ax * hin) {
+                T yy = py - hin;
+                return t_sqrt(ax * ax + yy * yy + pz * pz) - ((r1 + l) - t_sqrt(hin * hin + l * l));
+            }
+            T xx = ax + l;
+            return t_sqrt(xx * xx + py * py + pz * pz) - (r1 + l);
+        }
+        case 10:  // plane :720-735
+            return px * q[0] + py * q[1] + pz * q[2];
+    }
+    return T(1e30);
+}
+
+template <typename T>
+__device__ __forceinline__ T csg_op(int kind, T d1, T d2, T k) {  // src/sdfs/sdfModifiers.f90:428-491
+    switch (kind) {
+        case 20: return t_min(d1, d2);
+        case 21: {
+            T h = t_max(k - t_abs(d1 - d2), T(0)) / k;
+            return t_min(d1, d2) - h * h * h * k * T(1.0 / 6.0);
+        }
+        case 22: return t_max(-d1, d2);
+        default: return t_max(d1, d2);
+    }
+}
+
+// program interpreter for `model` / modifier trees (sdf_base.f90:146-161, sdfModifiers.f90:286-426).
+// Stacks are tiny (depth checked at compile time on the host: <= 4 distances, <= 3 saved points).
+template <typename T, typename PRIM, typename INSTR>
+__device__ __noinline__ T eval_program(const PRIM* prims, const INSTR* prog, int first, int count, T x, T y, T z) {
+    T ds[4];
+    T ps[3][3];
+    int nd = 0, np = 0;
+    for (int ip = first; ip < first + count; ++ip) {
+        const INSTR I = prog[ip];
+        switch (I.op) {
+            case I_PRIM: ds[nd++] = eval_prim<T>(prims[I.a], x, y, z); break;
+            case I_CSG: {
+                T d2 = ds[--nd], d1 = ds[--nd];
+                ds[nd++] = csg_op<T>(I.a, d1, d2, (T)I.f[0]);
+                break;
+            }
+            case I_PUSH_REV: {
+                ps[np][0] = x; ps[np][1] = y; ps[np][2] = z; ++np;
+                T ix = x - (T)I.f[1], iy = y - (T)I.f[2], iz = z - (T)I.g;
+                x = t_sqrt(ix * ix + iz * iz) - (T)I.f[0];
+                y = iy;
+                z = T(0);
+                break;
+            }
+            case I_PUSH_ELONG: {
+                ps[np][0] = x; ps[np][1] = y; ps[np][2] = z; ++np;
+                x = t_max(t_abs(x) - (T)I.f[0], T(0));
+                y = t_max(t_abs(y) - (T)I.f[1], T(0));
+                z = t_max(t_abs(z) - (T)I.f[2], T(0));
+                break;
+            }
+            case I_PUSH_TWIST: {
+                ps[np][0] = x; ps[np][1] = y; ps[np][2] = z; ++np;
+                T s, c;
+                t_sincos<T>((T)I.f[0] * z, &s, &c);
+                T nx = c * x - s * y, ny = s * x + c * y;
+                x = nx; y = ny;
+                break;
+            }
+            case I_PUSH_BEND: {
+                ps[np][0] = x; ps[np][1] = y; ps[np][2] = z; ++np;
+                T s, c;
+                t_sincos<T>((T)I.f[0] * x, &s, &c);
+                T nx = c * x - s * y, ny = s * x + c * y;
+                x = nx; y = ny;
+                break;
+            }
+            case I_POP_P: --np; x = ps[np][0]; y = ps[np][1]; z = ps[np][2]; break;
+            case I_EXTRUDE: {
+                T wx = ds[nd - 1], wy = t_abs(z) - (T)I.f[0];
+                T ox = t_max(wx, T(0)), oy = t_max(wy, T(0));
+                ds[nd - 1] = t_min(t_max(wx, wy), T(0)) + t_sqrt(ox * ox + oy * oy);
+                break;
+            }
+            case I_ONION: ds[nd - 1] = t_abs(ds[nd - 1]) - (T)I.f[0]; break;
+            case I_ELONG_ADD: {
+                T qx = t_abs(x) - (T)I.f[0], qy = t_abs(y) - (T)I.f[1], qz = t_abs(z) - (T)I.f[2];
+                ds[nd - 1] += t_min(t_max(qx, t_max(qy, qz)), T(0));
+                break;
+            }
+        }
+    }
+    return ds[0];
+}
+
+}  // namespace smcrt_dev

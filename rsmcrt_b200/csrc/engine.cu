@@ -1,0 +1,959 @@
+// engine.cu — host half of libsmcrt_gpu.so: the C ABI of include/smcrt.h on top of kernels.cuh.
+// One smcrt_ctx drives 1..N GPUs from one host thread (the reference's OpenMP threads become GPUs,
+// src/kernelsMod.f90:1833-1836); photon ids are split into contiguous ranges per GPU and every GPU owns private
+// tallies that are summed with NCCL at fetch time (the intent of the dead mpi_reduce block, :2351-2357).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smcrt.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace smcrt_dev;
+using smcrt_math::M44;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int set_err(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+extern "C" void smcrt_set_error_(const char* msg) { g_err = msg ? msg : ""; }
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ NCCL (lazy)
+// Bound at run time so that single-GPU use never needs NCCL and the library has no link-time dependency on a
+// particular libnccl build (torch ships its own libnccl.so.2; the system has another).
+namespace nccl {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclUint64 = 5, ncclSum = 0 };
+static void* lib = nullptr;
+static ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+static ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+static ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+static ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+static ncclResult_t (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+static ncclResult_t (*GroupStart)() = nullptr;
+static ncclResult_t (*GroupEnd)() = nullptr;
+static const char* (*GetErrorString)(ncclResult_t) = nullptr;
+static int load() {
+    if (lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return set_err("NCCL is required for multi-GPU reduction but libnccl.so.2 could not be loaded: %s", dlerror());
+#define SYM(var, name)                                                  \
+    *(void**)(&var) = dlsym(lib, name);                                 \
+    if (!var) return set_err("libnccl lacks symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Reduce, "ncclReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+}  // namespace nccl
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        int r_ = (call);                                                                          \
+        if (r_ != 0) return set_err("%s failed: %s", #call, nccl::GetErrorString ? nccl::GetErrorString(r_) : "?"); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ context
+struct DeviceState {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned char* blob = nullptr;
+    DevPrimD* primsD = nullptr;
+    DevInstrD* progD = nullptr;
+    float *jmean = nullptr, *absorb = nullptr, *emission = nullptr;
+    unsigned long long* det_bins = nullptr;
+    unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last)
+    nccl::ncclComm_t comm = nullptr;
+    int sm_count = 148;
+    bool ran = false;
+};
+
+struct HostDet {
+    int kind, nbins_user, stored;
+    long long count, offset;
+};
+
+struct smcrt_ctx {
+    std::vector<DeviceState> devs;
+    // grid
+    int nxg = 0, nyg = 0, nzg = 0;
+    double gmax[3] = {1, 1, 1};
+    // scene (host copies)
+    std::vector<DevPrim> prims;
+    std::vector<DevPrimD> primsD;
+    std::vector<DevTop> tops;
+    std::vector<DevInstr> prog;
+    std::vector<DevInstrD> progD;
+    std::vector<DevDet> dets;
+    std::vector<HostDet> hdets;
+    long long det_total = 0;
+    std::vector<double> opt_mus, opt_mua, opt_hgg, opt_n;
+    bool scene_dirty = true;
+    int off_tops = 0, off_prog = 0, off_dets = 0, blob_bytes = 0;
+    // source
+    int src_kind = SMCRT_SRC_POINT, src_sub = 0, src_alt = 0;
+    float sp[24] = {0};
+    float Tpos[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float Tdir[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // knobs
+    double eps0 = 1e-8, eps_rel = 4.76837158203125e-07 /* 2^-21 = 4 ulp(1.0f) */;
+    long long max_steps = 2000000;
+    // run state
+    bool comm_all = false;    // in-process communicator over devs
+    bool comm_rank = false;   // one-rank-per-process communicator (devs.size()==1)
+    int nranks = 1, rank = 0;
+    double last_ms = 0;
+    long long launches = 0;
+    bool pending = false;
+};
+
+static int n_voxels(const smcrt_ctx* c, size_t* out) {
+    *out = (size_t)c->nxg * c->nyg * c->nzg;
+    return 0;
+}
+
+extern "C" const char* smcrt_last_error(void) { return g_err.c_str(); }
+extern "C" const char* smcrt_version(void) { return "smcrt-b200 0.1 (sm_100a)"; }
+
+extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) {
+    if (!out) return set_err("smcrt_create: out is null");
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail == 0)
+        return set_err("smcrt_create: no CUDA device available (%s); this engine has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (n_gpus == 0) n_gpus = avail;
+    if (n_gpus < 0 || n_gpus > avail) return set_err("smcrt_create: %d GPUs requested, %d visible", n_gpus, avail);
+    smcrt_ctx* c = new smcrt_ctx();
+    c->devs.resize(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) {
+        DeviceState& D = c->devs[g];
+        D.dev = device_ids ? device_ids[g] : g;
+        if (D.dev < 0 || D.dev >= avail) {
+            delete c;
+            return set_err("smcrt_create: device id %d out of range", D.dev);
+        }
+        cudaDeviceProp prop;
+        if (cudaSetDevice(D.dev) != cudaSuccess || cudaGetDeviceProperties(&prop, D.dev) != cudaSuccess) {
+            delete c;
+            return set_err("smcrt_create: cannot select device %d", D.dev);
+        }
+        if (prop.major < 10) {
+            delete c;
+            return set_err("smcrt_create: device %d is sm_%d%d; this library contains sm_100a code only", D.dev, prop.major, prop.minor);
+        }
+        D.sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&D.ev0) != cudaSuccess || cudaEventCreate(&D.ev1) != cudaSuccess ||
+            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess ||
+            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess) {
+            delete c;
+            return set_err("smcrt_create: resource allocation failed on device %d: %s", D.dev, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    *out = c;
+    return 0;
+}
+
+static void free_grids(DeviceState& D) {
+    cudaSetDevice(D.dev);
+    cudaFree(D.jmean); cudaFree(D.absorb); cudaFree(D.emission);
+    D.jmean = D.absorb = D.emission = nullptr;
+}
+
+extern "C" void smcrt_destroy(smcrt_ctx* c) {
+    if (!c) return;
+    for (DeviceState& D : c->devs) {
+        cudaSetDevice(D.dev);
+        if (D.stream) cudaStreamSynchronize(D.stream);
+        if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
+        free_grids(D);
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters);
+        if (D.ev0) cudaEventDestroy(D.ev0);
+        if (D.ev1) cudaEventDestroy(D.ev1);
+        if (D.stream) cudaStreamDestroy(D.stream);
+    }
+    delete c;
+}
+
+extern "C" int smcrt_set_grid(smcrt_ctx* c, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax) {
+    if (!c) return set_err("null ctx");
+    if (nxg < 1 || nyg < 1 || nzg < 1 || !(xmax > 0) || !(ymax > 0) || !(zmax > 0)) return set_err("smcrt_set_grid: invalid grid");
+    c->nxg = nxg; c->nyg = nyg; c->nzg = nzg;
+    c->gmax[0] = xmax; c->gmax[1] = ymax; c->gmax[2] = zmax;
+    const size_t bytes = (size_t)nxg * nyg * nzg * sizeof(float);
+    for (DeviceState& D : c->devs) {
+        free_grids(D);
+        CU(cudaSetDevice(D.dev));
+        CU(cudaMalloc(&D.jmean, bytes));
+        CU(cudaMalloc(&D.absorb, bytes));
+        CU(cudaMalloc(&D.emission, bytes));
+        CU(cudaMemsetAsync(D.jmean, 0, bytes, D.stream));
+        CU(cudaMemsetAsync(D.absorb, 0, bytes, D.stream));
+        CU(cudaMemsetAsync(D.emission, 0, bytes, D.stream));
+        CU(cudaStreamSynchronize(D.stream));
+    }
+    return 0;
+}
+
+// ---- scene -----------------------------------------------------------------------------------------------
+static void fold_transform(const double* xf /*16, Fortran order*/, double m[12], int* cls) {
+    // p'_j = sum_i M(i,j) p_i + M(4,j)  (src/vector_class.f90:300-302), M(i,j) at xf[(j-1)*4 + (i-1)]
+    for (int j = 0; j < 3; ++j) {
+        m[4 * j + 0] = xf[j * 4 + 0];
+        m[4 * j + 1] = xf[j * 4 + 1];
+        m[4 * j + 2] = xf[j * 4 + 2];
+        m[4 * j + 3] = xf[j * 4 + 3];
+    }
+    const bool rot_id = m[0] == 1 && m[1] == 0 && m[2] == 0 && m[4] == 0 && m[5] == 1 && m[6] == 0 && m[8] == 0 && m[9] == 0 && m[10] == 1;
+    const bool no_t = m[3] == 0 && m[7] == 0 && m[11] == 0;
+    *cls = rot_id ? (no_t ? XF_IDENTITY : XF_TRANSLATE) : XF_AFFINE;
+}
+
+struct Compiler {
+    int n_nodes;
+    const int32_t *kind, *first_child, *n_child;
+    const double *xform, *params;
+    std::vector<DevPrim>* prims;
+    std::vector<DevPrimD>* primsD;
+    std::vector<DevInstr>* prog;
+    std::vector<DevInstrD>* progD;
+    int dmax = 0, pmax = 0;
+    std::string err;
+
+    int add_prim(int node) {
+        DevPrim a{};
+        DevPrimD b{};
+        double m[12];
+        int cls;
+        fold_transform(xform + 16 * (size_t)node, m, &cls);
+        a.kind = b.kind = kind[node];
+        a.xf = b.xf = cls;
+        for (int i = 0; i < 12; ++i) { a.m[i] = (float)m[i]; b.m[i] = m[i]; }
+        for (int i = 0; i < 8; ++i) { a.p[i] = (float)params[8 * (size_t)node + i]; b.p[i] = params[8 * (size_t)node + i]; }
+        prims->push_back(a);
+        primsD->push_back(b);
+        return (int)prims->size() - 1;
+    }
+    void emit(int op, int a, double f0 = 0, double f1 = 0, double f2 = 0, double g = 0) {
+        DevInstr i{};
+        i.op = op; i.a = a; i.f[0] = (float)f0; i.f[1] = (float)f1; i.f[2] = (float)f2; i.g = (float)g;
+        DevInstrD d{};
+        d.op = op; d.a = a; d.f[0] = f0; d.f[1] = f1; d.f[2] = f2; d.g = g;
+        prog->push_back(i);
+        progD->push_back(d);
+    }
+    // returns false on error; dd / pd: current stack depths
+    bool gen(int node, int dd, int pd, int depth) {
+        if (node < 0 || node >= n_nodes) { err = "node index out of range"; return false; }
+        if (depth > 32) { err = "scene tree too deep (cycle?)"; return false; }
+        const int k = kind[node];
+        const double* p = params + 8 * (size_t)node;
+        if (k >= SMCRT_SPHERE && k <= SMCRT_PLANE) {
+            emit(I_PRIM, add_prim(node));
+            dmax = std::max(dmax, dd + 1);
+            return true;
+        }
+        const int nc = n_child[node], fc = first_child[node];
+        if (k >= SMCRT_MODEL_UNION && k <= SMCRT_MODEL_INTERSECTION) {
+            if (nc < 1) { err = "model node without children"; return false; }
+            if (!gen(fc, dd, pd, depth + 1)) return false;
+            for (int i = 1; i < nc; ++i) {
+                if (!gen(fc + i, dd + 1, pd, depth + 1)) return false;
+                emit(I_CSG, k, p[0]);
+            }
+            return true;
+        }
+        if (nc != 1) { err = "modifier node must have exactly one child"; return false; }
+        switch (k) {
+            case SMCRT_MOD_EXTRUDE:
+                if (!gen(fc, dd, pd, depth + 1)) return false;
+                emit(I_EXTRUDE, 0, p[0]);
+                return true;
+            case SMCRT_MOD_ONION:
+                if (!gen(fc, dd, pd, depth + 1)) return false;
+                emit(I_ONION, 0, p[0]);
+                return true;
+            case SMCRT_MOD_REVOLUTION:
+                emit(I_PUSH_REV, 0, p[0], p[1], p[2], p[3]);
+                pmax = std::max(pmax, pd + 1);
+                if (!gen(fc, dd, pd + 1, depth + 1)) return false;
+                emit(I_POP_P, 0);
+                return true;
+            case SMCRT_MOD_TWIST:
+            case SMCRT_MOD_BEND:
+                emit(k == SMCRT_MOD_TWIST ? I_PUSH_TWIST : I_PUSH_BEND, 0, p[0]);
+                pmax = std::max(pmax, pd + 1);
+                if (!gen(fc, dd, pd + 1, depth + 1)) return false;
+                emit(I_POP_P, 0);
+                return true;
+            case SMCRT_MOD_ELONGATE:
+                emit(I_PUSH_ELONG, 0, p[0], p[1], p[2]);
+                pmax = std::max(pmax, pd + 1);
+                if (!gen(fc, dd, pd + 1, depth + 1)) return false;
+                emit(I_POP_P, 0);
+                emit(I_ELONG_ADD, 0, p[0], p[1], p[2]);
+                return true;
+        }
+        err = "unsupported node kind " + std::to_string(k);
+        return false;
+    }
+};
+
+static void set_optics(DevTop& T, double mus, double mua, double hgg, double n) {
+    // mono(), src/opticalProps/opticalProperties.f90:107-125
+    const double kappa = mus + mua;
+    const double albedo = (mua < 1e-9) ? 1.0 : mus / kappa;
+    T.kappa = (float)kappa; T.albedo = (float)albedo; T.hgg = (float)hgg; T.n = (float)n; T.mua = (float)mua;
+}
+
+extern "C" int smcrt_set_scene(smcrt_ctx* c, int n_nodes, const int32_t* kind, const int32_t* first_child, const int32_t* n_child,
+                               const double* xform, const double* params, int n_top, const int32_t* top_node, const double* mus,
+                               const double* mua, const double* hgg, const double* n_ref) {
+    if (!c) return set_err("null ctx");
+    if (n_nodes < 1 || n_top < 1 || !kind || !xform || !params || !top_node || !mus || !mua || !hgg || !n_ref)
+        return set_err("smcrt_set_scene: invalid arguments");
+    std::vector<int32_t> zeros(n_nodes, 0);
+    if (!first_child) first_child = zeros.data();
+    if (!n_child) n_child = zeros.data();
+    std::vector<DevPrim> prims;
+    std::vector<DevPrimD> primsD;
+    std::vector<DevInstr> prog;
+    std::vector<DevInstrD> progD;
+    std::vector<DevTop> tops(n_top);
+    Compiler comp{n_nodes, kind, first_child, n_child, xform, params, &prims, &primsD, &prog, &progD};
+    for (int t = 0; t < n_top; ++t) {
+        const int node = top_node[t];
+        if (node < 0 || node >= n_nodes) return set_err("smcrt_set_scene: top_node[%d]=%d out of range", t, node);
+        DevTop& T = tops[t];
+        const int k = kind[node];
+        if (k >= SMCRT_SPHERE && k <= SMCRT_PLANE) {
+            T.mode = 0;
+            T.first = comp.add_prim(node);
+            T.count = 1;
+        } else {
+            T.mode = 1;
+            T.first = (int)prog.size();
+            comp.dmax = comp.pmax = 0;
+            if (!comp.gen(node, 0, 0, 0)) return set_err("smcrt_set_scene: top-level SDF %d: %s", t + 1, comp.err.c_str());
+            if (comp.dmax > 4 || comp.pmax > 3)
+                return set_err("smcrt_set_scene: top-level SDF %d needs stack depth (%d distances, %d points) beyond the engine's (4,3)",
+                               t + 1, comp.dmax, comp.pmax);
+            T.count = (int)prog.size() - T.first;
+        }
+        set_optics(T, mus[t], mua[t], hgg[t], n_ref[t]);
+    }
+    c->prims.swap(prims); c->primsD.swap(primsD); c->prog.swap(prog); c->progD.swap(progD); c->tops.swap(tops);
+    c->opt_mus.assign(mus, mus + n_top); c->opt_mua.assign(mua, mua + n_top);
+    c->opt_hgg.assign(hgg, hgg + n_top); c->opt_n.assign(n_ref, n_ref + n_top);
+    c->scene_dirty = true;
+    return 0;
+}
+
+extern "C" int smcrt_set_optprops(smcrt_ctx* c, int top_index, double mus, double mua, double hgg, double n_ref) {
+    if (!c) return set_err("null ctx");
+    if (top_index < 1 || top_index > (int)c->tops.size()) return set_err("smcrt_set_optprops: top_index %d out of range", top_index);
+    set_optics(c->tops[top_index - 1], mus, mua, hgg, n_ref);
+    c->opt_mus[top_index - 1] = mus; c->opt_mua[top_index - 1] = mua; c->opt_hgg[top_index - 1] = hgg; c->opt_n[top_index - 1] = n_ref;
+    c->scene_dirty = true;
+    return 0;
+}
+
+// ---- source ----------------------------------------------------------------------------------------------
+extern "C" int smcrt_set_source(smcrt_ctx* c, int kind, int subtype, const double* p) {
+    if (!c || !p) return set_err("smcrt_set_source: null argument");
+    if (kind < SMCRT_SRC_POINT || kind > SMCRT_SRC_ANNULUS) return set_err("No such source!");  // init_source, photon.f90:155
+    if ((kind == SMCRT_SRC_FOCUS || kind == SMCRT_SRC_ANNULUS) && (subtype < 1 || subtype > 3)) return set_err("No such beam type!");
+    c->src_kind = kind; c->src_sub = subtype; c->src_alt = 0;
+    for (int i = 0; i < 24; ++i) c->sp[i] = (float)p[i];
+    M44 Tp = smcrt_math::identity(), Td = smcrt_math::identity();
+    const double* o = p + SMCRT_SP_POS;
+    if (kind == SMCRT_SRC_CIRCULAR) {  // photon.f90:243-264
+        double a[3] = {1, 0, 0}, b[3] = {p[SMCRT_SP_DIR], p[SMCRT_SP_DIR + 1], p[SMCRT_SP_DIR + 2]};
+        smcrt_math::normalise(b);
+        if (std::fabs(a[0]) == std::fabs(b[0]) && std::fabs(a[1]) == std::fabs(b[1]) && std::fabs(a[2]) == std::fabs(b[2])) {
+            a[0] = 0; a[2] = 1;
+            c->src_alt = 1;
+        }
+        Tp = smcrt_math::matmul(smcrt_math::rotation_align(a, b), smcrt_math::invert_affine(smcrt_math::translate(o[0], o[1], o[2])));
+    } else if (kind == SMCRT_SRC_FOCUS || kind == SMCRT_SRC_ANNULUS) {  // photon.f90:440-478, :927-958
+        double a[3] = {0, 0, -1}, b[3] = {p[SMCRT_SP_ROT], p[SMCRT_SP_ROT + 1], p[SMCRT_SP_ROT + 2]};
+        smcrt_math::normalise(b);
+        const bool same = a[0] == b[0] && a[1] == b[1] && a[2] == b[2];
+        const bool absame = std::fabs(a[0]) == std::fabs(b[0]) && std::fabs(a[1]) == std::fabs(b[1]) && std::fabs(a[2]) == std::fabs(b[2]);
+        M44 t = smcrt_math::identity();
+        if (same) {
+        } else if (absame) t.a(3, 3) = -1.0;
+        else t = smcrt_math::rotation_align(a, b);
+        Td = t;  // dir = dir .dot. t
+        if (absame && !same) t.a(3, 3) = 1.0;
+        Tp = smcrt_math::matmul(t, smcrt_math::invert_affine(smcrt_math::translate(-o[0], -o[1], -o[2])));
+    }
+    for (int j = 0; j < 3; ++j) {
+        for (int i = 0; i < 3; ++i) {
+            c->Tpos[4 * j + i] = (float)Tp.a(i + 1, j + 1);
+            c->Tdir[3 * j + i] = (float)Td.a(i + 1, j + 1);
+        }
+        c->Tpos[4 * j + 3] = (float)Tp.a(4, j + 1);
+    }
+    return 0;
+}
+
+// ---- detectors -------------------------------------------------------------------------------------------
+extern "C" int smcrt_set_detectors(smcrt_ctx* c, int n, const int32_t* kind, const double* p, const int32_t* nbins) {
+    if (!c) return set_err("null ctx");
+    if (n < 0 || (n > 0 && (!kind || !p || !nbins))) return set_err("smcrt_set_detectors: invalid arguments");
+    std::vector<DevDet> dets(n);
+    std::vector<HostDet> hd(n);
+    long long off = 0;
+    for (int i = 0; i < n; ++i) {
+        const double* q = p + (size_t)SMCRT_DET_PARAMS * i;
+        DevDet& D = dets[i];
+        std::memset(&D, 0, sizeof D);
+        D.kind = kind[i];
+        const int nb = nbins[i];
+        if (nb < 0) return set_err("smcrt_set_detectors: negative nbins");
+        const int stored = nb + 1;  // "extra bin for data beyond end of array", detectors.f90:133
+        D.nbins = stored;
+        for (int a = 0; a < 3; ++a) { D.pos[a] = (float)q[a]; D.dir[a] = (float)q[3 + a]; }
+        long long count = stored;
+        switch (kind[i]) {
+            case SMCRT_DET_CIRCLE:
+                D.q[0] = (float)q[6];
+                D.q[1] = (float)(nb == 0 ? 1.0 : q[6] / nb);
+                break;
+            case SMCRT_DET_ANNULUS:
+                D.q[0] = (float)q[6]; D.q[1] = (float)q[7];
+                D.q[2] = (float)(nb == 0 ? 1.0 : (q[7] - q[6]) / nb);
+                break;
+            case SMCRT_DET_FIBRE:
+                for (int a = 0; a < 3; ++a) D.pos[a] = (float)(q[a] + q[3 + a] * q[10]);  // pos + dir*frontOffset
+                D.q[0] = (float)q[8];   // f1Aperture
+                D.q[1] = (float)q[6];   // focalLength1
+                D.q[2] = (float)q[7];   // focalLength2
+                D.q[3] = (float)q[12];  // frontToPinSep
+                D.q[4] = (float)q[14];  // pinAperture
+                D.q[5] = (float)q[13];  // pinToBackSep
+                D.q[6] = (float)q[9];   // f2Aperture
+                D.q[7] = (float)q[11];  // backOffset
+                D.q[8] = (float)q[15];  // acceptAngle
+                D.q[9] = (float)(q[16] / 2);
+                D.q[10] = (float)(nb == 0 ? 1.0 : q[16] / 2 / nb);
+                break;
+            case SMCRT_DET_CAMERA: {  // init_camera, detectors.f90:395-445
+                const double e1[3] = {q[3] - q[0], q[4] - q[1], q[5] - q[2]}, e2[3] = {q[6] - q[0], q[7] - q[1], q[8] - q[2]};
+                double nn[3] = {e2[1] * e1[2] - e2[2] * e1[1], -e2[0] * e1[2] + e2[2] * e1[0], e2[0] * e1[1] - e2[1] * e1[0]};
+                smcrt_math::normalise(nn);
+                const double w = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+                const double h = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+                for (int a = 0; a < 3; ++a) { D.dir[a] = (float)nn[a]; D.q[a] = (float)e1[a]; D.q[3 + a] = (float)e2[a]; }
+                D.q[6] = (float)w; D.q[7] = (float)h;
+                D.q[8] = (float)(nb == 0 ? 1.0 : q[9] / stored);
+                D.q[9] = D.q[8];
+                D.q[10] = (float)q[0]; D.q[11] = (float)q[1];
+                count = (long long)stored * stored;
+                break;
+            }
+            default: return set_err("Invalid detector type. Valid types are [circle, annulus, camera]");
+        }
+        D.offset = (int)off;
+        hd[i] = HostDet{kind[i], nb, stored, count, off};
+        off += count;
+        if (off > (1ll << 30)) return set_err("smcrt_set_detectors: too many detector bins");
+    }
+    c->dets.swap(dets); c->hdets.swap(hd); c->det_total = off;
+    c->scene_dirty = true;
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
+        cudaFree(D.det_bins);
+        D.det_bins = nullptr;
+        const size_t bytes = sizeof(unsigned long long) * (size_t)std::max<long long>(off, 1);
+        CU(cudaMalloc(&D.det_bins, bytes));
+        CU(cudaMemset(D.det_bins, 0, bytes));
+    }
+    return 0;
+}
+extern "C" int64_t smcrt_det_bins_total(const smcrt_ctx* c) { return c ? c->det_total : 0; }
+
+extern "C" int smcrt_set_tolerances(smcrt_ctx* c, double eps0, double eps_rel, int64_t max_steps) {
+    if (!c) return set_err("null ctx");
+    if (eps0 > 0) c->eps0 = eps0;
+    if (eps_rel > 0) c->eps_rel = eps_rel;
+    if (max_steps > 0) c->max_steps = max_steps;
+    return 0;
+}
+
+// ---- upload ----------------------------------------------------------------------------------------------
+static int align16(int v) { return (v + 15) & ~15; }
+static int upload_scene(smcrt_ctx* c) {
+    if (!c->scene_dirty) return 0;
+    if (c->tops.empty()) return set_err("no scene set (smcrt_set_scene)");
+    const int b_prims = align16((int)(c->prims.size() * sizeof(DevPrim)));
+    const int b_tops = align16((int)(c->tops.size() * sizeof(DevTop)));
+    const int b_prog = align16((int)(c->prog.size() * sizeof(DevInstr)));
+    const int b_dets = align16((int)(c->dets.size() * sizeof(DevDet)));
+    c->off_tops = b_prims; c->off_prog = b_prims + b_tops; c->off_dets = c->off_prog + b_prog;
+    c->blob_bytes = c->off_dets + b_dets;
+    std::vector<unsigned char> blob(c->blob_bytes, 0);
+    std::memcpy(blob.data(), c->prims.data(), c->prims.size() * sizeof(DevPrim));
+    std::memcpy(blob.data() + c->off_tops, c->tops.data(), c->tops.size() * sizeof(DevTop));
+    if (!c->prog.empty()) std::memcpy(blob.data() + c->off_prog, c->prog.data(), c->prog.size() * sizeof(DevInstr));
+    if (!c->dets.empty()) std::memcpy(blob.data() + c->off_dets, c->dets.data(), c->dets.size() * sizeof(DevDet));
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD);
+        D.blob = nullptr; D.primsD = nullptr; D.progD = nullptr;
+        CU(cudaMalloc(&D.blob, blob.size()));
+        CU(cudaMemcpy(D.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&D.primsD, std::max<size_t>(1, c->primsD.size()) * sizeof(DevPrimD)));
+        CU(cudaMemcpy(D.primsD, c->primsD.data(), c->primsD.size() * sizeof(DevPrimD), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&D.progD, std::max<size_t>(1, c->progD.size()) * sizeof(DevInstrD)));
+        if (!c->progD.empty()) CU(cudaMemcpy(D.progD, c->progD.data(), c->progD.size() * sizeof(DevInstrD), cudaMemcpyHostToDevice));
+    }
+    c->scene_dirty = false;
+    return 0;
+}
+
+static const int SMEM_BIN_CAP = 8192;  // 64 KB of CTA-private Q40.24 bins at most
+
+static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
+    std::memset(&P, 0, sizeof P);
+    P.blob = D.blob; P.blob_bytes = c->blob_bytes;
+    P.n_prims = (int)c->prims.size(); P.n_top = (int)c->tops.size(); P.n_instr = (int)c->prog.size(); P.n_det = (int)c->dets.size();
+    P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets;
+    P.primsD = D.primsD; P.progD = D.progD;
+    P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;
+    const int nn[3] = {c->nxg, c->nyg, c->nzg};
+    for (int a = 0; a < 3; ++a) {
+        P.gmax[a] = (float)c->gmax[a];
+        P.vox[a] = (float)(2.0 * c->gmax[a] / nn[a]);
+        P.inv_vox[a] = (float)(nn[a] / (2.0 * c->gmax[a]));
+    }
+    P.src_kind = c->src_kind; P.src_sub = c->src_sub; P.src_alt = c->src_alt;
+    std::memcpy(P.sp, c->sp, sizeof P.sp);
+    std::memcpy(P.Tpos, c->Tpos, sizeof P.Tpos);
+    std::memcpy(P.Tdir, c->Tdir, sizeof P.Tdir);
+    P.jmean = D.jmean; P.absorb = D.absorb; P.emission = D.emission;
+    P.det_bins = D.det_bins; P.det_total = (int)c->det_total;
+    P.det_in_smem = (c->det_total > 0 && c->det_total <= SMEM_BIN_CAP) ? 1 : 0;
+    P.counters = D.counters; P.next = D.counters + C_COUNT;
+    P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
+    P.max_steps = (int)std::min<long long>(c->max_steps, 2000000000ll);
+    return 0;
+}
+
+template <bool PL, bool HD>
+static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
+    auto kern = trace_persistent<PL, HD>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_bytes));
+    if (per_sm < 1) return set_err("scene does not fit in shared memory (%d bytes per CTA)", smem_bytes);
+    // persistent grid: every SM full, no more; never more threads than packets
+    long long blocks = (long long)D.sm_count * per_sm;
+    const long long need = (P.nphotons + 255) / 256;
+    if (blocks > need) blocks = std::max<long long>(need, 1);
+    kern<<<(unsigned)blocks, 256, smem_bytes, D.stream>>>(P);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
+                         int survival, double threshold, double chance, int* out_fate, int* out_nscatt, int* out_events,
+                         float* out_pos) {
+    KParams P;
+    fill_params(c, D, P);
+    P.nphotons = nphotons; P.id_offset = (unsigned long long)id_offset;
+    P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+    P.tally_mode = tally_mode; P.survival = survival ? 1 : 0;
+    P.threshold = (float)(threshold > 0 ? threshold : 0.01);  // THRESHOLD, src/constants.f90:28
+    P.chance = (float)(chance > 0 ? chance : 0.1);            // CHANCE, src/constants.f90:30
+    P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos;
+    CU(cudaSetDevice(D.dev));
+    CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
+    const int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
+    CU(cudaEventRecord(D.ev0, D.stream));
+    const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
+    int rc;
+    if (pl) rc = hd ? launch_trace<true, true>(P, D, smem) : launch_trace<true, false>(P, D, smem);
+    else rc = hd ? launch_trace<false, true>(P, D, smem) : launch_trace<false, false>(P, D, smem);
+    if (rc) return rc;
+    CU(cudaEventRecord(D.ev1, D.stream));
+    D.ran = true;
+    c->launches += 1;
+    return 0;
+}
+
+static int check_ready(smcrt_ctx* c) {
+    if (!c) return set_err("null ctx");
+    if (c->nxg == 0) return set_err("no grid set (smcrt_set_grid)");
+    if (c->devs.empty() || !c->devs[0].det_bins) {
+        int rc = smcrt_set_detectors(c, 0, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    return upload_scene(c);
+}
+
+extern "C" int smcrt_run_async(smcrt_ctx* c, int64_t nphotons, uint64_t seed, int64_t id_offset, int tally_mode, int survival_bias,
+                               double threshold, double chance) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (nphotons < 0) return set_err("smcrt_run: negative nphotons");
+    if (c->pending) return set_err("smcrt_run_async: previous run not waited for");
+    const int G = (int)c->devs.size();
+    for (int g = 0; g < G; ++g) {
+        // contiguous id ranges per GPU: [g*N/G, (g+1)*N/G)
+        const long long lo = (long long)((__int128)nphotons * g / G), hi = (long long)((__int128)nphotons * (g + 1) / G);
+        c->devs[g].ran = false;
+        if (hi > lo) {
+            rc = run_on_device(c, c->devs[g], hi - lo, seed, id_offset + lo, tally_mode, survival_bias, threshold, chance, nullptr, nullptr,
+                               nullptr, nullptr);
+            if (rc) return rc;
+        }
+    }
+    c->pending = true;
+    return 0;
+}
+extern "C" int smcrt_wait(smcrt_ctx* c) {
+    if (!c) return set_err("null ctx");
+    double ms = 0;
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaStreamSynchronize(D.stream));
+        if (D.ran) {
+            float t = 0;
+            CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
+            ms = std::max(ms, (double)t);
+        }
+    }
+    if (c->pending) c->last_ms = ms;
+    c->pending = false;
+    return 0;
+}
+extern "C" int smcrt_run(smcrt_ctx* c, int64_t nphotons, uint64_t seed, int64_t id_offset, int tally_mode, int survival_bias,
+                         double threshold, double chance) {
+    int rc = smcrt_run_async(c, nphotons, seed, id_offset, tally_mode, survival_bias, threshold, chance);
+    if (rc) return rc;
+    return smcrt_wait(c);
+}
+extern "C" double smcrt_last_run_ms(const smcrt_ctx* c) { return c ? c->last_ms : 0.0; }
+extern "C" int64_t smcrt_launch_count(const smcrt_ctx* c) { return c ? c->launches : 0; }
+
+// ---- reduce + fetch --------------------------------------------------------------------------------------
+static int reduce_buffers(smcrt_ctx* c, int root_rank_or_dev) {
+    // one grouped ncclReduce per tally buffer; root receives in place
+    size_t nv;
+    n_voxels(c, &nv);
+    NC(nccl::GroupStart());
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceState& D = c->devs[g];
+        CU(cudaSetDevice(D.dev));
+        NC(nccl::Reduce(D.jmean, D.jmean, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        NC(nccl::Reduce(D.absorb, D.absorb, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        NC(nccl::Reduce(D.emission, D.emission, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        NC(nccl::Reduce(D.det_bins, D.det_bins, (size_t)std::max<long long>(c->det_total, 1), nccl::ncclUint64, nccl::ncclSum,
+                        root_rank_or_dev, D.comm, D.stream));
+        NC(nccl::Reduce(D.counters, D.counters, (size_t)C_COUNT, nccl::ncclUint64, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+    }
+    NC(nccl::GroupEnd());
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaStreamSynchronize(D.stream));
+    }
+    return 0;
+}
+static int zero_device_tallies(smcrt_ctx* c, DeviceState& D) {
+    size_t nv;
+    n_voxels(c, &nv);
+    CU(cudaSetDevice(D.dev));
+    CU(cudaMemsetAsync(D.jmean, 0, nv * 4, D.stream));
+    CU(cudaMemsetAsync(D.absorb, 0, nv * 4, D.stream));
+    CU(cudaMemsetAsync(D.emission, 0, nv * 4, D.stream));
+    CU(cudaMemsetAsync(D.det_bins, 0, sizeof(unsigned long long) * (size_t)std::max<long long>(c->det_total, 1), D.stream));
+    CU(cudaMemsetAsync(D.counters, 0, sizeof(unsigned long long) * C_COUNT, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    return 0;
+}
+
+extern "C" int smcrt_comm_unique_id(char id_out[128]) {
+    if (nccl::load()) return -1;
+    nccl::ncclUniqueId id;
+    NC(nccl::GetUniqueId(&id));
+    std::memcpy(id_out, id.internal, 128);
+    return 0;
+}
+extern "C" int smcrt_comm_init(smcrt_ctx* c, int nranks, int rank, const char id[128]) {
+    if (!c) return set_err("null ctx");
+    if (c->devs.size() != 1) return set_err("smcrt_comm_init: rank mode needs a context with exactly one GPU");
+    if (nccl::load()) return -1;
+    nccl::ncclUniqueId uid;
+    std::memcpy(uid.internal, id, 128);
+    CU(cudaSetDevice(c->devs[0].dev));
+    NC(nccl::CommInitRank(&c->devs[0].comm, nranks, uid, rank));
+    c->comm_rank = true; c->nranks = nranks; c->rank = rank;
+    return 0;
+}
+extern "C" int smcrt_comm_reduce(smcrt_ctx* c, int root) {
+    if (!c) return set_err("null ctx");
+    if (!c->comm_rank) return set_err("smcrt_comm_reduce: smcrt_comm_init was not called");
+    int rc = check_ready(c);
+    if (rc) return rc;
+    rc = reduce_buffers(c, root);
+    if (rc) return rc;
+    // non-root ranks have handed their tallies over: clear them so a later accumulate does not double count
+    if (c->rank != root) return zero_device_tallies(c, c->devs[0]);
+    return 0;
+}
+
+extern "C" int smcrt_fetch(smcrt_ctx* c, float* jmean, float* absorb, float* emission, double* det_bins, smcrt_counters* counters,
+                           int accumulate) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (c->pending && (rc = smcrt_wait(c))) return rc;
+    const int G = (int)c->devs.size();
+    if (G > 1) {
+        if (!c->comm_all) {
+            if (nccl::load()) return -1;
+            std::vector<nccl::ncclComm_t> comms(G);
+            std::vector<int> ids(G);
+            for (int g = 0; g < G; ++g) ids[g] = c->devs[g].dev;
+            NC(nccl::CommInitAll(comms.data(), G, ids.data()));
+            for (int g = 0; g < G; ++g) c->devs[g].comm = comms[g];
+            c->comm_all = true;
+        }
+        if ((rc = reduce_buffers(c, 0))) return rc;
+        for (int g = 1; g < G; ++g)
+            if ((rc = zero_device_tallies(c, c->devs[g]))) return rc;
+    }
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    size_t nv;
+    n_voxels(c, &nv);
+    std::vector<float> tmp;
+    auto pull = [&](float* host, const float* dev) -> int {
+        if (!host) return 0;
+        if (!accumulate) {
+            CU(cudaMemcpy(host, dev, nv * 4, cudaMemcpyDeviceToHost));
+        } else {
+            tmp.resize(nv);
+            CU(cudaMemcpy(tmp.data(), dev, nv * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nv; ++i) host[i] += tmp[i];
+        }
+        return 0;
+    };
+    if ((rc = pull(jmean, D.jmean)) || (rc = pull(absorb, D.absorb)) || (rc = pull(emission, D.emission))) return rc;
+    if (det_bins && c->det_total > 0) {
+        std::vector<unsigned long long> raw((size_t)c->det_total);
+        CU(cudaMemcpy(raw.data(), D.det_bins, raw.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < raw.size(); ++i) {
+            const double v = (double)raw[i] / 16777216.0;
+            det_bins[i] = accumulate ? det_bins[i] + v : v;
+        }
+    }
+    if (counters) {
+        unsigned long long raw[C_COUNT];
+        CU(cudaMemcpy(raw, D.counters, sizeof raw, cudaMemcpyDeviceToHost));
+        smcrt_counters k{};
+        k.nscatt = (double)raw[C_NSCATT];
+        k.sweeps = (double)raw[C_SWEEPS];
+        k.sdf_evals = (double)raw[C_SWEEPS] * (double)c->tops.size();
+        k.bounces = (double)raw[C_BOUNCES];
+        k.launched = (double)raw[C_LAUNCHED];
+        k.emit_retries = (double)raw[C_RETRIES];
+        k.lost = (double)raw[C_LOST];
+        k.det_hits = (double)raw[C_DETHITS];
+        if (accumulate) {
+            counters->nscatt += k.nscatt; counters->sdf_evals += k.sdf_evals; counters->bounces += k.bounces;
+            counters->launched += k.launched; counters->emit_retries += k.emit_retries; counters->lost += k.lost;
+            counters->sweeps += k.sweeps; counters->det_hits += k.det_hits;
+        } else
+            *counters = k;
+    }
+    return 0;
+}
+
+extern "C" int smcrt_reset_tallies(smcrt_ctx* c) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    for (DeviceState& D : c->devs)
+        if ((rc = zero_device_tallies(c, D))) return rc;
+    return 0;
+}
+
+// ---- probes ----------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)) == cudaSuccess ? 0 : -1; }
+    template <typename T> T* as() { return (T*)p; }
+};
+std::vector<float> to_f(const double* d, size_t n) {
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; ++i) f[i] = (float)d[i];
+    return f;
+}
+int up_f(DevBuf& b, const double* d, size_t n) {
+    std::vector<float> f = to_f(d, n);
+    if (b.alloc(n * 4)) return -1;
+    return cudaMemcpy(b.p, f.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+}
+int down_f(DevBuf& b, double* d, size_t n) {
+    std::vector<float> f(n);
+    if (cudaMemcpy(f.data(), b.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t i = 0; i < n; ++i) d[i] = (double)f[i];
+    return 0;
+}
+int grid_for(long long n) { return (int)std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148 * 8); }
+}  // namespace
+#define PROBE_FAIL() set_err("probe: CUDA error: %s", cudaGetErrorString(cudaGetLastError()))
+
+extern "C" int smcrt_probe_sdf(smcrt_ctx* c, int top_index, int64_t n, const double* pos, double* dist, double* normal) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (top_index < 0 || top_index > (int)c->tops.size()) return set_err("smcrt_probe_sdf: top_index out of range");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    KParams P;
+    fill_params(c, D, P);
+    const size_t nd = top_index > 0 ? (size_t)n : (size_t)n * c->tops.size();
+    DevBuf bp, bd, bn;
+    if (up_f(bp, pos, 3 * (size_t)n) || bd.alloc(nd * 4) || bn.alloc(3 * (size_t)n * 4)) return PROBE_FAIL();
+    const bool want_n = normal && top_index > 0;
+    CU(cudaFuncSetAttribute(probe_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->blob_bytes));
+    probe_sdf_kernel<<<grid_for(n), 256, c->blob_bytes, D.stream>>>(P, top_index, n, bp.as<float>(), bd.as<float>(),
+                                                                     want_n ? bn.as<float>() : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    if (down_f(bd, dist, nd)) return PROBE_FAIL();
+    if (want_n && down_f(bn, normal, 3 * (size_t)n)) return PROBE_FAIL();
+    return 0;
+}
+extern "C" int smcrt_probe_fresnel(smcrt_ctx* c, int64_t n, const double* dir, const double* nrm, const double* n1, const double* n2,
+                                   const double* xi, double* dir_out, double* refl_coeff, int32_t* rflag) {
+    if (!c) return set_err("null ctx");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    DevBuf a, b, e, f, g, o, r, fl;
+    if (up_f(a, dir, 3 * n) || up_f(b, nrm, 3 * n) || up_f(e, n1, n) || up_f(f, n2, n) || up_f(g, xi, n) || o.alloc(12 * n) ||
+        r.alloc(4 * n) || fl.alloc(4 * n))
+        return PROBE_FAIL();
+    probe_fresnel_kernel<<<grid_for(n), 256, 0, D.stream>>>(n, a.as<float>(), b.as<float>(), e.as<float>(), f.as<float>(), g.as<float>(),
+                                                            o.as<float>(), r.as<float>(), fl.as<int>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    if (down_f(o, dir_out, 3 * n)) return PROBE_FAIL();
+    if (refl_coeff && down_f(r, refl_coeff, n)) return PROBE_FAIL();
+    if (rflag) CU(cudaMemcpy(rflag, fl.p, 4 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int smcrt_probe_scatter(smcrt_ctx* c, int64_t n, const double* dir, const double* hgg, const double* xi, double* dir_out) {
+    if (!c) return set_err("null ctx");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    DevBuf a, b, e, o;
+    if (up_f(a, dir, 3 * n) || up_f(b, hgg, n) || up_f(e, xi, 2 * n) || o.alloc(12 * n)) return PROBE_FAIL();
+    probe_scatter_kernel<<<grid_for(n), 256, 0, D.stream>>>(n, a.as<float>(), b.as<float>(), e.as<float>(), o.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    if (down_f(o, dir_out, 3 * n)) return PROBE_FAIL();
+    return 0;
+}
+extern "C" int smcrt_probe_emit(smcrt_ctx* c, int64_t n, const double* xi4, double* pos, double* dir, int32_t* cell) {
+    if (!c) return set_err("null ctx");
+    if (c->nxg == 0) return set_err("no grid set (smcrt_set_grid)");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    KParams P;
+    fill_params(c, D, P);
+    DevBuf a, p, d, ce;
+    if (up_f(a, xi4, 4 * n) || p.alloc(12 * n) || d.alloc(12 * n) || ce.alloc(12 * n)) return PROBE_FAIL();
+    probe_emit_kernel<<<grid_for(n), 256, 0, D.stream>>>(P, n, a.as<float>(), p.as<float>(), d.as<float>(), ce.as<int>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    if (down_f(p, pos, 3 * n) || down_f(d, dir, 3 * n)) return PROBE_FAIL();
+    if (cell) CU(cudaMemcpy(cell, ce.p, 12 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int smcrt_probe_detector(smcrt_ctx* c, int det_index, int64_t n, const double* start, const double* dir, const double* seg_len,
+                                    int32_t* hit, int32_t* bin) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (det_index < 1 || det_index > (int)c->dets.size()) return set_err("smcrt_probe_detector: det_index out of range");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    KParams P;
+    fill_params(c, D, P);
+    DevBuf a, b, e, h, bi;
+    if (up_f(a, start, 3 * n) || up_f(b, dir, 3 * n) || up_f(e, seg_len, n) || h.alloc(4 * n) || bi.alloc(4 * n)) return PROBE_FAIL();
+    probe_detector_kernel<<<grid_for(n), 256, 0, D.stream>>>(P, det_index, n, a.as<float>(), b.as<float>(), e.as<float>(), h.as<int>(),
+                                                             bi.as<int>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    CU(cudaMemcpy(hit, h.p, 4 * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(bin, bi.p, 4 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode, int survival_bias,
+                                   int32_t* fate, int32_t* nscatt, double* final_pos, int32_t* n_events) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (c->pending) return set_err("smcrt_trace_packets: a run is pending");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    DevBuf f, s, e, p;
+    if (f.alloc(4 * n) || s.alloc(4 * n) || e.alloc(4 * n) || p.alloc(12 * n)) return PROBE_FAIL();
+    CU(cudaMemset(f.p, 0xff, 4 * n));
+    rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>());
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(D.stream));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
+    c->last_ms = t;
+    if (fate) CU(cudaMemcpy(fate, f.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (nscatt) CU(cudaMemcpy(nscatt, s.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (n_events) CU(cudaMemcpy(n_events, e.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (final_pos && down_f(p, final_pos, 3 * n)) return PROBE_FAIL();
+    return 0;
+}
+extern "C" int smcrt_probe_philox(uint64_t seed, uint64_t packet_id, uint32_t event, uint32_t out[4]) {
+    philox4x32_10(event, (uint32_t)packet_id, (uint32_t)(packet_id >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    return 0;
+}

@@ -1,0 +1,882 @@
+// kernels.cuh — the persistent photon-packet kernel for sm_100a and its device helpers.
+//
+// One thread = one packet at a time; a thread that loses its packet immediately launches the next one from a
+// global work counter (persistent threads).  The reference's four nested data-dependent loops
+// (src/kernelsMod.f90:1958, src/inttau2.f90:61,155,225) are flattened into ONE loop whose body is
+//     [cold events: Fresnel | end-of-tauint2 | interaction | emit]  ->  [sweep: evaluate ALL SDFs at one point]
+//     ->  [cheap state transition]
+// so that every live lane of a warp executes exactly one sweep per iteration (the sweep is the dominant cost
+// and its loop over primitives is warp-uniform), see DESIGN.md §4.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "device_scene.cuh"
+
+namespace smcrt_dev {
+
+// ------------------------------------------------------------------------------------------------ params
+struct KParams {
+    // scene blob (global) and its carve-up; copied to shared memory by every CTA
+    const unsigned char* blob;
+    int blob_bytes;
+    int n_prims, n_top, n_instr, n_det;
+    int off_tops, off_prog, off_dets;  // byte offsets inside the blob (prims at 0)
+    const DevPrimD* primsD;            // FP64 copies for the surface normal
+    const DevInstrD* progD;
+    // voxel grid (src/grid.f90:14-25)
+    int nxg, nyg, nzg;
+    float gmax[3];     // half extents
+    float vox[3];      // voxel edge 2*max/n
+    float inv_vox[3];  // n/(2*max)
+    // source (src/photon.f90), transforms precomputed on the host
+    int src_kind, src_sub, src_alt;
+    float sp[24];
+    float Tpos[12];  // local emit position -> world (row-vector affine folded to 3x4)
+    float Tdir[9];   // local emit direction -> world (3x3)
+    // tallies
+    float* jmean;
+    float* absorb;
+    float* emission;
+    unsigned long long* det_bins;  // Q40.24 fixed point
+    int det_total;
+    int det_in_smem;
+    unsigned long long* counters;  // [nscatt, sweeps, bounces, launched, retries, lost, n_top*sweeps(unused), det_hits]
+    unsigned long long* next;      // work counter
+    long long nphotons;
+    unsigned long long id_offset;
+    uint32_t seed_lo, seed_hi;
+    int tally_mode, survival;
+    float threshold, chance;
+    float eps0, eps_rel;
+    int max_steps;
+    // optional per-packet outputs (smcrt_trace_packets)
+    int* out_fate;
+    int* out_nscatt;
+    int* out_events;
+    float* out_pos;
+};
+
+enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE, C_DETHITS, C_COUNT };
+enum : int { TALLY_ABSORB = 1, TALLY_PATHLENGTH = 2, TALLY_EMISSION = 4 };
+constexpr float TWOPI_F = 6.283185307179586f;
+constexpr float DET_FIX = 16777216.0f;  // 2^24: detector bins are Q40.24 fixed point
+
+// ------------------------------------------------------------------------------------------------ RNG
+// Philox4x32-10 (Salmon et al. 2011).  counter = (event, id_lo, id_hi, 0), key = (seed_lo, seed_hi):
+// one 4-word block per packet "event" (emit attempt / interaction / Fresnel), DESIGN.md §5.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), hi1 = __umulhi(0xCD9E8D57u, c2);
+#else
+        const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32), hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
+#endif
+        const uint32_t lo0 = 0xD2511F53u * c0, lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t w) { return __fmul_rn((float)(w >> 8), 5.9604644775390625e-08f); }  // [0,1)
+__device__ __forceinline__ float u01_open0(uint32_t w) {                                                           // (0,1]
+    return __fmul_rn(__fadd_rn(__uint2float_rn(w), 1.0f), 2.3283064365386963e-10f);
+}
+
+// ------------------------------------------------------------------------------------------------ scene view
+struct SceneView {
+    const DevPrim* prims;
+    const DevTop* tops;
+    const DevInstr* prog;
+    const DevDet* dets;
+    int n_top, n_det;
+};
+
+__device__ __forceinline__ float eval_top_f(const SceneView& sc, int t, float x, float y, float z) {
+    const DevTop T = sc.tops[t];
+    if (T.mode == 0) return eval_prim<float>(sc.prims[T.first], x, y, z);
+    return eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, T.first, T.count, x, y, z);
+}
+__device__ __forceinline__ double eval_top_d(const KParams& P, const SceneView& sc, int t, double x, double y, double z) {
+    const DevTop T = sc.tops[t];
+    if (T.mode == 0) return eval_prim<double>(P.primsD[T.first], x, y, z);
+    return eval_program<double, DevPrimD, DevInstrD>(P.primsD, P.progD, T.first, T.count, x, y, z);
+}
+// calcNormal (src/sdfs/sdf_base.f90:166-190): tetrahedral 4-tap gradient with h = 1e-6, in FP64 like the
+// reference (h is far below FP32 resolution); only executed at refractive-index-mismatch crossings.
+__device__ __noinline__ void surface_normal(const KParams& P, const SceneView& sc, int t, float x, float y, float z, float n[3]) {
+    const double h = 1e-6, X = x, Y = y, Z = z;
+    const double f1 = eval_top_d(P, sc, t, X + h, Y - h, Z - h);
+    const double f2 = eval_top_d(P, sc, t, X - h, Y - h, Z + h);
+    const double f3 = eval_top_d(P, sc, t, X - h, Y + h, Z - h);
+    const double f4 = eval_top_d(P, sc, t, X + h, Y + h, Z + h);
+    double nx = f1 - f2 - f3 + f4, ny = -f1 - f2 + f3 + f4, nz = -f1 + f2 - f3 + f4;
+    const double il = rsqrt(nx * nx + ny * ny + nz * nz);
+    n[0] = (float)(nx * il); n[1] = (float)(ny * il); n[2] = (float)(nz * il);
+}
+
+// Evaluate ALL top-level SDFs at (x,y,z): min|d|, min d, argmax of the negatives (the reference's
+// maxloc(ds, mask=ds<0): innermost surface wins, ties -> lowest index, none -> 0), value there, and the value of
+// SDF `layer` (1-based).   src/inttau2.f90:63-68,80-84,135-139,179-183,216-221,229-234
+struct Sweep {
+    float amin, smin, dL, dcur;
+    int L;
+};
+__device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y, float z, int layer) {
+    Sweep s;
+    s.amin = 3.0e38f; s.smin = 3.0e38f; s.dL = -3.0e38f; s.dcur = 0.f; s.L = 0;
+    const int n = sc.n_top;
+    for (int i = 0; i < n; ++i) {
+        const float d = eval_top_f(sc, i, x, y, z);
+        s.amin = fminf(s.amin, fabsf(d));
+        s.smin = fminf(s.smin, d);
+        if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
+        if (i + 1 == layer) s.dcur = d;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ Fresnel
+// src/surfaces.f90:14-127 (fresnel :86-127, reflect :42-55, refract :57-84).  Returns the coefficient; sets rflag.
+__device__ __forceinline__ float reflect_refract(float d[3], const float N[3], float n1, float n2, float xi, bool& rflag) {
+    const float idn = d[0] * N[0] + d[1] * N[1] + d[2] * N[2];
+    float costt = fminf(fabsf(idn), 1.0f);
+    const float sintt = sqrtf(1.0f - costt * costt);
+    const float eta = n1 / n2;
+    const float sint2 = eta * sintt;
+    float R;
+    if (sint2 > 1.0f) R = 1.0f;            // total internal reflection
+    else if (costt == 1.0f) R = 0.0f;      // exactly normal incidence: transmitted (reference quirk Q10)
+    else {
+        const float cost2 = sqrtf(1.0f - sint2 * sint2);
+        const float a = (n1 * costt - n2 * cost2) / (n1 * costt + n2 * cost2);
+        const float b = (n1 * cost2 - n2 * costt) / (n1 * cost2 + n2 * costt);
+        R = 0.5f * (a * a + b * b);
+    }
+    if (xi <= R) {  // reflect: I - 2 (N.I) N
+        rflag = true;
+        const float k = 2.0f * idn;
+        d[0] -= k * N[0]; d[1] -= k * N[1]; d[2] -= k * N[2];
+    } else {  // refract with the normal flipped to oppose I
+        rflag = false;
+        float c1 = idn, sg = 1.0f;
+        if (c1 < 0.f) c1 = -c1;
+        else sg = -1.0f;
+        const float c2 = sqrtf(1.0f - eta * eta * (1.0f - c1 * c1));
+        const float k = (eta * c1 - c2) * sg;
+        d[0] = eta * d[0] + k * N[0]; d[1] = eta * d[1] + k * N[1]; d[2] = eta * d[2] + k * N[2];
+    }
+    return R;
+}
+
+// ------------------------------------------------------------------------------------------------ scatter
+// photon%scatter, src/photon.f90:1045-1103 (mcxyz direction update). xi_c: cos(theta) draw, xi_p: phi draw.
+__device__ __forceinline__ void hg_scatter(float d[3], float hgg, float xi_c, float xi_p) {
+    float cost;
+    if (hgg == 0.0f) cost = 2.0f * xi_c - 1.0f;
+    else {
+        const float t = (1.0f - hgg * hgg) / (1.0f - hgg + 2.0f * hgg * xi_c);
+        cost = (1.0f + hgg * hgg - t * t) / (2.0f * hgg);
+    }
+    cost = fminf(fmaxf(cost, -1.0f), 1.0f);  // FP32 guard: the HG inversion can overshoot |1| by an ulp
+    const float sint = sqrtf(1.0f - cost * cost);
+    float sinp, cosp;
+    sincosf(TWOPI_F * xi_p, &sinp, &cosp);
+    float ux, uy, uz;
+    const float nx = d[0], ny = d[1], nz = d[2];
+    // the reference switches at |nz| > 1 - 1e-12; in FP32 the equivalent guard is 1 - nz^2 ~ 0
+    if (nz > 1.0f - 1e-6f) {
+        ux = sint * cosp; uy = sint * sinp; uz = cost;
+    } else if (nz < -1.0f + 1e-6f) {
+        ux = sint * cosp; uy = sint * sinp; uz = -cost;
+    } else {
+        const float t = sqrtf(1.0f - nz * nz);
+        const float it = 1.0f / t;
+        ux = sint * ((nx * nz * cosp - ny * sinp) * it) + nx * cost;
+        uy = sint * ((ny * nz * cosp + nx * sinp) * it) + ny * cost;
+        uz = -sint * cosp * t + nz * cost;
+    }
+    // :1091-1097 renormalises until |len-1| <= 1e-12; one FP32 normalisation is the same operation at FP32 resolution
+    const float il = rsqrtf(ux * ux + uy * uy + uz * uz);
+    d[0] = ux * il; d[1] = uy * il; d[2] = uz * il;
+}
+
+// ------------------------------------------------------------------------------------------------ voxels
+__device__ __forceinline__ bool in_grid(const KParams& P, float x, float y, float z) {
+    // update_voxels (src/inttau2.f90:587-614): cell = floor(n * X / (2 max)) + 1 valid  <=>  0 <= X*n/(2max) < n
+    const float fx = (x + P.gmax[0]) * P.inv_vox[0], fy = (y + P.gmax[1]) * P.inv_vox[1], fz = (z + P.gmax[2]) * P.inv_vox[2];
+    return fx >= 0.f && fx < (float)P.nxg && fy >= 0.f && fy < (float)P.nyg && fz >= 0.f && fz < (float)P.nzg;
+}
+__device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y, float z) {
+    int i = (int)floorf((x + P.gmax[0]) * P.inv_vox[0]);
+    int j = (int)floorf((y + P.gmax[1]) * P.inv_vox[1]);
+    int k = (int)floorf((z + P.gmax[2]) * P.inv_vox[2]);
+    i = min(max(i, 0), P.nxg - 1); j = min(max(j, 0), P.nyg - 1); k = min(max(k, 0), P.nzg - 1);
+    return (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
+}
+// Warp-aggregated deposit: lanes of the converged group that hit the same voxel are summed with shuffles and
+// ONE red.global.add.f32 is issued per distinct voxel.
+__device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, vox);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    float sum = w;
+    if (peers != (1u << lane)) {
+        sum = 0.f;
+        unsigned rem = peers;
+        while (rem) {  // every peer executes the same number of shuffles
+            const int src = __ffs(rem) - 1;
+            sum += __shfl_sync(peers, w, src);
+            rem &= rem - 1;
+        }
+    }
+    if (lane == leader) atomicAdd(grid + vox, sum);  // result unused -> RED.E.ADD.F32
+}
+
+// update_grids (src/inttau2.f90:367-465).  Default build: only the end-of-step voxel matters (packet dies when it
+// is outside the grid).  -Dpathlength: 3-D DDA depositing (segment length * weight) in every voxel crossed.
+template <bool PATHLEN>
+__device__ __forceinline__ bool walk_grid(const KParams& P, float fx, float fy, float fz, const float d[3], float len, float weight) {
+    if (!PATHLEN) {
+        return !in_grid(P, fx + d[0] * len, fy + d[1] * len, fz + d[2] * len);
+    } else {
+        // corner-origin coordinates in voxel units
+        const float X = (fx + P.gmax[0]), Y = (fy + P.gmax[1]), Z = (fz + P.gmax[2]);
+        int i = (int)floorf(X * P.inv_vox[0]), j = (int)floorf(Y * P.inv_vox[1]), k = (int)floorf(Z * P.inv_vox[2]);
+        if (i < 0 || i >= P.nxg || j < 0 || j >= P.nyg || k < 0 || k >= P.nzg) return true;  // :411-415
+        const int sx = d[0] > 0.f ? 1 : -1, sy = d[1] > 0.f ? 1 : -1, sz = d[2] > 0.f ? 1 : -1;
+        const float BIG = 3.0e38f;
+        float tx = d[0] != 0.f ? (((float)(i + (sx > 0)) * P.vox[0]) - X) / d[0] : BIG;
+        float ty = d[1] != 0.f ? (((float)(j + (sy > 0)) * P.vox[1]) - Y) / d[1] : BIG;
+        float tz = d[2] != 0.f ? (((float)(k + (sz > 0)) * P.vox[2]) - Z) / d[2] : BIG;
+        const float dtx = d[0] != 0.f ? P.vox[0] / fabsf(d[0]) : BIG;
+        const float dty = d[1] != 0.f ? P.vox[1] / fabsf(d[1]) : BIG;
+        const float dtz = d[2] != 0.f ? P.vox[2] / fabsf(d[2]) : BIG;
+        float t = 0.f;
+        bool out = false;
+        for (;;) {
+            const float tn = fminf(tx, fminf(ty, tz));
+            const long long v = (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
+            if (tn >= len) {
+                deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
+                break;
+            }
+            deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
+            t = tn;
+            if (tx <= ty && tx <= tz) { i += sx; tx += dtx; out = (i < 0 || i >= P.nxg); }
+            else if (ty <= tz)        { j += sy; ty += dty; out = (j < 0 || j >= P.nyg); }
+            else                      { k += sz; tz += dtz; out = (k < 0 || k >= P.nzg); }
+            if (out) break;  // :437-440
+        }
+        return out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ detectors
+// One straight segment (start, dir, length) against one detector: record_hit_1D/2D + check_hit_*
+// (src/detectors/detector_base.f90:137-163,206-235; src/detectors/detectors.f90:147-469;
+//  intersectPlane/Circle src/geometryMod.f90:217-270).  Returns the 1-based flat bin, 0 on miss.
+__device__ __forceinline__ bool plane_hit(const float n[3], const float p0[3], const float s[3], const float d[3], float& t) {
+    const float denom = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+    if (denom > 1e-6f) {
+        t = ((p0[0] - s[0]) * n[0] + (p0[1] - s[1]) * n[1] + (p0[2] - s[2]) * n[2]) / denom;
+        return t > -1e-6f;
+    }
+    return false;
+}
+__device__ __forceinline__ bool disk_hit(const float n[3], const float p0[3], float radius, const float s[3], const float d[3],
+                                         float& t, float& r) {
+    t = 0.f;
+    if (plane_hit(n, p0, s, d, t)) {
+        const float vx = s[0] + d[0] * t - p0[0], vy = s[1] + d[1] * t - p0[1], vz = s[2] + d[2] * t - p0[2];
+        r = sqrtf(vx * vx + vy * vy + vz * vz);
+        return r <= radius;
+    }
+    return false;
+}
+__device__ __forceinline__ int nint_pos(float v) { return (int)floorf(v + 0.5f); }  // Fortran nint for v >= 0
+__device__ __noinline__ int detector_bin(const DevDet& D, const float s[3], const float d[3], float sep) {
+    float t = 0.f, r = 0.f;
+    switch (D.kind) {
+        case 1: {  // circle
+            if (!disk_hit(D.dir, D.pos, D.q[0], s, d, t, r)) return 0;
+            if (t <= 0.f || t > sep) return 0;
+            return min(nint_pos(r / D.q[1]) + 1, D.nbins);
+        }
+        case 2: {  // annulus: not inside r1, inside r2 (both tests share the plane hit -> same t)
+            const bool h1 = disk_hit(D.dir, D.pos, D.q[0], s, d, t, r);
+            const bool h2 = disk_hit(D.dir, D.pos, D.q[1], s, d, t, r);
+            if (h1 || !h2) return 0;
+            if (t <= 0.f || t > sep) return 0;
+            return max(min(nint_pos((r - D.q[0]) / D.q[2]) + 1, D.nbins), 1);
+        }
+        case 3: {  // fibre: 4f relay in the thin-lens approximation :323-393
+            if (!disk_hit(D.dir, D.pos, D.q[0], s, d, t, r)) return 0;
+            if (t <= 0.f || t > sep) return 0;
+            float costt = fminf(D.dir[0] * d[0] + D.dir[1] * d[1] + D.dir[2] * d[2], 1.0f);
+            const float sintt = sqrtf(1.0f - costt * costt);
+            float gradient = sintt / costt;
+            float radius = r;
+            gradient = -radius / D.q[1] + gradient;
+            radius = radius + gradient * D.q[3];
+            if (radius > D.q[4]) return 0;
+            radius = radius + gradient * D.q[5];
+            if (radius > D.q[6]) return 0;
+            gradient = -radius / D.q[2] + gradient;
+            radius = radius + gradient * D.q[7];
+            const float angle = fabsf(atanf(gradient)) * (360.0f / TWOPI_F);
+            if (angle > D.q[8] || radius > D.q[9]) return 0;
+            return min(nint_pos(fabsf(radius) / D.q[10]) + 1, D.nbins);
+        }
+        case 4: {  // camera :447-469 + record_hit_2D_sub (bins the segment START, adds 1)
+            const float dn = d[0] * D.dir[0] + d[1] * D.dir[1] + d[2] * D.dir[2];
+            const float tt = ((D.pos[0] - s[0]) * D.dir[0] + (D.pos[1] - s[1]) * D.dir[1] + (D.pos[2] - s[2]) * D.dir[2]) / dn;
+            if (!(tt >= 0.f)) return 0;
+            const float vx = s[0] + tt * d[0] - D.pos[0], vy = s[1] + tt * d[1] - D.pos[1], vz = s[2] + tt * d[2] - D.pos[2];
+            const float p1 = (vx * D.q[0] + vy * D.q[1] + vz * D.q[2]) / D.q[6];
+            const float p2 = (vx * D.q[3] + vy * D.q[4] + vz * D.q[5]) / D.q[7];
+            if (!(p1 < D.q[6] && p1 > 0.f && p2 < D.q[7] && p2 > 0.f)) return 0;
+            const float bx = s[2] + D.q[10], by = s[1] + D.q[11];  // sic: hitpoint%pos%z + this%pos%x
+            int ix = min((int)(bx / D.q[8]) + 1, D.nbins), iy = min((int)(by / D.q[9]) + 1, D.nbins);
+            if (ix < 1) ix = D.nbins;
+            if (iy < 1) iy = D.nbins;
+            return ix + (iy - 1) * D.nbins;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ emitters
+// src/photon.f90:214-1043.  u0..u2: uniforms of the event block.  Returns false when the emitter's own rejection
+// step (gaussian annulus, `rang` src/random_mod.f90:99-124) wants a fresh block.
+__device__ __forceinline__ void nudge_face(float& c, float cmax) {
+    // 7.9e-7 inset when exactly on a grid face (photon.f90:614-628); in FP32 the inset must survive rounding
+    const float inset = fmaxf(7.9e-7f, 4.0f * 1.1920929e-7f * cmax);
+    if (c == -cmax) c += inset;
+    else if (c == cmax) c -= inset;
+}
+__device__ __forceinline__ void clip_to_grid(const KParams& P, float pos[3], const float dir[3], int cap) {
+    // photon.f90:495-553 / :988-1036: project onto the grid box along the ray, at most `cap`+2 passes
+    bool in[3] = {false, false, false}, tried[3] = {false, false, false};
+    int counter = 0;
+    while (!in[0] || !in[1] || !in[2]) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float inset = fmaxf(9e-7f, 4.0f * 1.1920929e-7f * P.gmax[a]);
+            if (pos[a] <= -P.gmax[a]) {
+                const float st = (-P.gmax[a] - pos[a] + inset) / dir[a];
+                pos[0] += dir[0] * st; pos[1] += dir[1] * st; pos[2] += dir[2] * st;
+                tried[a] = true;
+            } else if (pos[a] >= P.gmax[a]) {
+                const float st = (P.gmax[a] - pos[a] - inset) / dir[a];
+                pos[0] += dir[0] * st; pos[1] += dir[1] * st; pos[2] += dir[2] * st;
+                tried[a] = true;
+            } else
+                in[a] = true;
+        }
+        if ((tried[0] && tried[1] && tried[2]) || counter > cap) break;
+        ++counter;
+    }
+}
+__device__ __forceinline__ void xform_pos(const float T[12], const float l[3], float o[3]) {
+    o[0] = T[0] * l[0] + T[1] * l[1] + T[2] * l[2] + T[3];
+    o[1] = T[4] * l[0] + T[5] * l[1] + T[6] * l[2] + T[7];
+    o[2] = T[8] * l[0] + T[9] * l[1] + T[10] * l[2] + T[11];
+}
+__device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]) {
+    const float* sp = P.sp;
+    switch (P.src_kind) {
+        case 1: {  // point :311-359
+            pos[0] = sp[0]; pos[1] = sp[1]; pos[2] = sp[2];
+            float sinp, cosp;
+            sincosf(u0 * TWOPI_F, &sinp, &cosp);
+            const float cost = 2.0f * u1 - 1.0f;
+            const float sint = sqrtf(1.0f - cost * cost);
+            dir[0] = sint * cosp; dir[1] = sint * sinp; dir[2] = cost;
+            return true;
+        }
+        case 2: {  // pencil :652-710
+            pos[0] = sp[0]; pos[1] = sp[1]; pos[2] = sp[2];
+            nudge_face(pos[0], P.gmax[0]); nudge_face(pos[1], P.gmax[1]); nudge_face(pos[2], P.gmax[2]);
+            dir[0] = sp[3]; dir[1] = sp[4]; dir[2] = sp[5];
+            return true;
+        }
+        case 3: {  // uniform :566-649
+            pos[0] = sp[6] + u0 * sp[9] + u1 * sp[12];
+            pos[1] = sp[7] + u0 * sp[10] + u1 * sp[13];
+            pos[2] = sp[8] + u0 * sp[11] + u1 * sp[14];
+            nudge_face(pos[0], P.gmax[0]); nudge_face(pos[1], P.gmax[1]); nudge_face(pos[2], P.gmax[2]);
+            dir[0] = sp[3]; dir[1] = sp[4]; dir[2] = sp[5];
+            return true;
+        }
+        case 4: {  // circular :214-308
+            const float r = sp[15] * sqrtf(u0);
+            float s, c;
+            sincosf(u1 * TWOPI_F, &s, &c);
+            float l[3];
+            if (P.src_alt) { l[0] = r * c; l[1] = r * s; l[2] = 0.f; }
+            else           { l[0] = 0.f;   l[1] = r * c; l[2] = r * s; }
+            float w[3];
+            xform_pos(P.Tpos, l, w);
+            pos[0] = -w[0]; pos[1] = -w[1]; pos[2] = -w[2];
+            nudge_face(pos[0], P.gmax[0]); nudge_face(pos[1], P.gmax[1]); nudge_face(pos[2], P.gmax[2]);
+            dir[0] = sp[3]; dir[1] = sp[4]; dir[2] = sp[5];
+            return true;
+        }
+        case 5:    // focus :361-563
+        case 6: {  // annulus :850-1043
+            float l[3] = {0.f, 0.f, 0.f}, a[3];  // local position, local aim point
+            const float focal = sp[16];
+            if (P.src_kind == 5) {
+                const float beam = sp[17];
+                if (P.src_sub == 1) {  // square
+                    l[0] = -beam + u0 * (2.0f * beam);
+                    l[1] = -beam + u1 * (2.0f * beam);
+                } else {
+                    const float rad = P.src_sub == 2 ? beam * sqrtf(u0) : beam * sqrtf(-logf(1.0f - u0));
+                    float s, c;
+                    sincosf(TWOPI_F * u1, &s, &c);
+                    l[0] = rad * c; l[1] = rad * s;
+                }
+                a[0] = l[0]; a[1] = l[1]; a[2] = 0.f;
+            } else {
+                const float rlo = sp[18], rhi = sp[19], mid = 0.5f * (rhi + rlo);
+                float rad;
+                if (P.src_sub == 1) rad = sqrtf(rlo * rlo + (rhi * rhi - rlo * rlo) * u0);
+                else if (P.src_sub == 2) rad = rlo + (rhi - rlo) * u0;
+                else {
+                    const float gx = -1.0f + 2.0f * u0, gy = -1.0f + 2.0f * u1;
+                    const float sq = gx * gx + gy * gy;
+                    if (sq >= 1.0f || sq == 0.0f) return false;
+                    rad = mid + sp[20] * (gx * sqrtf(-2.0f * logf(sq) / sq));
+                }
+                float s, c;
+                sincosf(TWOPI_F * u2, &s, &c);
+                l[0] = rad * c; l[1] = rad * s;
+                a[0] = mid * c; a[1] = mid * s; a[2] = 0.f;  // all rays aim from the ring-mid radius
+            }
+            // dir = -(a - targ)/|a - targ| * sign(1, focal), targ = (0,0,-focal)
+            float dl[3] = {-a[0], -a[1], -(a[2] + focal)};
+            const float sgn = focal >= 0.f ? 1.0f : -1.0f;
+            float il = sgn * rsqrtf(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+            dl[0] *= il; dl[1] *= il; dl[2] *= il;
+            float dw[3] = {P.Tdir[0] * dl[0] + P.Tdir[1] * dl[1] + P.Tdir[2] * dl[2],
+                           P.Tdir[3] * dl[0] + P.Tdir[4] * dl[1] + P.Tdir[5] * dl[2],
+                           P.Tdir[6] * dl[0] + P.Tdir[7] * dl[1] + P.Tdir[8] * dl[2]};
+            il = rsqrtf(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);
+            dir[0] = dw[0] * il; dir[1] = dw[1] * il; dir[2] = dw[2] * il;
+            xform_pos(P.Tpos, l, pos);
+            clip_to_grid(P, pos, dir, P.src_kind == 5 ? 4 : 3);
+            return true;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+enum : int { ST_TOP = 0, ST_BND_PROBE, ST_BND_RE, ST_TRACE, ST_CROSS, ST_FRESNEL, ST_FINISH, ST_INTERACT, ST_EMIT, ST_DONE };
+enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST = 3 };
+
+template <bool PATHLEN, bool HASDET>
+__global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // ---- stage the scene in shared memory (16-byte vector copies)
+    {
+        const int4* src = reinterpret_cast<const int4*>(P.blob);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    unsigned long long* sbins = reinterpret_cast<unsigned long long*>(smem + P.blob_bytes);
+    if (HASDET && P.det_in_smem)
+        for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
+    __syncthreads();
+    SceneView sc;
+    sc.prims = reinterpret_cast<const DevPrim*>(smem);
+    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
+    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
+    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
+    sc.n_top = P.n_top;
+    sc.n_det = P.n_det;
+
+    const int lane = threadIdx.x & 31;
+    // ---- per-thread packet state
+    float pos[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, start[3] = {0, 0, 0};
+    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
+    float ds_pos_cur = 0.f, dnew_L = 0.f, dnew_cur = 0.f;
+    int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0, fate = 0;
+    bool tflag = false, launch = false;
+    unsigned long long pid = 0;
+    uint32_t ev = 0;
+    // ---- per-thread counters
+    unsigned long long c_nscatt = 0, c_sweeps = 0, c_bounces = 0, c_launched = 0, c_retries = 0, c_lost = 0, c_dethits = 0;
+
+    auto segment_detect = [&]() {
+        if (HASDET) {
+            const float ex = pos[0] - start[0], ey = pos[1] - start[1], ez = pos[2] - start[2];
+            const float sep = sqrtf(ex * ex + ey * ey + ez * ez);
+            for (int i = 0; i < sc.n_det; ++i) {
+                const int b = detector_bin(sc.dets[i], start, dir, sep);
+                if (b > 0) {
+                    const float w = sc.dets[i].kind == 4 ? 1.0f : weight;
+                    const unsigned long long q = (unsigned long long)__float2ll_rn(w * DET_FIX);
+                    const int slot = sc.dets[i].offset + b - 1;
+                    if (P.det_in_smem) atomicAdd(&sbins[slot], q);
+                    else atomicAdd(&P.det_bins[slot], q);
+                    ++c_dethits;
+                }
+            }
+            start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
+        }
+    };
+    auto retire = [&](int f) {  // packet is finished: publish the optional per-packet record, ask for a new one
+        fate = f;
+        if (P.out_fate) {
+            const long long k = (long long)(pid - P.id_offset);
+            P.out_fate[k] = f;
+            if (P.out_nscatt) P.out_nscatt[k] = pk_nscatt;
+            if (P.out_events) P.out_events[k] = (int)ev;
+            if (P.out_pos) { P.out_pos[3 * k] = pos[0]; P.out_pos[3 * k + 1] = pos[1]; P.out_pos[3 * k + 2] = pos[2]; }
+        }
+        c_bounces += bounces;
+        if (f == FATE_LOST) ++c_lost;
+        state = ST_EMIT;
+    };
+
+    for (;;) {
+        // =============================== cold events ===============================
+        if (state == ST_FRESNEL) {
+            // src/inttau2.f90:248-317: pick the surface that is actually being crossed, normal, Fresnel
+            const float ds_pos_new = eval_top_f(sc, new_layer - 1, pos[0], pos[1], pos[2]);  // ds(new_layer)
+            int surf;
+            if (dnew_L < 0.f && ds_pos_new >= 0.f) surf = new_layer;
+            else if (dnew_cur >= 0.f && ds_pos_cur < 0.f) surf = layer;
+            else if (dnew_L < 0.f && dnew_cur < 0.f) surf = new_layer;
+            else if (ds_pos_cur >= 0.f && dnew_cur >= 0.f) surf = layer;
+            else surf = -1;  // reference: error stop (:276)
+            if (surf < 0) {
+                retire(FATE_LOST);
+            } else {
+                float N[3];
+                surface_normal(P, sc, surf - 1, pos[0], pos[1], pos[2], N);
+                uint32_t w[4];
+                philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
+                const float n1 = sc.tops[layer - 1].n, n2 = sc.tops[new_layer - 1].n;
+                const float probe[3] = {pos[0] + dstep * dir[0], pos[1] + dstep * dir[1], pos[2] + dstep * dir[2]};
+                bool rflag;
+                reflect_refract(dir, N, n1, n2, u01(w[0]), rflag);
+                if (!rflag) {  // transmitted :284-303
+                    layer = new_layer;
+                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
+                    taurun += dstep * sc.tops[layer - 1].kappa;
+                    pos[0] = probe[0]; pos[1] = probe[1]; pos[2] = probe[2];  // Q4: probe used the old direction
+                    segment_detect();
+                    state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
+                } else {  // reflected :304-317
+                    start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
+                    ++bounces;
+                    if (bounces > 1000) retire(FATE_LOST);
+                    else state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
+                }
+                qs = 0.f;
+            }
+        }
+        if (state == ST_FINISH) {  // tail of tauint2 (src/inttau2.f90:354-362) + loop test of kernelsMod.f90:1958
+            if (fabsf(pos[0]) > P.gmax[0] || fabsf(pos[1]) > P.gmax[1] || fabsf(pos[2]) > P.gmax[2]) tflag = true;
+            if (tflag) retire(FATE_ESCAPED);
+            else state = ST_INTERACT;
+        }
+        if (state == ST_INTERACT) {  // src/kernelsMod.f90:1958-1974 (analog) / :2032-2066 (survival bias)
+            uint32_t w[4];
+            philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
+            const float ran = u01(w[0]);
+            const DevTop T = sc.tops[layer - 1];
+            bool alive = true;
+            if (!P.survival) {
+                if (!(ran < T.albedo)) {
+                    if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, pos[0], pos[1], pos[2]), 1.0f);
+                    retire(FATE_ABSORBED);
+                    alive = false;
+                }
+            } else {
+                const float wabs = weight * (1.0f - T.albedo);
+                weight -= wabs;
+                if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, pos[0], pos[1], pos[2]), wabs);
+                if (weight < P.threshold) {
+                    if (ran < P.chance) weight = weight / P.chance;
+                    else {
+                        retire(FATE_ROULETTE);
+                        alive = false;
+                    }
+                }
+            }
+            if (alive) {
+                hg_scatter(dir, T.hgg, u01(w[1]), u01(w[2]));
+                ++c_nscatt; ++pk_nscatt;
+                tau = -logf(u01_open0(w[3]));
+                taurun = 0.f; qs = 0.f;
+                start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
+                state = ST_TOP;
+            }
+        }
+        if (state == ST_EMIT) {
+            // claim a packet id: one atomic per warp for all lanes that need one
+            const unsigned need = __ballot_sync(__activemask(), true);
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(need));
+            base = __shfl_sync(need, base, leader);
+            const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+            if (k >= (unsigned long long)P.nphotons) {
+                state = ST_DONE;
+            } else {
+                pid = P.id_offset + k;
+                ev = 0; bounces = 0; steps = 0; pk_nscatt = 0; weight = 1.0f; tflag = false;
+                ++c_launched;
+                uint32_t w[4];
+                int guard = 0;
+                for (;;) {  // emitter rejection + start-voxel rejection (kernelsMod.f90:1937-1943, quirk Q6)
+                    philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
+                    const bool ok = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]), pos, dir);
+                    if (ok && in_grid(P, pos[0], pos[1], pos[2])) break;
+                    ++c_retries;
+                    if (++guard > 100000) { guard = -1; break; }
+                }
+                if (guard < 0) {
+                    retire(FATE_LOST);
+                    continue;
+                }
+                if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, pos[0], pos[1], pos[2]), 1.0f);
+                tau = -logf(u01_open0(w[3]));
+                taurun = 0.f; qs = 0.f;
+                start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
+                launch = true;
+                layer = 0;
+                state = ST_TOP;
+            }
+        }
+        if (__all_sync(__activemask(), state == ST_DONE)) break;
+        if (state == ST_DONE) continue;
+
+        // =============================== sweep ===============================
+        const float qx = pos[0] + qs * dir[0], qy = pos[1] + qs * dir[1], qz = pos[2] + qs * dir[2];
+        const Sweep S = sweep_all(sc, qx, qy, qz, layer);
+        if (!launch) ++c_sweeps;
+        if (++steps > P.max_steps) {
+            retire(FATE_LOST);
+            continue;
+        }
+        const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(pos[0]), fmaxf(fabsf(pos[1]), fabsf(pos[2]))));
+
+        // =============================== transition ===============================
+        // d_cont >= 0: continue with the sphere-trace step logic using this distance
+        float d_cont = -1.f;
+        bool after_trace = false;
+        switch (state) {
+            case ST_TOP: {
+                if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
+                    launch = false;
+                    ++c_sweeps;
+                    layer = S.L;
+                    if (layer == 0) {  // the reference would index array(0); engine guard
+                        retire(FATE_LOST);
+                        continue;
+                    }
+                    ds_pos_cur = S.dL;
+                } else
+                    ds_pos_cur = S.dcur;
+                dlast = S.amin;
+                if (S.amin < eps) {  // sitting on a boundary :73-84
+                    dstep = S.amin + 2.0f * eps;
+                    qs = dstep;
+                    state = ST_BND_PROBE;
+                } else if (taurun >= tau || tflag)
+                    state = ST_FINISH;
+                else
+                    d_cont = S.amin;
+                break;
+            }
+            case ST_BND_PROBE: {  // :86-131
+                const float kap = sc.tops[layer - 1].kappa;
+                const float t = dstep * kap;
+                const float from[3] = {pos[0], pos[1], pos[2]};
+                const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
+                if (taurun + t < tau) {
+                    pos[0] += sg * dstep * dir[0]; pos[1] += sg * dstep * dir[1]; pos[2] += sg * dstep * dir[2];
+                    taurun += t;
+                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dstep, weight)) tflag = true;  // Q2: along +dir
+                } else {
+                    const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
+                    if (sg > 0.f) taurun += t;  // Q1: position not advanced
+                    else { pos[0] -= dd * dir[0]; pos[1] -= dd * dir[1]; pos[2] -= dd * dir[2]; }  // Q3: taurun not advanced
+                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
+                }
+                segment_detect();
+                qs = 0.f;
+                state = ST_BND_RE;
+                break;
+            }
+            case ST_BND_RE: {  // :134-152
+                ds_pos_cur = S.dcur;
+                dlast = S.amin;
+                if (S.smin > 0.f) tflag = true;
+                if (taurun >= tau || tflag) state = ST_FINISH;
+                else d_cont = S.amin;
+                break;
+            }
+            case ST_TRACE: {  // :177-191
+                ds_pos_cur = S.dcur;
+                dlast = S.amin;
+                if (S.smin > 0.f) { tflag = true; after_trace = true; }
+                else d_cont = S.amin;
+                break;
+            }
+            case ST_CROSS: {  // :220-337
+                if (S.L == layer && S.amin < eps) {  // creep :225-235
+                    dstep += eps;
+                    qs = dstep;
+                    break;
+                }
+                if (S.L == 0) {  // :237-241
+                    tflag = true;
+                    state = ST_FINISH;
+                    break;
+                }
+                const float n1 = sc.tops[layer - 1].n, n2 = sc.tops[S.L - 1].n;
+                if (n1 != n2) {
+                    new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
+                    state = ST_FRESNEL;
+                } else {  // :318-337
+                    layer = S.L;
+                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
+                    taurun += dstep * sc.tops[layer - 1].kappa;
+                    pos[0] = qx; pos[1] = qy; pos[2] = qz;
+                    segment_detect();
+                    qs = 0.f;
+                    state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
+                }
+                break;
+            }
+            default: break;
+        }
+        if (d_cont >= 0.f) {  // `do while (d_sdf >= eps)` body, :155-176
+            if (d_cont >= eps) {
+                const float kap = sc.tops[layer - 1].kappa;
+                const float t = d_cont * kap;
+                if (taurun + t < tau) {
+                    taurun += t;
+                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, d_cont, weight)) tflag = true;
+                    pos[0] += d_cont * dir[0]; pos[1] += d_cont * dir[1]; pos[2] += d_cont * dir[2];
+                    qs = 0.f;
+                    state = ST_TRACE;
+                } else {
+                    const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
+                    taurun = tau;
+                    const float from[3] = {pos[0], pos[1], pos[2]};
+                    pos[0] += dd * dir[0]; pos[1] += dd * dir[1]; pos[2] += dd * dir[2];
+                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
+                    after_trace = true;
+                }
+            } else
+                after_trace = true;
+        }
+        if (after_trace) {  // :196-221
+            segment_detect();
+            if (taurun >= tau || tflag) state = ST_FINISH;
+            else {
+                dstep = dlast + 2.0f * eps;
+                qs = dstep;
+                state = ST_CROSS;
+            }
+        }
+    }
+
+    // ---- epilogue: flush CTA-private detector bins and per-thread counters
+    __syncthreads();
+    if (HASDET && P.det_in_smem)
+        for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
+            if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
+    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, c_bounces, c_launched, c_retries, c_lost, 0ull, c_dethits};
+#pragma unroll
+    for (int c = 0; c < C_COUNT; ++c) {
+        unsigned long long v = cs[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&P.counters[c], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ probes
+// Deterministic-component kernels for the parity tests: same device functions as above.
+__global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_index, long long n, const float* pos, float* dist,
+                                 float* normal) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(smem)[i] = reinterpret_cast<const int4*>(P.blob)[i];
+    __syncthreads();
+    SceneView sc;
+    sc.prims = reinterpret_cast<const DevPrim*>(smem);
+    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
+    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
+    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
+    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        if (top_index > 0) {
+            dist[i] = eval_top_f(sc, top_index - 1, x, y, z);
+            if (normal) surface_normal(P, sc, top_index - 1, x, y, z, normal + 3 * i);
+        } else
+            for (int t = 0; t < P.n_top; ++t) dist[i * P.n_top + t] = eval_top_f(sc, t, x, y, z);
+    }
+}
+__global__ void probe_fresnel_kernel(long long n, const float* dir, const float* nrm, const float* n1, const float* n2,
+                                     const float* xi, float* dir_out, float* R, int* rflag) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+        const float N[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+        bool rf;
+        const float r = reflect_refract(d, N, n1[i], n2[i], xi[i], rf);
+        dir_out[3 * i] = d[0]; dir_out[3 * i + 1] = d[1]; dir_out[3 * i + 2] = d[2];
+        R[i] = r;
+        rflag[i] = rf ? 1 : 0;
+    }
+}
+__global__ void probe_scatter_kernel(long long n, const float* dir, const float* hgg, const float* xi, float* dir_out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+        hg_scatter(d, hgg[i], xi[2 * i], xi[2 * i + 1]);
+        dir_out[3 * i] = d[0]; dir_out[3 * i + 1] = d[1]; dir_out[3 * i + 2] = d[2];
+    }
+}
+__global__ void probe_emit_kernel(const __grid_constant__ KParams P, long long n, const float* xi4, float* pos, float* dir, int* cell) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+        emit_packet(P, xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], p, d);
+        for (int a = 0; a < 3; ++a) { pos[3 * i + a] = p[a]; dir[3 * i + a] = d[a]; }
+        // get_voxel_cart (src/grid.f90:51-78)
+        const int dims[3] = {P.nxg, P.nyg, P.nzg};
+        for (int a = 0; a < 3; ++a) {
+            int c = (int)floorf((p[a] + P.gmax[a]) * P.inv_vox[a]) + 1;
+            if (c < 1 || c > dims[a]) c = -1;
+            cell[3 * i + a] = c;
+        }
+    }
+}
+__global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det_index, long long n, const float* start,
+                                      const float* dir, const float* len, int* hit, int* bin) {
+    const DevDet D = reinterpret_cast<const DevDet*>(P.blob + P.off_dets)[det_index - 1];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float s[3] = {start[3 * i], start[3 * i + 1], start[3 * i + 2]};
+        const float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+        const int b = detector_bin(D, s, d, len[i]);
+        hit[i] = b > 0;
+        bin[i] = b;
+    }
+}
+
+}  // namespace smcrt_dev

@@ -151,9 +151,11 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
             T bax = q[3] - q[0], bay = q[4] - q[1], baz = q[5] - q[2];
             T pax = px - q[0], pay = py - q[1], paz = pz - q[2];
             T baba = bax * bax + bay * bay + baz * baz;
-            T papa = pax * pax + pay * pay + paz * paz;
             T paba = (pax * bax + pay * bay + paz * baz) / baba;
-            T xx = t_sqrt(papa - baba * paba * paba);
+            // reference: x = sqrt(pa.pa - baba*paba^2); identical in exact arithmetic to |pa - ba*paba| (the component of
+            // pa perpendicular to the axis) but without the catastrophic cancellation in FP32
+            T ex = pax - bax * paba, ey = pay - bay * paba, ez = paz - baz * paba;
+            T xx = t_sqrt(ex * ex + ey * ey + ez * ez);
             T cax = t_max(T(0), xx - (paba < T(0.5) ? ra : rb));
             T cay = t_abs(paba - T(0.5)) - T(0.5);
             T k = rba * rba + baba;

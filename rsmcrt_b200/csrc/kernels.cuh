@@ -109,15 +109,15 @@ __device__ __forceinline__ double eval_top_d(const KParams& P, const SceneView& 
 }
 // calcNormal (src/sdfs/sdf_base.f90:166-190): tetrahedral 4-tap gradient with h = 1e-6, in FP64 like the
 // reference (h is far below FP32 resolution); only executed at refractive-index-mismatch crossings.
-__device__ __noinline__ void surface_normal(const KParams& P, const SceneView& sc, int t, float x, float y, float z, float n[3]) {
-    const double h = 1e-6, X = x, Y = y, Z = z;
+__device__ __noinline__ void surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double n[3]) {
+    const double h = 1e-6;
     const double f1 = eval_top_d(P, sc, t, X + h, Y - h, Z - h);
     const double f2 = eval_top_d(P, sc, t, X - h, Y - h, Z + h);
     const double f3 = eval_top_d(P, sc, t, X - h, Y + h, Z - h);
     const double f4 = eval_top_d(P, sc, t, X + h, Y + h, Z + h);
     double nx = f1 - f2 - f3 + f4, ny = -f1 - f2 + f3 + f4, nz = -f1 + f2 - f3 + f4;
     const double il = rsqrt(nx * nx + ny * ny + nz * nz);
-    n[0] = (float)(nx * il); n[1] = (float)(ny * il); n[2] = (float)(nz * il);
+    n[0] = nx * il; n[1] = ny * il; n[2] = nz * il;
 }
 
 // Evaluate ALL top-level SDFs at (x,y,z): min|d|, min d, argmax of the negatives (the reference's
@@ -143,67 +143,84 @@ __device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y
 
 // ------------------------------------------------------------------------------------------------ Fresnel
 // src/surfaces.f90:14-127 (fresnel :86-127, reflect :42-55, refract :57-84).  Returns the coefficient; sets rflag.
-__device__ __forceinline__ float reflect_refract(float d[3], const float N[3], float n1, float n2, float xi, bool& rflag) {
-    const float idn = d[0] * N[0] + d[1] * N[1] + d[2] * N[2];
-    float costt = fminf(fabsf(idn), 1.0f);
-    const float sintt = sqrtf(1.0f - costt * costt);
-    const float eta = n1 / n2;
-    const float sint2 = eta * sintt;
-    float R;
-    if (sint2 > 1.0f) R = 1.0f;            // total internal reflection
-    else if (costt == 1.0f) R = 0.0f;      // exactly normal incidence: transmitted (reference quirk Q10)
+// Evaluated in FP64: it runs once per index-mismatch crossing (cold), and R(theta) is ill-conditioned next to the
+// total-internal-reflection knee, where FP32 rounding of I.N alone moves R by ~1e-5.
+__device__ __noinline__ float reflect_refract(float d[3], const double N[3], float n1f, float n2f, float xi, bool& rflag) {
+    const double n1 = n1f, n2 = n2f;
+    const double dx = d[0], dy = d[1], dz = d[2];
+    const double idn = dx * N[0] + dy * N[1] + dz * N[2];
+    const double costt = fmin(fabs(idn), 1.0);
+    const double sintt = sqrt(1.0 - costt * costt);
+    const double eta = n1 / n2;
+    const double sint2 = eta * sintt;
+    double R;
+    if (sint2 > 1.0) R = 1.0;            // total internal reflection
+    else if (costt == 1.0) R = 0.0;      // exactly normal incidence: transmitted (reference quirk Q10)
     else {
-        const float cost2 = sqrtf(1.0f - sint2 * sint2);
-        const float a = (n1 * costt - n2 * cost2) / (n1 * costt + n2 * cost2);
-        const float b = (n1 * cost2 - n2 * costt) / (n1 * cost2 + n2 * costt);
-        R = 0.5f * (a * a + b * b);
+        const double cost2 = sqrt(1.0 - sint2 * sint2);
+        const double a = (n1 * costt - n2 * cost2) / (n1 * costt + n2 * cost2);
+        const double b = (n1 * cost2 - n2 * costt) / (n1 * cost2 + n2 * costt);
+        R = 0.5 * (a * a + b * b);
     }
-    if (xi <= R) {  // reflect: I - 2 (N.I) N
+    if ((double)xi <= R) {  // reflect: I - 2 (N.I) N
         rflag = true;
-        const float k = 2.0f * idn;
-        d[0] -= k * N[0]; d[1] -= k * N[1]; d[2] -= k * N[2];
+        const double k = 2.0 * idn;
+        d[0] = (float)(dx - k * N[0]); d[1] = (float)(dy - k * N[1]); d[2] = (float)(dz - k * N[2]);
     } else {  // refract with the normal flipped to oppose I
         rflag = false;
-        float c1 = idn, sg = 1.0f;
-        if (c1 < 0.f) c1 = -c1;
-        else sg = -1.0f;
-        const float c2 = sqrtf(1.0f - eta * eta * (1.0f - c1 * c1));
-        const float k = (eta * c1 - c2) * sg;
-        d[0] = eta * d[0] + k * N[0]; d[1] = eta * d[1] + k * N[1]; d[2] = eta * d[2] + k * N[2];
+        double c1 = idn, sg = 1.0;
+        if (c1 < 0.0) c1 = -c1;
+        else sg = -1.0;
+        const double c2 = sqrt(1.0 - eta * eta * (1.0 - c1 * c1));
+        const double k = (eta * c1 - c2) * sg;
+        d[0] = (float)(eta * dx + k * N[0]); d[1] = (float)(eta * dy + k * N[1]); d[2] = (float)(eta * dz + k * N[2]);
     }
-    return R;
+    return (float)R;
 }
 
 // ------------------------------------------------------------------------------------------------ scatter
 // photon%scatter, src/photon.f90:1045-1103 (mcxyz direction update). xi_c: cos(theta) draw, xi_p: phi draw.
 __device__ __forceinline__ void hg_scatter(float d[3], float hgg, float xi_c, float xi_p) {
-    float cost;
-    if (hgg == 0.0f) cost = 2.0f * xi_c - 1.0f;
-    else {
-        const float t = (1.0f - hgg * hgg) / (1.0f - hgg + 2.0f * hgg * xi_c);
-        cost = (1.0f + hgg * hgg - t * t) / (2.0f * hgg);
+    // FP32-first algebra: the reference computes cos(theta) and then sin = sqrt(1 - cos^2), which cancels for the
+    // forward-peaked angles HG favours.  Here 1 - cos(theta) is formed without cancellation:
+    //   g = 0 : 1 - cos = 2 (1 - xi)
+    //   g != 0: t = (1-g^2)/(1-g+2 g xi), cos = (1+g^2-t^2)/(2g)  =>  1 - cos = (1-g)(1-xi)(t+1-g)/(1-g+2 g xi)
+    //   and symmetrically          1 + cos = (1+g) xi (t+1+g)/(1-g+2 g xi)          (back-scattering, g < 0)
+    float omc, opc;
+    if (hgg == 0.0f) {
+        omc = 2.0f * (1.0f - xi_c);
+        opc = 2.0f * xi_c;
+    } else {
+        const float den = 1.0f - hgg + 2.0f * hgg * xi_c;
+        const float t = (1.0f - hgg * hgg) / den;
+        omc = (1.0f - hgg) * (1.0f - xi_c) * (t + 1.0f - hgg) / den;
+        opc = (1.0f + hgg) * xi_c * (t + 1.0f + hgg) / den;
     }
-    cost = fminf(fmaxf(cost, -1.0f), 1.0f);  // FP32 guard: the HG inversion can overshoot |1| by an ulp
-    const float sint = sqrtf(1.0f - cost * cost);
+    omc = fminf(fmaxf(omc, 0.0f), 2.0f);
+    opc = fminf(fmaxf(opc, 0.0f), 2.0f);
+    const float cost = omc < 1.0f ? 1.0f - omc : opc - 1.0f;
+    const float sint = sqrtf(omc * opc);
     float sinp, cosp;
     sincosf(TWOPI_F * xi_p, &sinp, &cosp);
     float ux, uy, uz;
     const float nx = d[0], ny = d[1], nz = d[2];
-    // the reference switches at |nz| > 1 - 1e-12; in FP32 the equivalent guard is 1 - nz^2 ~ 0
-    if (nz > 1.0f - 1e-6f) {
-        ux = sint * cosp; uy = sint * sinp; uz = cost;
-    } else if (nz < -1.0f + 1e-6f) {
-        ux = sint * cosp; uy = sint * sinp; uz = -cost;
+    // sqrt(1 - nz^2) of the reference == sqrt(nx^2 + ny^2) for a unit vector, without the cancellation near the poles.
+    // The reference switches to the polar form at |nz| > 1 - 1e-12, i.e. (in FP32) when nx = ny = 0 to rounding.
+    const float t2 = nx * nx + ny * ny;
+    if (t2 < 1e-12f) {
+        ux = sint * cosp; uy = sint * sinp; uz = nz > 0.f ? cost : -cost;
     } else {
-        const float t = sqrtf(1.0f - nz * nz);
-        const float it = 1.0f / t;
+        const float it = rsqrtf(t2);
+        const float t = t2 * it;
         ux = sint * ((nx * nz * cosp - ny * sinp) * it) + nx * cost;
         uy = sint * ((ny * nz * cosp + nx * sinp) * it) + ny * cost;
         uz = -sint * cosp * t + nz * cost;
     }
     // :1091-1097 renormalises until |len-1| <= 1e-12; one FP32 normalisation is the same operation at FP32 resolution
-    const float il = rsqrtf(ux * ux + uy * uy + uz * uz);
-    d[0] = ux * il; d[1] = uy * il; d[2] = uz * il;
+    const float l2 = ux * ux + uy * uy + uz * uz;
+    const float il = rsqrtf(l2);
+    const float il2 = il * (1.5f - 0.5f * l2 * il * il);  // one Newton step: rsqrt.approx is only ~2 ulp
+    d[0] = ux * il2; d[1] = uy * il2; d[2] = uz * il2;
 }
 
 // ------------------------------------------------------------------------------------------------ voxels
@@ -282,43 +299,45 @@ __device__ __forceinline__ bool walk_grid(const KParams& P, float fx, float fy, 
 // One straight segment (start, dir, length) against one detector: record_hit_1D/2D + check_hit_*
 // (src/detectors/detector_base.f90:137-163,206-235; src/detectors/detectors.f90:147-469;
 //  intersectPlane/Circle src/geometryMod.f90:217-270).  Returns the 1-based flat bin, 0 on miss.
-__device__ __forceinline__ bool plane_hit(const float n[3], const float p0[3], const float s[3], const float d[3], float& t) {
+// FP32 note: the reference accepts a hit when 0 < t <= pointSep with t = ((p0-l0).n)/(n.l).  In FP32
+// the rounding of t against pointSep (both ~1e-7 relative) is comparable to the sub-eps gaps between consecutive
+// segments, so crossings would be dropped or double counted.  The same condition is therefore evaluated as a sign
+// change of the plane side function g(x) = (p0 - x).n between the segment's two stored end points: a crossing is
+// recorded iff g(start) >= 0 and g(end) < 0.  Consecutive segments share their end point bit-for-bit, so every
+// crossing is seen exactly once ("watertight"), which is what the reference's FP64 arithmetic achieves implicitly.
+__device__ __forceinline__ bool plane_cross(const float n[3], const float p0[3], const float s[3], const float d[3],
+                                            const float e[3], float& t) {
     const float denom = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
-    if (denom > 1e-6f) {
-        t = ((p0[0] - s[0]) * n[0] + (p0[1] - s[1]) * n[1] + (p0[2] - s[2]) * n[2]) / denom;
-        return t > -1e-6f;
-    }
-    return false;
+    if (!(denom > 1e-6f)) return false;  // intersectPlane: src/geometryMod.f90:234
+    const float gs = (p0[0] - s[0]) * n[0] + (p0[1] - s[1]) * n[1] + (p0[2] - s[2]) * n[2];
+    const float ge = (p0[0] - e[0]) * n[0] + (p0[1] - e[1]) * n[1] + (p0[2] - e[2]) * n[2];
+    t = gs / denom;
+    return gs >= 0.f && ge < 0.f;
 }
-__device__ __forceinline__ bool disk_hit(const float n[3], const float p0[3], float radius, const float s[3], const float d[3],
-                                         float& t, float& r) {
-    t = 0.f;
-    if (plane_hit(n, p0, s, d, t)) {
-        const float vx = s[0] + d[0] * t - p0[0], vy = s[1] + d[1] * t - p0[1], vz = s[2] + d[2] * t - p0[2];
-        r = sqrtf(vx * vx + vy * vy + vz * vz);
-        return r <= radius;
-    }
-    return false;
+__device__ __forceinline__ float hit_radius(const float p0[3], const float s[3], const float d[3], float t) {
+    const float vx = s[0] + d[0] * t - p0[0], vy = s[1] + d[1] * t - p0[1], vz = s[2] + d[2] * t - p0[2];
+    return sqrtf(vx * vx + vy * vy + vz * vz);
 }
 __device__ __forceinline__ int nint_pos(float v) { return (int)floorf(v + 0.5f); }  // Fortran nint for v >= 0
-__device__ __noinline__ int detector_bin(const DevDet& D, const float s[3], const float d[3], float sep) {
-    float t = 0.f, r = 0.f;
+__device__ __noinline__ int detector_bin(const DevDet& D, const float s[3], const float d[3], const float e[3]) {
+    float t = 0.f;
     switch (D.kind) {
-        case 1: {  // circle
-            if (!disk_hit(D.dir, D.pos, D.q[0], s, d, t, r)) return 0;
-            if (t <= 0.f || t > sep) return 0;
+        case 1: {  // circle :147-164
+            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
+            const float r = hit_radius(D.pos, s, d, t);
+            if (!(r <= D.q[0])) return 0;
             return min(nint_pos(r / D.q[1]) + 1, D.nbins);
         }
-        case 2: {  // annulus: not inside r1, inside r2 (both tests share the plane hit -> same t)
-            const bool h1 = disk_hit(D.dir, D.pos, D.q[0], s, d, t, r);
-            const bool h2 = disk_hit(D.dir, D.pos, D.q[1], s, d, t, r);
-            if (h1 || !h2) return 0;
-            if (t <= 0.f || t > sep) return 0;
+        case 2: {  // annulus :212-244: not inside r1, inside r2
+            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
+            const float r = hit_radius(D.pos, s, d, t);
+            if (r <= D.q[0] || !(r <= D.q[1])) return 0;
             return max(min(nint_pos((r - D.q[0]) / D.q[2]) + 1, D.nbins), 1);
         }
         case 3: {  // fibre: 4f relay in the thin-lens approximation :323-393
-            if (!disk_hit(D.dir, D.pos, D.q[0], s, d, t, r)) return 0;
-            if (t <= 0.f || t > sep) return 0;
+            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
+            const float r = hit_radius(D.pos, s, d, t);
+            if (!(r <= D.q[0])) return 0;
             float costt = fminf(D.dir[0] * d[0] + D.dir[1] * d[1] + D.dir[2] * d[2], 1.0f);
             const float sintt = sqrtf(1.0f - costt * costt);
             float gradient = sintt / costt;
@@ -334,7 +353,7 @@ __device__ __noinline__ int detector_bin(const DevDet& D, const float s[3], cons
             if (angle > D.q[8] || radius > D.q[9]) return 0;
             return min(nint_pos(fabsf(radius) / D.q[10]) + 1, D.nbins);
         }
-        case 4: {  // camera :447-469 + record_hit_2D_sub (bins the segment START, adds 1)
+        case 4: {  // camera :447-469 + record_hit_2D_sub (no pointSep test, bins the segment START, adds 1)
             const float dn = d[0] * D.dir[0] + d[1] * D.dir[1] + d[2] * D.dir[2];
             const float tt = ((D.pos[0] - s[0]) * D.dir[0] + (D.pos[1] - s[1]) * D.dir[1] + (D.pos[2] - s[2]) * D.dir[2]) / dn;
             if (!(tt >= 0.f)) return 0;
@@ -506,11 +525,20 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
 
     const int lane = threadIdx.x & 31;
     // ---- per-thread packet state
+    // The position is carried in FP64 and mirrored to FP32 for everything that is evaluated per sweep: with an FP32
+    // position a sphere-trace step d*dir smaller than half an ulp of the coordinate is lost, so rays grazing a wall stop
+    // converging (d stays >= eps forever); three DFMA per step keep the sub-ulp progress.
+    double posd[3] = {0, 0, 0};
     float pos[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, start[3] = {0, 0, 0};
+    auto advance = [&](float s, const float* v) {
+        posd[0] += (double)s * (double)v[0]; posd[1] += (double)s * (double)v[1]; posd[2] += (double)s * (double)v[2];
+        pos[0] = (float)posd[0]; pos[1] = (float)posd[1]; pos[2] = (float)posd[2];
+    };
     float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
     float ds_pos_cur = 0.f, dnew_L = 0.f, dnew_cur = 0.f;
     int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0, fate = 0;
     bool tflag = false, launch = false;
+    int lost_why = 0;  // 1 step cap, 2 no crossing surface (reference: error stop), 3 bounces>1000, 4 outside all SDFs at launch, 5 emit
     unsigned long long pid = 0;
     uint32_t ev = 0;
     // ---- per-thread counters
@@ -518,10 +546,8 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
 
     auto segment_detect = [&]() {
         if (HASDET) {
-            const float ex = pos[0] - start[0], ey = pos[1] - start[1], ez = pos[2] - start[2];
-            const float sep = sqrtf(ex * ex + ey * ey + ez * ez);
             for (int i = 0; i < sc.n_det; ++i) {
-                const int b = detector_bin(sc.dets[i], start, dir, sep);
+                const int b = detector_bin(sc.dets[i], start, dir, pos);
                 if (b > 0) {
                     const float w = sc.dets[i].kind == 4 ? 1.0f : weight;
                     const unsigned long long q = (unsigned long long)__float2ll_rn(w * DET_FIX);
@@ -540,7 +566,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             const long long k = (long long)(pid - P.id_offset);
             P.out_fate[k] = f;
             if (P.out_nscatt) P.out_nscatt[k] = pk_nscatt;
-            if (P.out_events) P.out_events[k] = (int)ev;
+            if (P.out_events) P.out_events[k] = f == FATE_LOST ? -lost_why : (int)ev;
             if (P.out_pos) { P.out_pos[3 * k] = pos[0]; P.out_pos[3 * k + 1] = pos[1]; P.out_pos[3 * k + 2] = pos[2]; }
         }
         c_bounces += bounces;
@@ -560,27 +586,28 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             else if (ds_pos_cur >= 0.f && dnew_cur >= 0.f) surf = layer;
             else surf = -1;  // reference: error stop (:276)
             if (surf < 0) {
+                lost_why = 2;
                 retire(FATE_LOST);
             } else {
-                float N[3];
-                surface_normal(P, sc, surf - 1, pos[0], pos[1], pos[2], N);
+                double N[3];
+                surface_normal(P, sc, surf - 1, posd[0], posd[1], posd[2], N);
                 uint32_t w[4];
                 philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
                 const float n1 = sc.tops[layer - 1].n, n2 = sc.tops[new_layer - 1].n;
-                const float probe[3] = {pos[0] + dstep * dir[0], pos[1] + dstep * dir[1], pos[2] + dstep * dir[2]};
+                const float old_dir[3] = {dir[0], dir[1], dir[2]};
                 bool rflag;
                 reflect_refract(dir, N, n1, n2, u01(w[0]), rflag);
                 if (!rflag) {  // transmitted :284-303
                     layer = new_layer;
                     if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
                     taurun += dstep * sc.tops[layer - 1].kappa;
-                    pos[0] = probe[0]; pos[1] = probe[1]; pos[2] = probe[2];  // Q4: probe used the old direction
+                    advance(dstep, old_dir);  // Q4: the probe point was computed with the pre-refraction direction
                     segment_detect();
                     state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
                 } else {  // reflected :304-317
                     start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
                     ++bounces;
-                    if (bounces > 1000) retire(FATE_LOST);
+                    if (bounces > 1000) { lost_why = 3; retire(FATE_LOST); }
                     else state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
                 }
                 qs = 0.f;
@@ -643,11 +670,13 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                 for (;;) {  // emitter rejection + start-voxel rejection (kernelsMod.f90:1937-1943, quirk Q6)
                     philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
                     const bool ok = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]), pos, dir);
+                    posd[0] = pos[0]; posd[1] = pos[1]; posd[2] = pos[2];
                     if (ok && in_grid(P, pos[0], pos[1], pos[2])) break;
                     ++c_retries;
                     if (++guard > 100000) { guard = -1; break; }
                 }
                 if (guard < 0) {
+                    lost_why = 5;
                     retire(FATE_LOST);
                     continue;
                 }
@@ -664,10 +693,12 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
         if (state == ST_DONE) continue;
 
         // =============================== sweep ===============================
-        const float qx = pos[0] + qs * dir[0], qy = pos[1] + qs * dir[1], qz = pos[2] + qs * dir[2];
+        const float qx = (float)(posd[0] + (double)qs * (double)dir[0]), qy = (float)(posd[1] + (double)qs * (double)dir[1]),
+                    qz = (float)(posd[2] + (double)qs * (double)dir[2]);
         const Sweep S = sweep_all(sc, qx, qy, qz, layer);
         if (!launch) ++c_sweeps;
         if (++steps > P.max_steps) {
+            lost_why = 1;
             retire(FATE_LOST);
             continue;
         }
@@ -684,6 +715,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                     ++c_sweeps;
                     layer = S.L;
                     if (layer == 0) {  // the reference would index array(0); engine guard
+                        lost_why = 4;
                         retire(FATE_LOST);
                         continue;
                     }
@@ -707,13 +739,13 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                 const float from[3] = {pos[0], pos[1], pos[2]};
                 const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
                 if (taurun + t < tau) {
-                    pos[0] += sg * dstep * dir[0]; pos[1] += sg * dstep * dir[1]; pos[2] += sg * dstep * dir[2];
+                    advance(sg * dstep, dir);
                     taurun += t;
                     if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dstep, weight)) tflag = true;  // Q2: along +dir
                 } else {
                     const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
                     if (sg > 0.f) taurun += t;  // Q1: position not advanced
-                    else { pos[0] -= dd * dir[0]; pos[1] -= dd * dir[1]; pos[2] -= dd * dir[2]; }  // Q3: taurun not advanced
+                    else advance(-dd, dir);  // Q3: taurun not advanced
                     if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
                 }
                 segment_detect();
@@ -755,7 +787,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                     layer = S.L;
                     if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
                     taurun += dstep * sc.tops[layer - 1].kappa;
-                    pos[0] = qx; pos[1] = qy; pos[2] = qz;
+                    advance(dstep, dir);
                     segment_detect();
                     qs = 0.f;
                     state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
@@ -771,14 +803,14 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                 if (taurun + t < tau) {
                     taurun += t;
                     if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, d_cont, weight)) tflag = true;
-                    pos[0] += d_cont * dir[0]; pos[1] += d_cont * dir[1]; pos[2] += d_cont * dir[2];
+                    advance(d_cont, dir);
                     qs = 0.f;
                     state = ST_TRACE;
                 } else {
                     const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
                     taurun = tau;
                     const float from[3] = {pos[0], pos[1], pos[2]};
-                    pos[0] += dd * dir[0]; pos[1] += dd * dir[1]; pos[2] += dd * dir[2];
+                    advance(dd, dir);
                     if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
                     after_trace = true;
                 }
@@ -829,7 +861,11 @@ __global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_inde
         const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
         if (top_index > 0) {
             dist[i] = eval_top_f(sc, top_index - 1, x, y, z);
-            if (normal) surface_normal(P, sc, top_index - 1, x, y, z, normal + 3 * i);
+            if (normal) {
+                double nn[3];
+                surface_normal(P, sc, top_index - 1, x, y, z, nn);
+                normal[3 * i] = (float)nn[0]; normal[3 * i + 1] = (float)nn[1]; normal[3 * i + 2] = (float)nn[2];
+            }
         } else
             for (int t = 0; t < P.n_top; ++t) dist[i * P.n_top + t] = eval_top_f(sc, t, x, y, z);
     }
@@ -838,7 +874,7 @@ __global__ void probe_fresnel_kernel(long long n, const float* dir, const float*
                                      const float* xi, float* dir_out, float* R, int* rflag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
-        const float N[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+        const double N[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
         bool rf;
         const float r = reflect_refract(d, N, n1[i], n2[i], xi[i], rf);
         dir_out[3 * i] = d[0]; dir_out[3 * i + 1] = d[1]; dir_out[3 * i + 2] = d[2];
@@ -873,7 +909,8 @@ __global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float s[3] = {start[3 * i], start[3 * i + 1], start[3 * i + 2]};
         const float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
-        const int b = detector_bin(D, s, d, len[i]);
+        const float e[3] = {s[0] + d[0] * len[i], s[1] + d[1] * len[i], s[2] + d[2] * len[i]};
+        const int b = detector_bin(D, s, d, e);
         hit[i] = b > 0;
         bin[i] = b;
     }

@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — photon packets/s of the run_MCRT hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (restated oracle) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, NCCL reduce of the tallies
+
+A "step" is one pass of the hot path over one batch of packets of the workload scene (default: the slab validation
+res/validation1.toml, BASELINE configs[1], 1e8 packets per step per GPU).  `value` = packets of all ranks / device time
+(CUDA events on the launch stream, max over ranks) with the scene resident in HBM; `e2e` = the same through the
+public API with host buffers: scene/source/detector upload + run + download of the absorb grid, detector bins and
+counters inside the timed region.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "photon_packets_per_s"
+UNIT = "packets/s"
+
+# ---- frozen per-operation table for the algorithmic work per packet: minimal FP32 op counts of the
+# reference formulas (add=mul=cmp=abs=min/max=1, fma=2, sqrt=div=1, sin/cos/log/atan=1), identical for CPU and GPU.
+F_AFFINE = 18
+F_PRIM = {1: 25, 2: 37, 3: 28, 4: 70, 5: 23, 6: 47, 7: 47, 8: 80, 9: 45, 10: 23}
+F_FRESNEL, F_HG, F_DET_CIRCLE, F_VOXEL, F_EMIT = 45, 60, 30, 9, 20
+
+
+def flops_per_sweep(scene) -> float:
+    """One evaluation of ALL top-level SDFs (what `cnts += N` counts, src/inttau2.f90:67)."""
+    total = 0.0
+    kinds = scene.kind
+    for k in kinds:
+        if int(k) in F_PRIM:
+            total += F_PRIM[int(k)] + F_AFFINE
+        else:
+            total += 8  # csg op / modifier arithmetic
+    return total
+
+
+def algorithmic_flops_per_packet(scene, n_det: int, c: dict, n: float) -> float:
+    """W_flop of SURVEY §8(d) from measured expectations (counters of a run over n packets)."""
+    sweeps = c["sweeps"] / n
+    nscatt = c["nscatt"] / n
+    fres = c.get("fresnel_events", c["bounces"]) / n
+    w = sweeps * flops_per_sweep(scene)
+    w += fres * (F_FRESNEL + 4 * max(F_PRIM.get(int(scene.kind[0]), 30) + F_AFFINE, 1))
+    w += nscatt * F_HG
+    # straight segments tested against detectors: one per tauint2 call + one per crossing ~ (nscatt + 2)
+    w += (nscatt + 2.0) * n_det * F_DET_CIRCLE
+    w += F_EMIT + F_VOXEL
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_leg(cfg, seconds_target: float, threads: int = 0):
+    """Time the oracle (CPU restatement of the reference path) on a bounded sample of the same workload."""
+    from oracle import binding as O
+    O.build()
+    osc = O.OracleScene.from_config(cfg)
+    threads = threads or O.max_threads()
+    nv = int(np.prod(cfg.grid[0]))
+    # calibrate on a small sample, then size the timed sample for ~seconds_target of CPU work
+    r = osc.run(20000, cfg.iseed, rng_mode=1, nthreads=threads, grids=False, tally_mode=1)
+    rate = 20000 / max(r["seconds"], 1e-6)
+    n = int(min(max(rate * seconds_target, 50_000), 50_000_000))
+    r = osc.run(n, cfg.iseed + 1, rng_mode=1, nthreads=threads, grids=(nv <= 64_000_000), tally_mode=1)
+    return n, r["seconds"], r["counters"], threads
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores.  The Fortran
+    binary cannot be built in this image (no compiler, un-vendored deps: SURVEY F2/F3), so this is the oracle port."""
+    if rank != 0:
+        return
+    import rsmcrt_b200 as R
+    cfg = R.Config.load(ROOT / "res" / args.scene)
+    from oracle import binding as O
+    O.build()
+    osc = O.OracleScene.from_config(cfg)
+    threads = O.max_threads()
+    r = osc.run(20000, cfg.iseed, rng_mode=1, nthreads=threads, grids=False)
+    rate = 20000 / max(r["seconds"], 1e-6)
+    per_step = int(min(max(rate * args.cpu_seconds, 20_000), 20_000_000))
+    for w in range(args.warmup):
+        osc.run(max(per_step // 10, 1000), cfg.iseed + 10 + w, rng_mode=1, nthreads=threads, grids=False)
+    secs = 0.0
+    for s in range(args.steps):
+        r = osc.run(per_step, cfg.iseed + 100 + s, rng_mode=1, nthreads=threads, grids=False)
+        secs += r["seconds"]
+    value = per_step * args.steps / secs
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"res/{args.scene} (BASELINE configs[1] slab validation)", "packets_per_step": per_step,
+                   "note": "CPU restatement of the reference path (oracle/oracle.cpp, OpenMP); the gfortran/fpm binary cannot be built here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} packets/step x {args.steps} steps of res/{args.scene}, xoshiro256** per thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scene", default="validation1.toml")
+    ap.add_argument("--photons", type=float, default=1e8, help="packets per step per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline sample / reference step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pathlength", action="store_true", help="also accumulate path-length fluence (jmean)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import rsmcrt_b200 as R
+    from rsmcrt_b200 import api as A
+    R.load()  # fails loudly if the CUDA library is missing: no CPU fallback
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = R.Config.load(ROOT / "res" / args.scene)
+    scene = cfg.scene
+    kind, dp, nb, _ids = cfg.detectors
+    eng = R.Engine(1, device_ids=[local_rank])
+    eng.apply(cfg)
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(R.Engine.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        eng.comm_init(world, rank, bytes(uid.cpu().tolist()))
+
+    n_step = int(args.photons)
+    mode = A.TALLY_ABSORB | (A.TALLY_PATHLENGTH if args.pathlength else 0)
+    seed = cfg.iseed
+    nv = int(np.prod(cfg.grid[0]))
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- warm-up
+    for w in range(args.warmup):
+        eng.run(max(n_step // 20, 100_000), seed, id_offset=0, tally_mode=mode)
+    eng.reset_tallies()
+
+    # ---------------- timed region 1: device-resident (value)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for s in range(args.steps):
+        off = (s * world + rank) * n_step
+        eng.run_async(n_step, seed, id_offset=off, tally_mode=mode)
+        eng.wait()
+        dev_ms += eng.last_run_ms
+    red_ms = 0.0
+    if world > 1:  # the single NCCL reduce of the tallies at the end of the job (part of the timed region)
+        t0 = time.perf_counter()
+        eng.comm_reduce(0)
+        red_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count - launches0
+    total_ms = max_over_ranks(dev_ms + red_ms)
+    kernel_ms = max_over_ranks(dev_ms)
+    res = eng.fetch(absorb=False) if rank == 0 else None
+    packets = n_step * args.steps * world
+    value = packets / (total_ms * 1e-3)
+
+    # ---------------- timed region 2: end to end through the public API with host buffers (e2e)
+    eng.reset_tallies()
+    h2d = scene.kind.nbytes + scene.first_child.nbytes + scene.n_child.nbytes + scene.xform.nbytes + scene.params.nbytes + \
+        scene.top_node.nbytes + 4 * scene.mus.nbytes + 24 * 8 + (kind.nbytes + dp.nbytes + nb.nbytes)
+    d2h = nv * 4 + eng.det_bins_total * 8 + 8 * 8
+    src_k, src_s, src_p = cfg.source
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        off = (s * world + rank) * n_step
+        eng.set_scene(scene)                       # host -> device: flattened scene
+        eng.set_source(src_k, src_s, src_p)
+        eng.set_detectors(kind, dp, nb)            # (also zeroes the detector tallies, like the escape driver's reset)
+        eng.run(n_step, seed + 1, id_offset=off, tally_mode=mode)
+        out = eng.fetch(absorb=True)               # device -> host: absorb grid, detector bins, counters
+        _ = float(out["det_bins"].sum()) + out["counters"]["nscatt"]
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = packets / e2e_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    c = res["counters"]
+    n_run = c["launched"]
+    # ---------------- CPU baseline (rank 0, N=1 only) + algorithmic work from the oracle's counters
+    cpu = None
+    w_flop = algorithmic_flops_per_packet(scene, len(kind), c, n_run)
+    w_basis = "engine counters"
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu, secs, cc, threads = cpu_leg(cfg, args.cpu_seconds)
+        cpu = {"value": n_cpu / secs, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} packets of res/{args.scene} on {threads} OpenMP threads (oracle/oracle.cpp, FP64, xoshiro256**)"}
+        w_flop = algorithmic_flops_per_packet(scene, len(kind), cc, float(n_cpu))
+        w_basis = "oracle counters (reference algorithm, eps=1e-8)"
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s FP32 FMA at max clock
+    kern_rate = packets / (kernel_ms * 1e-3)
+    achieved = kern_rate * w_flop / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"res/{args.scene} (BASELINE configs[1]: slab validation, pencil beam, 500^3 grid, 2 circle detectors)",
+                   "packets_per_step_per_gpu": n_step, "tally_mode": mode, "parallelism": f"packets sharded over {world} GPU(s), NCCL reduce at end",
+                   "l2_note": "no HBM-resident input stream: scene (<1 KB) lives in shared memory; tally grid 500 MB > L2",
+                   "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                     "traffic": None,
+                     "note": "path is FP32/SFU-issue bound, not HBM or tensor (SURVEY 8d); achieved = packets/s x algorithmic flops/packet "
+                             f"({w_flop:.0f}, from {w_basis} x frozen op table in bench.py); peak = 148 SM x 128 lanes x 2 x sm_max_mhz "
+                             "(nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",
+                     "flops_per_packet": w_flop,
+                     "engine_sweeps_per_packet": c["sweeps"] / n_run, "engine_nscatt_per_packet": c["nscatt"] / n_run,
+                     "engine_lost_fraction": c["lost"] / n_run},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -214,11 +214,11 @@ int smcrt_probe_emit(smcrt_ctx* ctx, int64_t n, const double* xi4, double* pos, 
 int smcrt_probe_detector(smcrt_ctx* ctx, int det_index, int64_t n, const double* start, const double* dir,
                          const double* seg_len, int32_t* hit, int32_t* bin);
 /* Trace packets [id_offset, id_offset+n) exactly like smcrt_run (tallies ARE updated) and also return, per
-   packet: fate (0 absorbed, 1 left geometry/grid, 2 roulette, 3 lost), scatter count, final position.
-   Any out pointer may be NULL. */
+   packet: fate (0 absorbed, 1 left geometry/grid, 2 roulette, 3 lost), scatter count, final position, RNG events
+   consumed (lost packets: minus the engine-guard code) and sweeps executed.  Any out pointer may be NULL. */
 int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode,
                         int survival_bias, int32_t* fate, int32_t* nscatt, double* final_pos,
-                        int32_t* n_events);
+                        int32_t* n_events, int32_t* n_sweeps);
 /* The engine's Philox4x32-10 block for (seed, packet id, event index): 4 words. */
 int smcrt_probe_philox(uint64_t seed, uint64_t packet_id, uint32_t event, uint32_t out[4]);
 

@@ -328,11 +328,12 @@ class Engine:
         return hit, b
 
     def trace_packets(self, n, seed, id_offset=0, tally_mode=TALLY_ABSORB, survival_bias=False):
-        fate, nsc, ev = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        fate, nsc, ev, sw = (np.zeros(n, np.int32) for _ in range(4))
         pos = np.zeros((n, 3))
         check(self._L.smcrt_trace_packets(self._h, n, int(seed), int(id_offset), int(tally_mode), int(survival_bias),
-                                          _p(fate, C.c_int32), _p(nsc, C.c_int32), _p(pos, C.c_double), _p(ev, C.c_int32)))
-        return {"fate": fate, "nscatt": nsc, "pos": pos, "events": ev}
+                                          _p(fate, C.c_int32), _p(nsc, C.c_int32), _p(pos, C.c_double), _p(ev, C.c_int32),
+                                          _p(sw, C.c_int32)))
+        return {"fate": fate, "nscatt": nsc, "pos": pos, "events": ev, "sweeps": sw}
 
 
 def philox(seed, packet_id, event):

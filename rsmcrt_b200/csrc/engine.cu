@@ -592,7 +592,7 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
 
 static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
                          int survival, double threshold, double chance, int* out_fate, int* out_nscatt, int* out_events,
-                         float* out_pos) {
+                         float* out_pos, int* out_sweeps = nullptr) {
     KParams P;
     fill_params(c, D, P);
     P.nphotons = nphotons; P.id_offset = (unsigned long long)id_offset;
@@ -600,7 +600,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.tally_mode = tally_mode; P.survival = survival ? 1 : 0;
     P.threshold = (float)(threshold > 0 ? threshold : 0.01);  // THRESHOLD, src/constants.f90:28
     P.chance = (float)(chance > 0 ? chance : 0.1);            // CHANCE, src/constants.f90:30
-    P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos;
+    P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps;
     CU(cudaSetDevice(D.dev));
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     const int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
@@ -932,16 +932,16 @@ extern "C" int smcrt_probe_detector(smcrt_ctx* c, int det_index, int64_t n, cons
     return 0;
 }
 extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode, int survival_bias,
-                                   int32_t* fate, int32_t* nscatt, double* final_pos, int32_t* n_events) {
+                                   int32_t* fate, int32_t* nscatt, double* final_pos, int32_t* n_events, int32_t* n_sweeps) {
     int rc = check_ready(c);
     if (rc) return rc;
     if (c->pending) return set_err("smcrt_trace_packets: a run is pending");
     DeviceState& D = c->devs[0];
     CU(cudaSetDevice(D.dev));
-    DevBuf f, s, e, p;
-    if (f.alloc(4 * n) || s.alloc(4 * n) || e.alloc(4 * n) || p.alloc(12 * n)) return PROBE_FAIL();
+    DevBuf f, s, e, p, w;
+    if (f.alloc(4 * n) || s.alloc(4 * n) || e.alloc(4 * n) || p.alloc(12 * n) || w.alloc(4 * n)) return PROBE_FAIL();
     CU(cudaMemset(f.p, 0xff, 4 * n));
-    rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>());
+    rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>(), w.as<int>());
     if (rc) return rc;
     CU(cudaStreamSynchronize(D.stream));
     float t = 0;
@@ -950,6 +950,7 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     if (fate) CU(cudaMemcpy(fate, f.p, 4 * n, cudaMemcpyDeviceToHost));
     if (nscatt) CU(cudaMemcpy(nscatt, s.p, 4 * n, cudaMemcpyDeviceToHost));
     if (n_events) CU(cudaMemcpy(n_events, e.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (n_sweeps) CU(cudaMemcpy(n_sweeps, w.p, 4 * n, cudaMemcpyDeviceToHost));
     if (final_pos && down_f(p, final_pos, 3 * n)) return PROBE_FAIL();
     return 0;
 }

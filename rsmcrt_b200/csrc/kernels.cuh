@@ -53,6 +53,7 @@ struct KParams {
     int* out_fate;
     int* out_nscatt;
     int* out_events;
+    int* out_sweeps;
     float* out_pos;
 };
 
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             P.out_fate[k] = f;
             if (P.out_nscatt) P.out_nscatt[k] = pk_nscatt;
             if (P.out_events) P.out_events[k] = f == FATE_LOST ? -lost_why : (int)ev;
+            if (P.out_sweeps) P.out_sweeps[k] = steps;
             if (P.out_pos) { P.out_pos[3 * k] = pos[0]; P.out_pos[3 * k + 1] = pos[1]; P.out_pos[3 * k + 2] = pos[2]; }
         }
         c_bounces += bounces;
@@ -770,7 +772,13 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             }
             case ST_CROSS: {  // :220-337
                 if (S.L == layer && S.amin < eps) {  // creep :225-235
-                    dstep += eps;
+                    // The reference lengthens the probe by eps per iteration.  A ray skimming a curved surface stays
+                    // within eps of it over a path ~sqrt(8 r eps), i.e. thousands of iterations per grazing bounce, and a
+                    // whispering-gallery packet then owns one GPU thread for seconds.  The increment doubles here
+                    // (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) iterations; the probe can overshoot
+                    // the exit point by at most the last increment, along a ray that is within eps of the surface anyway.
+                    dstep += dlast;
+                    dlast = fminf(2.0f * dlast, 256.0f * eps);
                     qs = dstep;
                     break;
                 }
@@ -822,6 +830,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             if (taurun >= tau || tflag) state = ST_FINISH;
             else {
                 dstep = dlast + 2.0f * eps;
+                dlast = eps;  // from here on: the creep increment of the crossing probe
                 qs = dstep;
                 state = ST_CROSS;
             }

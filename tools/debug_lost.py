@@ -24,4 +24,5 @@ for name, n in (("scat_test.toml", 400000), ("validation2.toml", 4000), ("valida
             o = osc.run(1, cfg.iseed, id_offset=int(i), per_packet=True, grids=False, tally_mode=mode)
             print(f"   id={i} why={-g['events'][i]} pos={g['pos'][i]} nsc={g['nscatt'][i]} | oracle fate={o['fate'][0]} nsc={o['nscatt'][0]} "
                   f"pos={o['pos'][0]} sweeps={o['counters']['sweeps']}")
-    e.close()
+    pass
+    print("   sweeps per packet: mean %.1f  p99 %d  max %d   top5 %s" % (g["sweeps"].mean(), np.percentile(g["sweeps"], 99), g["sweeps"].max(), np.sort(g["sweeps"])[-5:]))

@@ -183,6 +183,80 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
     return T(1e30);
 }
 
+// Distance AND directional step bound of one primitive (FP32 transport path).
+// The reference advances by min_i |d_i| (sphere tracing, src/inttau2.f90:155-192): |d_i| is a lower bound of the distance
+// to surface i in ANY direction.  Along the packet's own ray a tighter bound exists for the primitives with a closed-form
+// ray intersection: the exact distance t_i >= |d_i| at which the ray meets surface i (+inf if it never does).  Stepping
+// by min_i max(|d_i|, t_i) visits the same boundary points with the same optical depth (kappa is constant inside a
+// layer and deposits are linear along a straight ray), in one step instead of O(log(1/eps)/(1-cos)).
+// Kinds without a closed form keep b = |d| (plain sphere tracing).  *exact tells whether b is an exact hit distance.
+#define SMCRT_BIG 3.0e38f
+__device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz,
+                                               float& bound, bool& exact) {
+    float px, py, pz, vx = ux, vy = uy, vz = uz;
+    if (P.xf == XF_IDENTITY) {
+        px = x; py = y; pz = z;
+    } else if (P.xf == XF_TRANSLATE) {
+        px = x + P.m[3]; py = y + P.m[7]; pz = z + P.m[11];
+    } else {
+        px = P.m[0] * x + P.m[1] * y + P.m[2] * z + P.m[3];
+        py = P.m[4] * x + P.m[5] * y + P.m[6] * z + P.m[7];
+        pz = P.m[8] * x + P.m[9] * y + P.m[10] * z + P.m[11];
+        vx = P.m[0] * ux + P.m[1] * uy + P.m[2] * uz;
+        vy = P.m[4] * ux + P.m[5] * uy + P.m[6] * uz;
+        vz = P.m[8] * ux + P.m[9] * uy + P.m[10] * uz;
+    }
+    const float* q = P.p;
+    if (P.kind == 1) {  // sphere: t^2 + 2 b t + c = 0 with c = |p|^2 - r^2 = d (|p| + r)  (no cancellation near the surface)
+        const float len = sqrtf(px * px + py * py + pz * pz);
+        const float d = len - q[0];
+        const float b = px * vx + py * vy + pz * vz;
+        const float c = d * (len + q[0]);
+        // discriminant b^2 - c = r^2 - |p - b v|^2 (v unit): the rejection form does not subtract two O(|p|^2) numbers,
+        // which matters for grazing rays (disc -> 0)
+        const float rx = px - b * vx, ry = py - b * vy, rz = pz - b * vz;
+        const float disc = q[0] * q[0] - (rx * rx + ry * ry + rz * rz);
+        float t = SMCRT_BIG;
+        if (disc >= 0.f) {
+            const float w = -(b + copysignf(sqrtf(disc), b));  // numerically stable root pair {w, c/w}
+            const float t1 = w, t2 = (w != 0.f) ? c / w : SMCRT_BIG;
+            const float lo = fminf(t1, t2), hi = fmaxf(t1, t2);
+            t = lo > 0.f ? lo : (hi > 0.f ? hi : SMCRT_BIG);
+        }
+        bound = fmaxf(fabsf(d), t);
+        exact = true;
+        return d;
+    }
+    if (P.kind == 2) {  // box: slab method in the local frame
+        const float dx = fabsf(px) - q[0], dy = fabsf(py) - q[1], dz = fabsf(pz) - q[2];
+        const float ox = fmaxf(dx, 0.f), oy = fmaxf(dy, 0.f), oz = fmaxf(dz, 0.f);
+        const float d = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(dx, fmaxf(dy, dz)), 0.f);
+        const float ix = 1.0f / vx, iy = 1.0f / vy, iz = 1.0f / vz;  // +-inf for an axis-parallel ray: handled by min/max
+        const float sx = copysignf(q[0], vx), sy = copysignf(q[1], vy), sz = copysignf(q[2], vz);
+        const float n1 = (-sx - px) * ix, f1 = (sx - px) * ix;
+        const float n2 = (-sy - py) * iy, f2 = (sy - py) * iy;
+        const float n3 = (-sz - pz) * iz, f3 = (sz - pz) * iz;
+        const float tn = fmaxf(n1, fmaxf(n2, n3)), tf = fminf(f1, fminf(f2, f3));  // fmaxf/fminf drop a NaN (0*inf) operand
+        float t = SMCRT_BIG;
+        if (tf >= 0.f && tn <= tf) t = tn > 0.f ? tn : tf;
+        bound = fmaxf(fabsf(d), t);
+        exact = true;
+        return d;
+    }
+    if (P.kind == 10) {  // plane
+        const float d = px * q[0] + py * q[1] + pz * q[2];
+        const float dn = vx * q[0] + vy * q[1] + vz * q[2];
+        const float t = -d / dn;
+        bound = fmaxf(fabsf(d), (t > 0.f && t < SMCRT_BIG) ? t : SMCRT_BIG);
+        exact = true;
+        return d;
+    }
+    const float d = eval_prim<float>(P, x, y, z);
+    bound = fabsf(d);
+    exact = false;
+    return d;
+}
+
 template <typename T>
 __device__ __forceinline__ T csg_op(int kind, T d1, T d2, T k) {  // src/sdfs/sdfModifiers.f90:428-491
     switch (kind) {

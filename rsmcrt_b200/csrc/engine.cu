@@ -129,7 +129,7 @@ struct smcrt_ctx {
     float Tdir[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     // knobs
     double eps0 = 1e-8, eps_rel = 4.76837158203125e-07 /* 2^-21 = 4 ulp(1.0f) */;
-    long long max_steps = 2000000;
+    long long max_steps = 200000;
     // run state
     bool comm_all = false;    // in-process communicator over devs
     bool comm_rank = false;   // one-rank-per-process communicator (devs.size()==1)
@@ -137,6 +137,9 @@ struct smcrt_ctx {
     double last_ms = 0;
     long long launches = 0;
     bool pending = false;
+    long long dbg_pid = -1;
+    float* dbg_log = nullptr;
+    int dbg_cap = 0;
 };
 
 static int n_voxels(const smcrt_ctx* c, size_t* out) {
@@ -592,7 +595,7 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
 
 static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
                          int survival, double threshold, double chance, int* out_fate, int* out_nscatt, int* out_events,
-                         float* out_pos, int* out_sweeps = nullptr) {
+                         float* out_pos, int* out_sweeps = nullptr, float* out_dbg = nullptr) {
     KParams P;
     fill_params(c, D, P);
     P.nphotons = nphotons; P.id_offset = (unsigned long long)id_offset;
@@ -600,7 +603,8 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.tally_mode = tally_mode; P.survival = survival ? 1 : 0;
     P.threshold = (float)(threshold > 0 ? threshold : 0.01);  // THRESHOLD, src/constants.f90:28
     P.chance = (float)(chance > 0 ? chance : 0.1);            // CHANCE, src/constants.f90:30
-    P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps;
+    P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps; P.out_dbg = out_dbg;
+    P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
     CU(cudaSetDevice(D.dev));
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     const int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
@@ -938,10 +942,17 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     if (c->pending) return set_err("smcrt_trace_packets: a run is pending");
     DeviceState& D = c->devs[0];
     CU(cudaSetDevice(D.dev));
-    DevBuf f, s, e, p, w;
+    DevBuf f, s, e, p, w, dbg;
     if (f.alloc(4 * n) || s.alloc(4 * n) || e.alloc(4 * n) || p.alloc(12 * n) || w.alloc(4 * n)) return PROBE_FAIL();
+    const char* dbg_pid_s = getenv("SMCRT_DEBUG_PID");  // engine diagnostics: boundary-event log of one packet
+    DevBuf dlog;
+    const int dcap = 256;
+    if (dbg_pid_s && (dlog.alloc(64 * dcap) || cudaMemset(dlog.p, 0, 64 * dcap) != cudaSuccess)) return PROBE_FAIL();
+    c->dbg_pid = dbg_pid_s ? atoll(dbg_pid_s) : -1; c->dbg_log = dbg_pid_s ? dlog.as<float>() : nullptr; c->dbg_cap = dcap;
+    const char* dbg_path = getenv("SMCRT_DEBUG_LOST");  // engine diagnostics: dump the state of step-capped packets
+    if (dbg_path && (dbg.alloc(48 * n) || cudaMemset(dbg.p, 0, 48 * n) != cudaSuccess)) return PROBE_FAIL();
     CU(cudaMemset(f.p, 0xff, 4 * n));
-    rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>(), w.as<int>());
+    rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>(), w.as<int>(), dbg_path ? dbg.as<float>() : nullptr);
     if (rc) return rc;
     CU(cudaStreamSynchronize(D.stream));
     float t = 0;
@@ -951,6 +962,32 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     if (nscatt) CU(cudaMemcpy(nscatt, s.p, 4 * n, cudaMemcpyDeviceToHost));
     if (n_events) CU(cudaMemcpy(n_events, e.p, 4 * n, cudaMemcpyDeviceToHost));
     if (n_sweeps) CU(cudaMemcpy(n_sweeps, w.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (dbg_pid_s) {
+        std::vector<float> h(16 * dcap);
+        CU(cudaMemcpy(h.data(), dlog.p, 64 * dcap, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < dcap; ++k)
+            if (h[16 * k + 1] != 0.f) {
+                fprintf(stderr, "ev=%d", k + 1);
+                for (int q = 0; q < 16; ++q) fprintf(stderr, " %.9g", h[16 * k + q]);
+                fprintf(stderr, "\n");
+            }
+        c->dbg_log = nullptr;
+    }
+    if (dbg_path) {
+        std::vector<float> h(12 * (size_t)n);
+        std::vector<int> hf((size_t)n);
+        CU(cudaMemcpy(h.data(), dbg.p, 48 * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hf.data(), f.p, 4 * n, cudaMemcpyDeviceToHost));
+        if (FILE* fp = fopen(dbg_path, "a")) {
+            for (int64_t i = 0; i < n; ++i)
+                if (hf[i] == 3 && h[12 * i + 9] != 0.f) {
+                    fprintf(fp, "id=%lld", (long long)(id_offset + i));
+                    for (int k = 0; k < 12; ++k) fprintf(fp, " %.9g", h[12 * i + k]);
+                    fprintf(fp, "\n");
+                }
+            fclose(fp);
+        }
+    }
     if (final_pos && down_f(p, final_pos, 3 * n)) return PROBE_FAIL();
     return 0;
 }

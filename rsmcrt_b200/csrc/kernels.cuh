@@ -55,6 +55,10 @@ struct KParams {
     int* out_events;
     int* out_sweeps;
     float* out_pos;
+    float* out_dbg;  // 12 floats per packet, written when a packet hits the step cap (engine diagnostics)
+    long long dbg_pid;  // engine diagnostics: log the boundary events of this one packet into dbg_log (16 floats each)
+    float* dbg_log;
+    int dbg_cap;
 };
 
 enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE, C_DETHITS, C_COUNT };
@@ -110,7 +114,7 @@ __device__ __forceinline__ double eval_top_d(const KParams& P, const SceneView& 
 }
 // calcNormal (src/sdfs/sdf_base.f90:166-190): tetrahedral 4-tap gradient with h = 1e-6, in FP64 like the
 // reference (h is far below FP32 resolution); only executed at refractive-index-mismatch crossings.
-__device__ __noinline__ void surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double n[3]) {
+__device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
     const double h = 1e-6;
     const double f1 = eval_top_d(P, sc, t, X + h, Y - h, Z - h);
     const double f2 = eval_top_d(P, sc, t, X - h, Y - h, Z + h);
@@ -118,24 +122,56 @@ __device__ __noinline__ void surface_normal(const KParams& P, const SceneView& s
     const double f4 = eval_top_d(P, sc, t, X + h, Y + h, Z + h);
     double nx = f1 - f2 - f3 + f4, ny = -f1 - f2 + f3 + f4, nz = -f1 + f2 - f3 + f4;
     const double il = rsqrt(nx * nx + ny * ny + nz * nz);
-    n[0] = nx * il; n[1] = ny * il; n[2] = nz * il;
+    return make_double3(nx * il, ny * il, nz * il);
+}
+
+// FP64 "polish" of a boundary hit.  The FP32 march stops within eps ~ 4 ulp(|pos|) of the surface, the
+// reference within 1e-8.  Reflecting/refracting a few 1e-7 off the surface perturbs the impact parameter of every bounce,
+// which pumps packets into whispering-gallery orbits of (unions of) spheres ~100x faster than the reference does.  One
+// Newton step of the FP64 distance along the ray puts the packet on the surface to ~1e-12 before the normal is taken.
+// Returns the signed distance moved along the ray (|t| <= tmax).
+__device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
+                                          double uz, double tmax) {
+    const double h = 1e-6;
+    double moved = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {  // two Newton steps: the second removes the curvature term of the first
+        const double f0 = eval_top_d(P, sc, t, X, Y, Z);
+        const double f1 = eval_top_d(P, sc, t, X + h * ux, Y + h * uy, Z + h * uz);
+        const double g = (f1 - f0) / h;
+        if (!(fabs(g) > 1e-3)) break;  // grazing: the along-ray root is ill-conditioned, keep the landing point
+        const double dt = fmin(fmax(-f0 / g, -tmax - moved), tmax - moved);
+        X += dt * ux; Y += dt * uy; Z += dt * uz;
+        moved += dt;
+    }
+    return moved;
 }
 
 // Evaluate ALL top-level SDFs at (x,y,z): min|d|, min d, argmax of the negatives (the reference's
 // maxloc(ds, mask=ds<0): innermost surface wins, ties -> lowest index, none -> 0), value there, and the value of
 // SDF `layer` (1-based).   src/inttau2.f90:63-68,80-84,135-139,179-183,216-221,229-234
 struct Sweep {
-    float amin, smin, dL, dcur;
+    float amin, smin, dL, dcur, bmin;
     int L;
+    bool bexact;
 };
-__device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y, float z, int layer) {
+__device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y, float z, float ux, float uy, float uz, int layer) {
     Sweep s;
-    s.amin = 3.0e38f; s.smin = 3.0e38f; s.dL = -3.0e38f; s.dcur = 0.f; s.L = 0;
+    s.amin = SMCRT_BIG; s.smin = SMCRT_BIG; s.dL = -SMCRT_BIG; s.dcur = 0.f; s.L = 0; s.bmin = SMCRT_BIG; s.bexact = false;
     const int n = sc.n_top;
     for (int i = 0; i < n; ++i) {
-        const float d = eval_top_f(sc, i, x, y, z);
+        float d, b;
+        bool ex;
+        const int mode = sc.tops[i].mode, first = sc.tops[i].first;
+        if (mode == 0) d = eval_prim_ray(sc.prims[first], x, y, z, ux, uy, uz, b, ex);
+        else {
+            d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[i].count, x, y, z);
+            b = fabsf(d);
+            ex = false;
+        }
         s.amin = fminf(s.amin, fabsf(d));
         s.smin = fminf(s.smin, d);
+        if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
         if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
         if (i + 1 == layer) s.dcur = d;
     }
@@ -146,10 +182,14 @@ __device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y
 // src/surfaces.f90:14-127 (fresnel :86-127, reflect :42-55, refract :57-84).  Returns the coefficient; sets rflag.
 // Evaluated in FP64: it runs once per index-mismatch crossing (cold), and R(theta) is ill-conditioned next to the
 // total-internal-reflection knee, where FP32 rounding of I.N alone moves R by ~1e-5.
-__device__ __noinline__ float reflect_refract(float d[3], const double N[3], float n1f, float n2f, float xi, bool& rflag) {
+struct Refl {
+    float x, y, z, R;
+    bool reflected;
+};
+__device__ __noinline__ Refl reflect_refract(float ux, float uy, float uz, double3 N, float n1f, float n2f, float xi) {
     const double n1 = n1f, n2 = n2f;
-    const double dx = d[0], dy = d[1], dz = d[2];
-    const double idn = dx * N[0] + dy * N[1] + dz * N[2];
+    const double dx = ux, dy = uy, dz = uz;
+    const double idn = dx * N.x + dy * N.y + dz * N.z;
     const double costt = fmin(fabs(idn), 1.0);
     const double sintt = sqrt(1.0 - costt * costt);
     const double eta = n1 / n2;
@@ -163,25 +203,27 @@ __device__ __noinline__ float reflect_refract(float d[3], const double N[3], flo
         const double b = (n1 * cost2 - n2 * costt) / (n1 * cost2 + n2 * costt);
         R = 0.5 * (a * a + b * b);
     }
+    Refl o;
+    o.R = (float)R;
     if ((double)xi <= R) {  // reflect: I - 2 (N.I) N
-        rflag = true;
+        o.reflected = true;
         const double k = 2.0 * idn;
-        d[0] = (float)(dx - k * N[0]); d[1] = (float)(dy - k * N[1]); d[2] = (float)(dz - k * N[2]);
+        o.x = (float)(dx - k * N.x); o.y = (float)(dy - k * N.y); o.z = (float)(dz - k * N.z);
     } else {  // refract with the normal flipped to oppose I
-        rflag = false;
+        o.reflected = false;
         double c1 = idn, sg = 1.0;
         if (c1 < 0.0) c1 = -c1;
         else sg = -1.0;
         const double c2 = sqrt(1.0 - eta * eta * (1.0 - c1 * c1));
         const double k = (eta * c1 - c2) * sg;
-        d[0] = (float)(eta * dx + k * N[0]); d[1] = (float)(eta * dy + k * N[1]); d[2] = (float)(eta * dz + k * N[2]);
+        o.x = (float)(eta * dx + k * N.x); o.y = (float)(eta * dy + k * N.y); o.z = (float)(eta * dz + k * N.z);
     }
-    return (float)R;
+    return o;
 }
 
 // ------------------------------------------------------------------------------------------------ scatter
 // photon%scatter, src/photon.f90:1045-1103 (mcxyz direction update). xi_c: cos(theta) draw, xi_p: phi draw.
-__device__ __forceinline__ void hg_scatter(float d[3], float hgg, float xi_c, float xi_p) {
+__device__ __forceinline__ void hg_scatter(float& dx_, float& dy_, float& dz_, float hgg, float xi_c, float xi_p) {
     // FP32-first algebra: the reference computes cos(theta) and then sin = sqrt(1 - cos^2), which cancels for the
     // forward-peaked angles HG favours.  Here 1 - cos(theta) is formed without cancellation:
     //   g = 0 : 1 - cos = 2 (1 - xi)
@@ -202,9 +244,9 @@ __device__ __forceinline__ void hg_scatter(float d[3], float hgg, float xi_c, fl
     const float cost = omc < 1.0f ? 1.0f - omc : opc - 1.0f;
     const float sint = sqrtf(omc * opc);
     float sinp, cosp;
-    sincosf(TWOPI_F * xi_p, &sinp, &cosp);
+    sincospif(2.0f * xi_p, &sinp, &cosp);  // exact range reduction, no slow path
     float ux, uy, uz;
-    const float nx = d[0], ny = d[1], nz = d[2];
+    const float nx = dx_, ny = dy_, nz = dz_;
     // sqrt(1 - nz^2) of the reference == sqrt(nx^2 + ny^2) for a unit vector, without the cancellation near the poles.
     // The reference switches to the polar form at |nz| > 1 - 1e-12, i.e. (in FP32) when nx = ny = 0 to rounding.
     const float t2 = nx * nx + ny * ny;
@@ -221,7 +263,7 @@ __device__ __forceinline__ void hg_scatter(float d[3], float hgg, float xi_c, fl
     const float l2 = ux * ux + uy * uy + uz * uz;
     const float il = rsqrtf(l2);
     const float il2 = il * (1.5f - 0.5f * l2 * il * il);  // one Newton step: rsqrt.approx is only ~2 ulp
-    d[0] = ux * il2; d[1] = uy * il2; d[2] = uz * il2;
+    dx_ = ux * il2; dy_ = uy * il2; dz_ = uz * il2;
 }
 
 // ------------------------------------------------------------------------------------------------ voxels
@@ -257,43 +299,40 @@ __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
     if (lane == leader) atomicAdd(grid + vox, sum);  // result unused -> RED.E.ADD.F32
 }
 
-// update_grids (src/inttau2.f90:367-465).  Default build: only the end-of-step voxel matters (packet dies when it
-// is outside the grid).  -Dpathlength: 3-D DDA depositing (segment length * weight) in every voxel crossed.
-template <bool PATHLEN>
-__device__ __forceinline__ bool walk_grid(const KParams& P, float fx, float fy, float fz, const float d[3], float len, float weight) {
-    if (!PATHLEN) {
-        return !in_grid(P, fx + d[0] * len, fy + d[1] * len, fz + d[2] * len);
-    } else {
-        // corner-origin coordinates in voxel units
-        const float X = (fx + P.gmax[0]), Y = (fy + P.gmax[1]), Z = (fz + P.gmax[2]);
-        int i = (int)floorf(X * P.inv_vox[0]), j = (int)floorf(Y * P.inv_vox[1]), k = (int)floorf(Z * P.inv_vox[2]);
-        if (i < 0 || i >= P.nxg || j < 0 || j >= P.nyg || k < 0 || k >= P.nzg) return true;  // :411-415
-        const int sx = d[0] > 0.f ? 1 : -1, sy = d[1] > 0.f ? 1 : -1, sz = d[2] > 0.f ? 1 : -1;
-        const float BIG = 3.0e38f;
-        float tx = d[0] != 0.f ? (((float)(i + (sx > 0)) * P.vox[0]) - X) / d[0] : BIG;
-        float ty = d[1] != 0.f ? (((float)(j + (sy > 0)) * P.vox[1]) - Y) / d[1] : BIG;
-        float tz = d[2] != 0.f ? (((float)(k + (sz > 0)) * P.vox[2]) - Z) / d[2] : BIG;
-        const float dtx = d[0] != 0.f ? P.vox[0] / fabsf(d[0]) : BIG;
-        const float dty = d[1] != 0.f ? P.vox[1] / fabsf(d[1]) : BIG;
-        const float dtz = d[2] != 0.f ? P.vox[2] / fabsf(d[2]) : BIG;
-        float t = 0.f;
-        bool out = false;
-        for (;;) {
-            const float tn = fminf(tx, fminf(ty, tz));
-            const long long v = (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
-            if (tn >= len) {
-                deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
-                break;
-            }
-            deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
-            t = tn;
-            if (tx <= ty && tx <= tz) { i += sx; tx += dtx; out = (i < 0 || i >= P.nxg); }
-            else if (ty <= tz)        { j += sy; ty += dty; out = (j < 0 || j >= P.nyg); }
-            else                      { k += sz; tz += dtz; out = (k < 0 || k >= P.nzg); }
-            if (out) break;  // :437-440
+// update_grids in -Dpathlength mode (src/inttau2.f90:408-445): 3-D DDA depositing (segment length * weight) into every
+// voxel the straight piece crosses.  Returns true when the walk starts or ends outside the grid (packet dies).
+// (Default build: only the end-of-step voxel matters, see the WALK macro of the kernel.)  Arguments by value: a pointer
+// argument would force the caller's state into local memory.
+__device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+    // corner-origin coordinates
+    const float X = (fx + P.gmax[0]), Y = (fy + P.gmax[1]), Z = (fz + P.gmax[2]);
+    int i = (int)floorf(X * P.inv_vox[0]), j = (int)floorf(Y * P.inv_vox[1]), k = (int)floorf(Z * P.inv_vox[2]);
+    if (i < 0 || i >= P.nxg || j < 0 || j >= P.nyg || k < 0 || k >= P.nzg) return true;  // :411-415
+    const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
+    const float BIG = 3.0e38f;
+    float tx = dx != 0.f ? (((float)(i + (sx > 0)) * P.vox[0]) - X) / dx : BIG;
+    float ty = dy != 0.f ? (((float)(j + (sy > 0)) * P.vox[1]) - Y) / dy : BIG;
+    float tz = dz != 0.f ? (((float)(k + (sz > 0)) * P.vox[2]) - Z) / dz : BIG;
+    const float dtx = dx != 0.f ? P.vox[0] / fabsf(dx) : BIG;
+    const float dty = dy != 0.f ? P.vox[1] / fabsf(dy) : BIG;
+    const float dtz = dz != 0.f ? P.vox[2] / fabsf(dz) : BIG;
+    float t = 0.f;
+    bool out = false;
+    for (;;) {
+        const float tn = fminf(tx, fminf(ty, tz));
+        const long long v = (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
+        if (tn >= len) {
+            deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
+            break;
         }
-        return out;
+        deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
+        t = tn;
+        if (tx <= ty && tx <= tz) { i += sx; tx += dtx; out = (i < 0 || i >= P.nxg); }
+        else if (ty <= tz)        { j += sy; ty += dty; out = (j < 0 || j >= P.nyg); }
+        else                      { k += sz; tz += dtz; out = (k < 0 || k >= P.nzg); }
+        if (out) break;  // :437-440
     }
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------ detectors
@@ -320,7 +359,10 @@ __device__ __forceinline__ float hit_radius(const float p0[3], const float s[3],
     return sqrtf(vx * vx + vy * vy + vz * vz);
 }
 __device__ __forceinline__ int nint_pos(float v) { return (int)floorf(v + 0.5f); }  // Fortran nint for v >= 0
-__device__ __noinline__ int detector_bin(const DevDet& D, const float s[3], const float d[3], const float e[3]) {
+__device__ __noinline__ int detector_bin(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
+                                         float e1, float e2) {
+    const DevDet& D = *Dp;
+    const float s[3] = {s0, s1, s2}, d[3] = {d0, d1, d2}, e[3] = {e0, e1, e2};
     float t = 0.f;
     switch (D.kind) {
         case 1: {  // circle :147-164
@@ -409,13 +451,21 @@ __device__ __forceinline__ void xform_pos(const float T[12], const float l[3], f
     o[1] = T[4] * l[0] + T[5] * l[1] + T[6] * l[2] + T[7];
     o[2] = T[8] * l[0] + T[9] * l[1] + T[10] * l[2] + T[11];
 }
-__device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]) {
+__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]);
+__device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1, float u2, float& x, float& y, float& z, float& dx,
+                                            float& dy, float& dz) {
+    float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
+    const bool ok = emit_packet_v(P, u0, u1, u2, pos, dir);
+    x = pos[0]; y = pos[1]; z = pos[2]; dx = dir[0]; dy = dir[1]; dz = dir[2];
+    return ok;
+}
+__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]) {
     const float* sp = P.sp;
     switch (P.src_kind) {
         case 1: {  // point :311-359
             pos[0] = sp[0]; pos[1] = sp[1]; pos[2] = sp[2];
             float sinp, cosp;
-            sincosf(u0 * TWOPI_F, &sinp, &cosp);
+            sincospif(2.0f * u0, &sinp, &cosp);
             const float cost = 2.0f * u1 - 1.0f;
             const float sint = sqrtf(1.0f - cost * cost);
             dir[0] = sint * cosp; dir[1] = sint * sinp; dir[2] = cost;
@@ -438,7 +488,7 @@ __device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1
         case 4: {  // circular :214-308
             const float r = sp[15] * sqrtf(u0);
             float s, c;
-            sincosf(u1 * TWOPI_F, &s, &c);
+            sincospif(2.0f * u1, &s, &c);
             float l[3];
             if (P.src_alt) { l[0] = r * c; l[1] = r * s; l[2] = 0.f; }
             else           { l[0] = 0.f;   l[1] = r * c; l[2] = r * s; }
@@ -461,7 +511,7 @@ __device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1
                 } else {
                     const float rad = P.src_sub == 2 ? beam * sqrtf(u0) : beam * sqrtf(-logf(1.0f - u0));
                     float s, c;
-                    sincosf(TWOPI_F * u1, &s, &c);
+                    sincospif(2.0f * u1, &s, &c);
                     l[0] = rad * c; l[1] = rad * s;
                 }
                 a[0] = l[0]; a[1] = l[1]; a[2] = 0.f;
@@ -477,7 +527,7 @@ __device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1
                     rad = mid + sp[20] * (gx * sqrtf(-2.0f * logf(sq) / sq));
                 }
                 float s, c;
-                sincosf(TWOPI_F * u2, &s, &c);
+                sincospif(2.0f * u2, &s, &c);
                 l[0] = rad * c; l[1] = rad * s;
                 a[0] = mid * c; a[1] = mid * s; a[2] = 0.f;  // all rays aim from the ring-mid radius
             }
@@ -500,14 +550,21 @@ __device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-enum : int { ST_TOP = 0, ST_BND_PROBE, ST_BND_RE, ST_TRACE, ST_CROSS, ST_FRESNEL, ST_FINISH, ST_INTERACT, ST_EMIT, ST_DONE };
+// Per-lane state machine.  Hot states own one sweep (evaluation of ALL SDFs at one point) per loop iteration:
+//   ST_MARCH     sweep at pos: the reference's top-of-loop / re-evaluation / sphere-trace evaluations (inttau2.f90:63,134,179)
+//   ST_BND_PROBE sweep at pos + (d+2eps) dir: on-boundary nudge probe (:77-84)
+//   ST_CROSS     sweep at pos + dstep dir: boundary-crossing probe and its creep (:213-235)
+// Cold states are resolved at the top of an iteration; each consumes exactly one Philox block, generated at ONE site:
+//   ST_FRESNEL   index-mismatch crossing (:248-317)        ST_INTERACT  scatter / absorb (kernelsMod.f90:1958-1974)
+//   ST_EMIT      launch a new packet (kernelsMod.f90:1937-1952)
+enum : int { ST_MARCH = 0, ST_BND_PROBE, ST_CROSS, ST_FRESNEL, ST_INTERACT, ST_EMIT, ST_DONE };
 enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST = 3 };
+enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYER = 4, LOST_EMIT = 5 };
 
 template <bool PATHLEN, bool HASDET>
 __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // ---- stage the scene in shared memory (16-byte vector copies)
-    {
+    {  // stage the scene in shared memory (16-byte vector copies)
         const int4* src = reinterpret_cast<const int4*>(P.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
@@ -523,319 +580,324 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
     sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
     sc.n_top = P.n_top;
     sc.n_det = P.n_det;
-
     const int lane = threadIdx.x & 31;
-    // ---- per-thread packet state
-    // The position is carried in FP64 and mirrored to FP32 for everything that is evaluated per sweep: with an FP32
-    // position a sphere-trace step d*dir smaller than half an ulp of the coordinate is lost, so rays grazing a wall stop
-    // converging (d stays >= eps forever); three DFMA per step keep the sub-ulp progress.
-    double posd[3] = {0, 0, 0};
-    float pos[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, start[3] = {0, 0, 0};
-    auto advance = [&](float s, const float* v) {
-        posd[0] += (double)s * (double)v[0]; posd[1] += (double)s * (double)v[1]; posd[2] += (double)s * (double)v[2];
-        pos[0] = (float)posd[0]; pos[1] = (float)posd[1]; pos[2] = (float)posd[2];
-    };
-    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
-    float ds_pos_cur = 0.f, dnew_L = 0.f, dnew_cur = 0.f;
-    int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0, fate = 0;
-    bool tflag = false, launch = false;
-    int lost_why = 0;  // 1 step cap, 2 no crossing surface (reference: error stop), 3 bounces>1000, 4 outside all SDFs at launch, 5 emit
+
+    // ---- packet state (scalars only: nothing here may be address-taken, or it lands in local memory)
+    // Position in FP64, mirrored to FP32 for everything evaluated per sweep: with an FP32 position a step smaller than
+    // half an ulp of a coordinate is lost and rays grazing a wall stop converging.
+    double pxd = 0, pyd = 0, pzd = 0;
+    float px = 0, py = 0, pz = 0, ux = 0, uy = 0, uz = 1, sx = 0, sy = 0, sz = 0;  // position, direction, segment start
+    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f, dnew_L = 0.f, dnew_cur = 0.f;
+    int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0;
+    bool tflag = false, launch = false, have_pid = false;
+    int phase = 0;  // of ST_MARCH: 0 = top of the tauint2 loop, 1 = re-evaluation after a boundary nudge, 2 = inside the sphere-trace loop
     unsigned long long pid = 0;
     uint32_t ev = 0;
-    // ---- per-thread counters
-    unsigned long long c_nscatt = 0, c_sweeps = 0, c_bounces = 0, c_launched = 0, c_retries = 0, c_lost = 0, c_dethits = 0;
+    unsigned int c_nscatt = 0, c_sweeps = 0, c_bounces = 0, c_launched = 0, c_retries = 0, c_lost = 0, c_dethits = 0;  // per thread: < 2^32
 
-    auto segment_detect = [&]() {
-        if (HASDET) {
-            for (int i = 0; i < sc.n_det; ++i) {
-                const int b = detector_bin(sc.dets[i], start, dir, pos);
-                if (b > 0) {
-                    const float w = sc.dets[i].kind == 4 ? 1.0f : weight;
-                    const unsigned long long q = (unsigned long long)__float2ll_rn(w * DET_FIX);
-                    const int slot = sc.dets[i].offset + b - 1;
-                    if (P.det_in_smem) atomicAdd(&sbins[slot], q);
-                    else atomicAdd(&P.det_bins[slot], q);
-                    ++c_dethits;
-                }
-            }
-            start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
-        }
-    };
-    auto retire = [&](int f) {  // packet is finished: publish the optional per-packet record, ask for a new one
-        fate = f;
-        if (P.out_fate) {
-            const long long k = (long long)(pid - P.id_offset);
-            P.out_fate[k] = f;
-            if (P.out_nscatt) P.out_nscatt[k] = pk_nscatt;
-            if (P.out_events) P.out_events[k] = f == FATE_LOST ? -lost_why : (int)ev;
-            if (P.out_sweeps) P.out_sweeps[k] = steps;
-            if (P.out_pos) { P.out_pos[3 * k] = pos[0]; P.out_pos[3 * k + 1] = pos[1]; P.out_pos[3 * k + 2] = pos[2]; }
-        }
-        c_bounces += bounces;
-        if (f == FATE_LOST) ++c_lost;
-        state = ST_EMIT;
-    };
+#define ADVANCE(S, VX, VY, VZ)                                                          \
+    do {                                                                                \
+        pxd += (double)(S) * (double)(VX); pyd += (double)(S) * (double)(VY); pzd += (double)(S) * (double)(VZ); \
+        px = (float)pxd; py = (float)pyd; pz = (float)pzd;                              \
+    } while (0)
+    // update_grids (inttau2.f90:367-465) for the straight piece (FX,FY,FZ) + t*(ux,uy,uz), t in [0, LEN]
+#define WALK(FX, FY, FZ, LEN)                                                                                         \
+    do {                                                                                                              \
+        if (PATHLEN) { if (walk_dda(P, FX, FY, FZ, ux, uy, uz, LEN, weight)) tflag = true; }                          \
+        else if (!in_grid(P, (FX) + ux * (LEN), (FY) + uy * (LEN), (FZ) + uz * (LEN))) tflag = true;                  \
+    } while (0)
+    // record_hit on the straight segment start -> pos for every detector (inttau2.f90:126-131,196-201,298-303,330-335)
+#define DETECT()                                                                                                      \
+    do {                                                                                                              \
+        if (HASDET) {                                                                                                 \
+            for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                   \
+                const int b_ = detector_bin(&sc.dets[i_], sx, sy, sz, ux, uy, uz, px, py, pz);                        \
+                if (b_ > 0) {                                                                                         \
+                    const float w_ = sc.dets[i_].kind == 4 ? 1.0f : weight;                                           \
+                    const unsigned long long q_ = (unsigned long long)__float2ll_rn(w_ * DET_FIX);                    \
+                    const int slot_ = sc.dets[i_].offset + b_ - 1;                                                    \
+                    if (P.det_in_smem) atomicAdd(&sbins[slot_], q_);                                                  \
+                    else atomicAdd(&P.det_bins[slot_], q_);                                                           \
+                    ++c_dethits;                                                                                      \
+                }                                                                                                     \
+            }                                                                                                         \
+            sx = px; sy = py; sz = pz;                                                                                \
+        }                                                                                                             \
+    } while (0)
+    // packet finished: publish the optional per-packet record and ask for a new packet
+#define RETIRE(FATE, WHY)                                                                                             \
+    do {                                                                                                              \
+        if (P.out_fate) {                                                                                             \
+            const long long k_ = (long long)(pid - P.id_offset);                                                      \
+            P.out_fate[k_] = (FATE);                                                                                  \
+            if (P.out_nscatt) P.out_nscatt[k_] = pk_nscatt;                                                           \
+            if (P.out_events) P.out_events[k_] = (FATE) == FATE_LOST ? -(WHY) : (int)ev;                              \
+            if (P.out_sweeps) P.out_sweeps[k_] = steps;                                                               \
+            if (P.out_pos) { P.out_pos[3 * k_] = px; P.out_pos[3 * k_ + 1] = py; P.out_pos[3 * k_ + 2] = pz; }        \
+        }                                                                                                             \
+        c_bounces += bounces;                                                                                         \
+        if ((FATE) == FATE_LOST) ++c_lost;                                                                            \
+        state = ST_EMIT; have_pid = false;                                                                            \
+    } while (0)
+    // end of tauint2 (inttau2.f90:354-362) + loop test of kernelsMod.f90:1958
+#define FINISH()                                                                                                      \
+    do {                                                                                                              \
+        if (fabsf(px) > P.gmax[0] || fabsf(py) > P.gmax[1] || fabsf(pz) > P.gmax[2]) tflag = true;                    \
+        if (tflag) RETIRE(FATE_ESCAPED, 0);                                                                           \
+        else state = ST_INTERACT;                                                                                     \
+    } while (0)
+    // straight piece ended on a surface: detectors, then probe across it (inttau2.f90:196-221)
+#define AFTER_TRACE(DL, EPS)                                                                                          \
+    do {                                                                                                              \
+        DETECT();                                                                                                     \
+        if (taurun >= tau || tflag) FINISH();                                                                         \
+        else { dstep = (DL) + 2.0f * (EPS); dlast = (EPS); qs = dstep; state = ST_CROSS; }                            \
+    } while (0)
+#define NEXT_LOOP() /* `do while (taurun <= tau)` head, inttau2.f90:61 */                                             \
+    do {                                                                                                              \
+        qs = 0.f;                                                                                                     \
+        if (tflag || !(taurun <= tau)) FINISH();                                                                      \
+        else { state = ST_MARCH; phase = 0; }                                                                      \
+    } while (0)
 
     for (;;) {
-        // =============================== cold events ===============================
-        if (state == ST_FRESNEL) {
-            // src/inttau2.f90:248-317: pick the surface that is actually being crossed, normal, Fresnel
-            const float ds_pos_new = eval_top_f(sc, new_layer - 1, pos[0], pos[1], pos[2]);  // ds(new_layer)
-            int surf;
-            if (dnew_L < 0.f && ds_pos_new >= 0.f) surf = new_layer;
-            else if (dnew_cur >= 0.f && ds_pos_cur < 0.f) surf = layer;
-            else if (dnew_L < 0.f && dnew_cur < 0.f) surf = new_layer;
-            else if (ds_pos_cur >= 0.f && dnew_cur >= 0.f) surf = layer;
-            else surf = -1;  // reference: error stop (:276)
-            if (surf < 0) {
-                lost_why = 2;
-                retire(FATE_LOST);
-            } else {
-                double N[3];
-                surface_normal(P, sc, surf - 1, posd[0], posd[1], posd[2], N);
-                uint32_t w[4];
-                philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
-                const float n1 = sc.tops[layer - 1].n, n2 = sc.tops[new_layer - 1].n;
-                const float old_dir[3] = {dir[0], dir[1], dir[2]};
-                bool rflag;
-                reflect_refract(dir, N, n1, n2, u01(w[0]), rflag);
-                if (!rflag) {  // transmitted :284-303
-                    layer = new_layer;
-                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
-                    taurun += dstep * sc.tops[layer - 1].kappa;
-                    advance(dstep, old_dir);  // Q4: the probe point was computed with the pre-refraction direction
-                    segment_detect();
-                    state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
-                } else {  // reflected :304-317
-                    start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
-                    ++bounces;
-                    if (bounces > 1000) { lost_why = 3; retire(FATE_LOST); }
-                    else state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
-                }
-                qs = 0.f;
-            }
-        }
-        if (state == ST_FINISH) {  // tail of tauint2 (src/inttau2.f90:354-362) + loop test of kernelsMod.f90:1958
-            if (fabsf(pos[0]) > P.gmax[0] || fabsf(pos[1]) > P.gmax[1] || fabsf(pos[2]) > P.gmax[2]) tflag = true;
-            if (tflag) retire(FATE_ESCAPED);
-            else state = ST_INTERACT;
-        }
-        if (state == ST_INTERACT) {  // src/kernelsMod.f90:1958-1974 (analog) / :2032-2066 (survival bias)
-            uint32_t w[4];
-            philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
-            const float ran = u01(w[0]);
-            const DevTop T = sc.tops[layer - 1];
-            bool alive = true;
-            if (!P.survival) {
-                if (!(ran < T.albedo)) {
-                    if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, pos[0], pos[1], pos[2]), 1.0f);
-                    retire(FATE_ABSORBED);
-                    alive = false;
-                }
-            } else {
-                const float wabs = weight * (1.0f - T.albedo);
-                weight -= wabs;
-                if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, pos[0], pos[1], pos[2]), wabs);
-                if (weight < P.threshold) {
-                    if (ran < P.chance) weight = weight / P.chance;
-                    else {
-                        retire(FATE_ROULETTE);
-                        alive = false;
-                    }
-                }
-            }
-            if (alive) {
-                hg_scatter(dir, T.hgg, u01(w[1]), u01(w[2]));
-                ++c_nscatt; ++pk_nscatt;
-                tau = -logf(u01_open0(w[3]));
-                taurun = 0.f; qs = 0.f;
-                start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
-                state = ST_TOP;
-            }
-        }
-        if (state == ST_EMIT) {
-            // claim a packet id: one atomic per warp for all lanes that need one
+        // ===================================== cold phase =====================================
+        if (state == ST_EMIT && !have_pid) {  // claim a packet id: one atomic per warp for all lanes that need one
             const unsigned need = __ballot_sync(__activemask(), true);
             unsigned long long base = 0;
             const int leader = __ffs(need) - 1;
             if (lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(need));
             base = __shfl_sync(need, base, leader);
             const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-            if (k >= (unsigned long long)P.nphotons) {
-                state = ST_DONE;
-            } else {
+            if (k >= (unsigned long long)P.nphotons) state = ST_DONE;
+            else {
                 pid = P.id_offset + k;
+                have_pid = true;
                 ev = 0; bounces = 0; steps = 0; pk_nscatt = 0; weight = 1.0f; tflag = false;
                 ++c_launched;
-                uint32_t w[4];
-                int guard = 0;
-                for (;;) {  // emitter rejection + start-voxel rejection (kernelsMod.f90:1937-1943, quirk Q6)
-                    philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
-                    const bool ok = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]), pos, dir);
-                    posd[0] = pos[0]; posd[1] = pos[1]; posd[2] = pos[2];
-                    if (ok && in_grid(P, pos[0], pos[1], pos[2])) break;
+            }
+        }
+        if (state >= ST_FRESNEL && state <= ST_EMIT) {
+            uint32_t w[4];  // the ONE Philox site: one block per event
+            philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
+            if (state == ST_FRESNEL) {
+                // inttau2.f90:248-317: which surface is being crossed, its normal, Fresnel reflect/refract
+                const float ds_pos_new = eval_top_f(sc, new_layer - 1, px, py, pz);  // ds(new_layer)
+                const float ds_pos_cur = eval_top_f(sc, layer - 1, px, py, pz);      // ds(old_layer)
+                int surf;
+                if (dnew_L < 0.f && ds_pos_new >= 0.f) surf = new_layer;
+                else if (dnew_cur >= 0.f && ds_pos_cur < 0.f) surf = layer;
+                else if (dnew_L < 0.f && dnew_cur < 0.f) surf = new_layer;
+                else if (ds_pos_cur >= 0.f && dnew_cur >= 0.f) surf = layer;
+                else surf = -1;  // reference: error stop (:276)
+                if (surf < 0) RETIRE(FATE_LOST, LOST_NO_SURFACE);
+                else {
+                    {
+                        const float e_ = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
+                        // reach: the FP32 ray/primitive root of a grazing ray is only good to ~1e-5 along the ray
+                        const double tp = polish_hit(P, sc, surf - 1, pxd, pyd, pzd, ux, uy, uz, 256.0 * (double)e_);
+                        pxd += tp * (double)ux; pyd += tp * (double)uy; pzd += tp * (double)uz;
+                        px = (float)pxd; py = (float)pyd; pz = (float)pzd;
+                    }
+                    const double3 N = surface_normal(P, sc, surf - 1, pxd, pyd, pzd);
+                    // FP32 guard: the SDF gradient points out of `surf`.  Leaving `layer` through its own surface
+                    // needs I.N > 0, entering `new_layer` through its surface needs I.N < 0.  The opposite sign means the packet
+                    // sits in the rounding skin of a surface it is moving AWAY from (impossible at the reference's FP64/1e-8
+                    // scales), i.e. its layer label lags behind where it is; a Fresnel event there would flip it back and forth
+                    // for ever.  It is moved on like an equal-index crossing: the probe's layer is adopted, direction unchanged.
+                    const double idn = (double)ux * N.x + (double)uy * N.y + (double)uz * N.z;
+                    const bool spurious = (surf == layer) ? (idn < 0.0) : (idn > 0.0);
+                    if (P.dbg_log && (long long)pid == P.dbg_pid && (int)ev <= P.dbg_cap) {
+                        float* g = P.dbg_log + 16 * (ev - 1);
+                        g[0] = (float)steps; g[1] = (float)layer; g[2] = (float)new_layer; g[3] = (float)surf; g[4] = (float)idn;
+                        g[5] = spurious ? 1.f : 0.f; g[6] = dstep; g[7] = px; g[8] = py; g[9] = pz; g[10] = ux; g[11] = uy; g[12] = uz;
+                        g[13] = dnew_L; g[14] = ds_pos_new; g[15] = ds_pos_cur;
+                    }
+                    Refl R;
+                    if (spurious) { R.x = ux; R.y = uy; R.z = uz; R.R = 0.f; R.reflected = false; --ev; }
+                    else R = reflect_refract(ux, uy, uz, N, sc.tops[layer - 1].n, sc.tops[new_layer - 1].n, u01(w[0]));
+                    ux = R.x; uy = R.y; uz = R.z;
+                    if (!R.reflected) {  // transmitted :284-303
+                        layer = new_layer;
+                        WALK(px, py, pz, dstep);
+                        taurun += dstep * sc.tops[layer - 1].kappa;
+                        // The reference continues from the probe point, which was computed with the PRE-refraction direction
+                        // (quirk Q4: a 2e-8 lateral offset there).  With FP32-sized probes the same offset is 1e-6..1e-4 and
+                        // measurably changes the impact parameter inside curved bodies (packets refracted at grazing incidence
+                        // end up beyond the critical angle and are trapped); the packet continues along the refracted ray here.
+                        ADVANCE(dstep, ux, uy, uz);
+                        DETECT();
+                        NEXT_LOOP();
+                    } else {  // reflected :304-317
+                        sx = px; sy = py; sz = pz;
+                        ++bounces;
+                        if (bounces > 1000) {
+                            if (P.out_dbg) {
+                                float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
+                                g[0] = -3.f; g[1] = (float)layer; g[2] = (float)new_layer; g[3] = (float)idn; g[4] = dstep; g[5] = ux;
+                                g[6] = uy; g[7] = uz; g[8] = R.R; g[9] = 1.f; g[10] = (float)surf; g[11] = (float)steps;
+                            }
+                            RETIRE(FATE_LOST, LOST_BOUNCES);
+                        }
+                        else NEXT_LOOP();
+                    }
+                }
+            } else if (state == ST_INTERACT) {  // kernelsMod.f90:1958-1974 (analog) / :2032-2066 (survival bias)
+                const float ran = u01(w[0]);
+                const float albedo = sc.tops[layer - 1].albedo;
+                bool alive = true;
+                if (!P.survival) {
+                    if (!(ran < albedo)) {
+                        if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, px, py, pz), 1.0f);
+                        RETIRE(FATE_ABSORBED, 0);
+                        alive = false;
+                    }
+                } else {
+                    const float wabs = weight * (1.0f - albedo);
+                    weight -= wabs;
+                    if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, px, py, pz), wabs);
+                    if (weight < P.threshold) {
+                        if (ran < P.chance) weight = weight / P.chance;
+                        else {
+                            RETIRE(FATE_ROULETTE, 0);
+                            alive = false;
+                        }
+                    }
+                }
+                if (alive) {
+                    hg_scatter(ux, uy, uz, sc.tops[layer - 1].hgg, u01(w[1]), u01(w[2]));
+                    ++c_nscatt; ++pk_nscatt;
+                    tau = -logf(u01_open0(w[3]));
+                    taurun = 0.f; qs = 0.f;
+                    sx = px; sy = py; sz = pz;
+                    state = ST_MARCH; phase = 0;
+                }
+            } else {  // ST_EMIT with a packet id: one emission attempt per iteration (rejections retry next iteration)
+                const bool ok = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]), px, py, pz, ux, uy, uz);
+                if (ok && in_grid(P, px, py, pz)) {
+                    pxd = px; pyd = py; pzd = pz;
+                    if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, px, py, pz), 1.0f);
+                    tau = -logf(u01_open0(w[3]));
+                    taurun = 0.f; qs = 0.f;
+                    sx = px; sy = py; sz = pz;
+                    launch = true; layer = 0;
+                    state = ST_MARCH; phase = 0;
+                } else {  // emitter rejection / start voxel outside the grid (kernelsMod.f90:1939-1943, quirk Q6)
                     ++c_retries;
-                    if (++guard > 100000) { guard = -1; break; }
+                    if (ev > 100000u) RETIRE(FATE_LOST, LOST_EMIT);
                 }
-                if (guard < 0) {
-                    lost_why = 5;
-                    retire(FATE_LOST);
-                    continue;
-                }
-                if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, pos[0], pos[1], pos[2]), 1.0f);
-                tau = -logf(u01_open0(w[3]));
-                taurun = 0.f; qs = 0.f;
-                start[0] = pos[0]; start[1] = pos[1]; start[2] = pos[2];
-                launch = true;
-                layer = 0;
-                state = ST_TOP;
             }
         }
         if (__all_sync(__activemask(), state == ST_DONE)) break;
-        if (state == ST_DONE) continue;
+        if (state > ST_CROSS) continue;  // cold or done lanes sit this sweep out
 
-        // =============================== sweep ===============================
-        const float qx = (float)(posd[0] + (double)qs * (double)dir[0]), qy = (float)(posd[1] + (double)qs * (double)dir[1]),
-                    qz = (float)(posd[2] + (double)qs * (double)dir[2]);
-        const Sweep S = sweep_all(sc, qx, qy, qz, layer);
-        if (!launch) ++c_sweeps;
+        // ===================================== sweep =====================================
+        const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
+                    qz = (float)(pzd + (double)qs * (double)uz);
+        const Sweep S = sweep_all(sc, qx, qy, qz, ux, uy, uz, layer);
+        ++c_sweeps;
         if (++steps > P.max_steps) {
-            lost_why = 1;
-            retire(FATE_LOST);
+            if (P.out_dbg) {
+                float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
+                g[0] = (float)state; g[1] = (float)phase; g[2] = S.amin; g[3] = S.bmin; g[4] = dstep; g[5] = qs; g[6] = (float)layer;
+                g[7] = (float)S.L; g[8] = taurun; g[9] = tau; g[10] = S.smin; g[11] = (float)bounces;
+            }
+            RETIRE(FATE_LOST, LOST_STEPS);
             continue;
         }
-        const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(pos[0]), fmaxf(fabsf(pos[1]), fabsf(pos[2]))));
+        const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
 
-        // =============================== transition ===============================
-        // d_cont >= 0: continue with the sphere-trace step logic using this distance
-        float d_cont = -1.f;
-        bool after_trace = false;
-        switch (state) {
-            case ST_TOP: {
-                if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
-                    launch = false;
-                    ++c_sweeps;
-                    layer = S.L;
-                    if (layer == 0) {  // the reference would index array(0); engine guard
-                        lost_why = 4;
-                        retire(FATE_LOST);
-                        continue;
-                    }
-                    ds_pos_cur = S.dL;
-                } else
-                    ds_pos_cur = S.dcur;
-                dlast = S.amin;
-                if (S.amin < eps) {  // sitting on a boundary :73-84
-                    dstep = S.amin + 2.0f * eps;
-                    qs = dstep;
-                    state = ST_BND_PROBE;
-                } else if (taurun >= tau || tflag)
-                    state = ST_FINISH;
-                else
-                    d_cont = S.amin;
-                break;
+        // ===================================== transition =====================================
+        if (state == ST_MARCH) {
+            if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
+                launch = false;
+                layer = S.L;
             }
-            case ST_BND_PROBE: {  // :86-131
+            if (layer == 0) {  // outside every SDF at launch: the reference would index array(0); engine guard
+                RETIRE(FATE_LOST, LOST_NO_LAYER);
+                continue;
+            }
+            if (phase != 0 && S.smin > 0.f) tflag = true;  // left all SDFs (:143-145, :188-191)
+            if (phase == 0 && S.amin < eps) {           // sitting on a boundary (:73-84)
+                dstep = S.amin + 2.0f * eps;
+                qs = dstep;
+                state = ST_BND_PROBE;
+            } else if (taurun >= tau || tflag) {
+                if (phase == 2) DETECT();  // end of the sphere-trace loop (:196-201); not at the loop top / after a nudge (:149)
+                FINISH();
+            } else if (S.amin >= eps) {  // sphere-trace step (:155-176) with the directional bound
+                phase = 2;
                 const float kap = sc.tops[layer - 1].kappa;
-                const float t = dstep * kap;
-                const float from[3] = {pos[0], pos[1], pos[2]};
-                const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
-                if (taurun + t < tau) {
-                    advance(sg * dstep, dir);
-                    taurun += t;
-                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dstep, weight)) tflag = true;  // Q2: along +dir
-                } else {
-                    const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                    if (sg > 0.f) taurun += t;  // Q1: position not advanced
-                    else advance(-dd, dir);  // Q3: taurun not advanced
-                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
-                }
-                segment_detect();
-                qs = 0.f;
-                state = ST_BND_RE;
-                break;
-            }
-            case ST_BND_RE: {  // :134-152
-                ds_pos_cur = S.dcur;
-                dlast = S.amin;
-                if (S.smin > 0.f) tflag = true;
-                if (taurun >= tau || tflag) state = ST_FINISH;
-                else d_cont = S.amin;
-                break;
-            }
-            case ST_TRACE: {  // :177-191
-                ds_pos_cur = S.dcur;
-                dlast = S.amin;
-                if (S.smin > 0.f) { tflag = true; after_trace = true; }
-                else d_cont = S.amin;
-                break;
-            }
-            case ST_CROSS: {  // :220-337
-                if (S.L == layer && S.amin < eps) {  // creep :225-235
-                    // The reference lengthens the probe by eps per iteration.  A ray skimming a curved surface stays
-                    // within eps of it over a path ~sqrt(8 r eps), i.e. thousands of iterations per grazing bounce, and a
-                    // whispering-gallery packet then owns one GPU thread for seconds.  The increment doubles here
-                    // (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) iterations; the probe can overshoot
-                    // the exit point by at most the last increment, along a ray that is within eps of the surface anyway.
-                    dstep += dlast;
-                    dlast = fminf(2.0f * dlast, 256.0f * eps);
-                    qs = dstep;
-                    break;
-                }
-                if (S.L == 0) {  // :237-241
-                    tflag = true;
-                    state = ST_FINISH;
-                    break;
-                }
-                const float n1 = sc.tops[layer - 1].n, n2 = sc.tops[S.L - 1].n;
-                if (n1 != n2) {
-                    new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
-                    state = ST_FRESNEL;
-                } else {  // :318-337
-                    layer = S.L;
-                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, dstep, weight)) tflag = true;
-                    taurun += dstep * sc.tops[layer - 1].kappa;
-                    advance(dstep, dir);
-                    segment_detect();
-                    qs = 0.f;
-                    state = tflag ? ST_FINISH : (taurun <= tau ? ST_TOP : ST_FINISH);
-                }
-                break;
-            }
-            default: break;
-        }
-        if (d_cont >= 0.f) {  // `do while (d_sdf >= eps)` body, :155-176
-            if (d_cont >= eps) {
-                const float kap = sc.tops[layer - 1].kappa;
-                const float t = d_cont * kap;
-                if (taurun + t < tau) {
-                    taurun += t;
-                    if (walk_grid<PATHLEN>(P, pos[0], pos[1], pos[2], dir, d_cont, weight)) tflag = true;
-                    advance(d_cont, dir);
-                    qs = 0.f;
-                    state = ST_TRACE;
+                // exact hit distances are shortened by a rounding margin so that the packet lands just INSIDE its layer
+                // (|d| < eps), like the reference's approach from inside; never below the plain sphere-trace step
+                const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
+                if (taurun + s * kap < tau) {
+                    taurun += s * kap;
+                    WALK(px, py, pz, s);
+                    ADVANCE(s, ux, uy, uz);
+                    if (S.bexact) AFTER_TRACE(0.0f, eps);  // landed ON the nearest surface: no confirmation sweep needed
                 } else {
                     const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
                     taurun = tau;
-                    const float from[3] = {pos[0], pos[1], pos[2]};
-                    advance(dd, dir);
-                    if (walk_grid<PATHLEN>(P, from[0], from[1], from[2], dir, dd, weight)) tflag = true;
-                    after_trace = true;
+                    WALK(px, py, pz, dd);
+                    ADVANCE(dd, ux, uy, uz);
+                    DETECT();
+                    FINISH();
                 }
-            } else
-                after_trace = true;
-        }
-        if (after_trace) {  // :196-221
-            segment_detect();
-            if (taurun >= tau || tflag) state = ST_FINISH;
-            else {
-                dstep = dlast + 2.0f * eps;
-                dlast = eps;  // from here on: the creep increment of the crossing probe
+            } else {
+                AFTER_TRACE(S.amin, eps);
+            }
+        } else if (state == ST_BND_PROBE) {  // :86-131
+            const float kap = sc.tops[layer - 1].kappa;
+            const float t = dstep * kap;
+            const float fx = px, fy = py, fz = pz;
+            const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
+            if (taurun + t < tau) {
+                taurun += t;
+                ADVANCE(sg * dstep, ux, uy, uz);
+                WALK(fx, fy, fz, dstep);  // Q2: deposits along +dir even when stepping back
+            } else {
+                const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
+                if (sg > 0.f) taurun += t;          // Q1: position not advanced
+                else ADVANCE(-dd, ux, uy, uz);      // Q3: taurun not advanced
+                WALK(fx, fy, fz, dd);
+            }
+            DETECT();
+            qs = 0.f;
+            state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
+        } else {  // ST_CROSS :220-337
+            if ((S.L == layer && S.amin < eps) || S.amin < 0.5f * eps) {
+                // FP32: a probe point closer than eps/2 (~2 ulp of the coordinate) to ANY surface has unreliable signs, so its
+                // layer classification is not trusted either; keep lengthening the probe.
+                // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
+                // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment
+                // doubles here (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) sweeps.
+                dstep += dlast;
+                dlast = fminf(2.0f * dlast, 256.0f * eps);
                 qs = dstep;
-                state = ST_CROSS;
+            } else if (S.L == 0) {  // :237-241
+                tflag = true;
+                FINISH();
+            } else if (sc.tops[layer - 1].n != sc.tops[S.L - 1].n) {
+                new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
+                state = ST_FRESNEL;
+            } else {  // :318-337
+                layer = S.L;
+                WALK(px, py, pz, dstep);
+                taurun += dstep * sc.tops[layer - 1].kappa;
+                ADVANCE(dstep, ux, uy, uz);
+                DETECT();
+                NEXT_LOOP();
             }
         }
     }
+#undef ADVANCE
+#undef WALK
+#undef DETECT
+#undef RETIRE
+#undef FINISH
+#undef AFTER_TRACE
+#undef NEXT_LOOP
 
     // ---- epilogue: flush CTA-private detector bins and per-thread counters
     __syncthreads();
@@ -871,9 +933,8 @@ __global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_inde
         if (top_index > 0) {
             dist[i] = eval_top_f(sc, top_index - 1, x, y, z);
             if (normal) {
-                double nn[3];
-                surface_normal(P, sc, top_index - 1, x, y, z, nn);
-                normal[3 * i] = (float)nn[0]; normal[3 * i + 1] = (float)nn[1]; normal[3 * i + 2] = (float)nn[2];
+                const double3 nn = surface_normal(P, sc, top_index - 1, x, y, z);
+                normal[3 * i] = (float)nn.x; normal[3 * i + 1] = (float)nn.y; normal[3 * i + 2] = (float)nn.z;
             }
         } else
             for (int t = 0; t < P.n_top; ++t) dist[i * P.n_top + t] = eval_top_f(sc, t, x, y, z);
@@ -882,26 +943,24 @@ __global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_inde
 __global__ void probe_fresnel_kernel(long long n, const float* dir, const float* nrm, const float* n1, const float* n2,
                                      const float* xi, float* dir_out, float* R, int* rflag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
-        const double N[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
-        bool rf;
-        const float r = reflect_refract(d, N, n1[i], n2[i], xi[i], rf);
-        dir_out[3 * i] = d[0]; dir_out[3 * i + 1] = d[1]; dir_out[3 * i + 2] = d[2];
-        R[i] = r;
-        rflag[i] = rf ? 1 : 0;
+        const double3 N = make_double3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+        const Refl o = reflect_refract(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], N, n1[i], n2[i], xi[i]);
+        dir_out[3 * i] = o.x; dir_out[3 * i + 1] = o.y; dir_out[3 * i + 2] = o.z;
+        R[i] = o.R;
+        rflag[i] = o.reflected ? 1 : 0;
     }
 }
 __global__ void probe_scatter_kernel(long long n, const float* dir, const float* hgg, const float* xi, float* dir_out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
-        hg_scatter(d, hgg[i], xi[2 * i], xi[2 * i + 1]);
-        dir_out[3 * i] = d[0]; dir_out[3 * i + 1] = d[1]; dir_out[3 * i + 2] = d[2];
+        float d0 = dir[3 * i], d1 = dir[3 * i + 1], d2 = dir[3 * i + 2];
+        hg_scatter(d0, d1, d2, hgg[i], xi[2 * i], xi[2 * i + 1]);
+        dir_out[3 * i] = d0; dir_out[3 * i + 1] = d1; dir_out[3 * i + 2] = d2;
     }
 }
 __global__ void probe_emit_kernel(const __grid_constant__ KParams P, long long n, const float* xi4, float* pos, float* dir, int* cell) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
-        emit_packet(P, xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], p, d);
+        emit_packet_v(P, xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], p, d);
         for (int a = 0; a < 3; ++a) { pos[3 * i + a] = p[a]; dir[3 * i + a] = d[a]; }
         // get_voxel_cart (src/grid.f90:51-78)
         const int dims[3] = {P.nxg, P.nyg, P.nzg};
@@ -914,12 +973,12 @@ __global__ void probe_emit_kernel(const __grid_constant__ KParams P, long long n
 }
 __global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det_index, long long n, const float* start,
                                       const float* dir, const float* len, int* hit, int* bin) {
-    const DevDet D = reinterpret_cast<const DevDet*>(P.blob + P.off_dets)[det_index - 1];
+    const DevDet* D = reinterpret_cast<const DevDet*>(P.blob + P.off_dets) + (det_index - 1);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float s[3] = {start[3 * i], start[3 * i + 1], start[3 * i + 2]};
         const float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
         const float e[3] = {s[0] + d[0] * len[i], s[1] + d[1] * len[i], s[2] + d[2] * len[i]};
-        const int b = detector_bin(D, s, d, e);
+        const int b = detector_bin(D, s[0], s[1], s[2], d[0], d[1], d[2], e[0], e[1], e[2]);
         hit[i] = b > 0;
         bin[i] = b;
     }

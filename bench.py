@@ -188,6 +188,7 @@ def main():
 
     import rsmcrt_b200 as R
     from rsmcrt_b200 import api as A
+    from rsmcrt_b200.sharding import step_offset
     R.load()  # fails loudly if the CUDA library is missing: no CPU fallback
 
     dist = None
@@ -243,7 +244,7 @@ def main():
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
     for s in range(args.steps):
-        off = (s * world + rank) * n_step
+        off = step_offset(s, world, rank, n_step)
         eng.run_async(n_step, seed, id_offset=off, tally_mode=mode)
         eng.wait()
         dev_ms += eng.last_run_ms
@@ -271,7 +272,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        off = (s * world + rank) * n_step
+        off = step_offset(s, world, rank, n_step)
         eng.set_scene(scene)                       # host -> device: flattened scene
         eng.set_source(src_k, src_s, src_p)
         eng.set_detectors(kind, dp, nb)            # (also zeroes the detector tallies, like the escape driver's reset)

@@ -78,6 +78,8 @@ def load():
     L.orc_matmul.argtypes = [dp, dp, dp]
     L.orc_vec_dot_mat.argtypes = [dp, dp, dp]
     L.orc_mono.argtypes = [C.c_double] * 4 + [dp]
+    L.orc_test_kernel.restype = C.c_double
+    L.orc_test_kernel.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_int, dp]
     L.orc_max_threads.restype = C.c_int
     L.orc_run.restype = C.c_double
     L.orc_run.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -249,6 +251,12 @@ class OracleScene:
         c = np.zeros(3, np.int32)
         self.L.orc_get_voxel(self.h, _P(p, C.c_double), _P(c, C.c_int32))
         return c
+
+    def test_kernel(self, nphotons, seed, end_early=True, nthreads=0):
+        """test_kernel of the reference (kernelsMod.f90:2069-2182) -> (mean scatters, moments[2,4,3])."""
+        m = np.zeros(24)
+        nsc = self.L.orc_test_kernel(self.h, int(nphotons), int(seed), int(end_early), int(nthreads), _P(m, C.c_double))
+        return nsc, m.reshape(2, 4, 3)
 
     def run(self, nphotons, seed, id_offset=0, tally_mode=1, survival_bias=False, threshold=-1.0, chance=-1.0, nthreads=0,
             rng_mode=0, per_packet=False, grids=True):

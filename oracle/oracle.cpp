@@ -1463,6 +1463,84 @@ void orc_mono(double mus, double mua, double hgg, double n, double* out7) {
     out7[0] = o.mus; out7[1] = o.mua; out7[2] = o.hgg; out7[3] = o.g2; out7[4] = o.n; out7[5] = o.kappa; out7[6] = o.albedo;
 }
 
+// test_kernel (src/kernelsMod.f90:2069-2182): the serial variant the reference's end-to-end tests run.  Differences to
+// noBiasPropagation that matter: launch layer uses mask=(distances<=0) (:2136), no start-voxel rejection loop, no absorb
+// deposit, positions summed after scatter orders 1..4 and (end_early) the packet is dropped after the 5th scatter.
+// moments: 24 doubles = 10*<r> for orders 1..4 (x,y,z) then 100*<r^2> for orders 1..4, exactly what positions.dat holds.
+double orc_test_kernel(void* h, int64_t nphotons, uint64_t seed, int end_early, int nthreads, double* moments) {
+    Scene* s = (Scene*)h;
+    const int N = (int)s->top.size();
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    double sum[24] = {0};
+    double nscatt = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        double loc[24] = {0};
+        double lsc = 0;
+        Tally T;
+        T.mode = 0;
+        T.parallel = nthreads > 1;
+        ThreadCounters C;
+        Rng rng;
+        rng.mode = 0;
+        Work W;
+        W.ds.resize(N); W.dsNew.resize(N);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int64_t j = 0; j < nphotons; ++j) {
+            rng.start_packet(seed, (uint64_t)j);
+            Packet pk{};
+            for (;;) {
+                rng.begin_event();
+                double xi[3] = {rng.draw(0), rng.draw(1), rng.draw(2)};
+                if (emit(*s, pk, xi)) break;
+            }
+            pk.step = 0;
+            for (int i = 0; i < N; ++i) W.ds[i] = eval_top(*s, i, pk.pos);
+            pk.layer = maxloc_neg(W.ds.data(), N, true);
+            if (pk.layer == 0) continue;
+            bool ok = tauint2(*s, T, C, pk, rng, W);
+            while (ok && !pk.tflag) {
+                rng.begin_event();
+                const Optics& o = s->opt[pk.layer - 1];
+                if (rng.draw(0) < o.albedo) {
+                    scatter(pk, o.hgg, rng.draw(1), rng.draw(2));
+                    lsc += 1;
+                    pk.step += 1;
+                    if (pk.step >= 1 && pk.step <= 4) {
+                        const int k = pk.step - 1;
+                        loc[3 * k] += pk.pos.x; loc[3 * k + 1] += pk.pos.y; loc[3 * k + 2] += pk.pos.z;
+                        loc[12 + 3 * k] += pk.pos.x * pk.pos.x; loc[12 + 3 * k + 1] += pk.pos.y * pk.pos.y;
+                        loc[12 + 3 * k + 2] += pk.pos.z * pk.pos.z;
+                    } else if (end_early)
+                        pk.tflag = true;
+                } else {
+                    pk.tflag = true;
+                    break;
+                }
+                ok = tauint2(*s, T, C, pk, rng, W);
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            for (int i = 0; i < 24; ++i) sum[i] += loc[i];
+            nscatt += lsc;
+        }
+    }
+    for (int i = 0; i < 12; ++i) moments[i] = 10.0 * sum[i] / (double)nphotons;
+    for (int i = 12; i < 24; ++i) moments[i] = 100.0 * sum[i] / (double)nphotons;
+    return nscatt / (double)nphotons;
+}
+
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -559,6 +559,7 @@ __device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float 
 //   ST_EMIT      launch a new packet (kernelsMod.f90:1937-1952)
 enum : int { ST_MARCH = 0, ST_BND_PROBE, ST_CROSS, ST_FRESNEL, ST_INTERACT, ST_EMIT, ST_DONE };
 enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST = 3 };
+enum : int { POST_NONE = 0, POST_FINISH, POST_AFTER_TRACE, POST_NEXT_LOOP };
 enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYER = 4, LOST_EMIT = 5 };
 
 template <bool PATHLEN, bool HASDET>
@@ -609,20 +610,24 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
     // record_hit on the straight segment start -> pos for every detector (inttau2.f90:126-131,196-201,298-303,330-335)
 #define DETECT()                                                                                                      \
     do {                                                                                                              \
-        if (HASDET) {                                                                                                 \
-            for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                   \
-                const int b_ = detector_bin(&sc.dets[i_], sx, sy, sz, ux, uy, uz, px, py, pz);                        \
+        for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                       \
+            const DevDet* D_ = &sc.dets[i_];                                                                          \
+            /* plane side function g(x) = (p0 - x).n at both ends: a crossing needs g(start) >= 0 > g(end) */         \
+            const float gs_ = (D_->pos[0] - sx) * D_->dir[0] + (D_->pos[1] - sy) * D_->dir[1] + (D_->pos[2] - sz) * D_->dir[2]; \
+            const float ge_ = (D_->pos[0] - px) * D_->dir[0] + (D_->pos[1] - py) * D_->dir[1] + (D_->pos[2] - pz) * D_->dir[2]; \
+            if (D_->kind == 4 || (gs_ >= 0.f && ge_ < 0.f)) {                                                         \
+                const int b_ = detector_bin(D_, sx, sy, sz, ux, uy, uz, px, py, pz);                                  \
                 if (b_ > 0) {                                                                                         \
-                    const float w_ = sc.dets[i_].kind == 4 ? 1.0f : weight;                                           \
+                    const float w_ = D_->kind == 4 ? 1.0f : weight;                                                   \
                     const unsigned long long q_ = (unsigned long long)__float2ll_rn(w_ * DET_FIX);                    \
-                    const int slot_ = sc.dets[i_].offset + b_ - 1;                                                    \
+                    const int slot_ = D_->offset + b_ - 1;                                                            \
                     if (P.det_in_smem) atomicAdd(&sbins[slot_], q_);                                                  \
                     else atomicAdd(&P.det_bins[slot_], q_);                                                           \
                     ++c_dethits;                                                                                      \
                 }                                                                                                     \
             }                                                                                                         \
-            sx = px; sy = py; sz = pz;                                                                                \
         }                                                                                                             \
+        sx = px; sy = py; sz = pz;                                                                                    \
     } while (0)
     // packet finished: publish the optional per-packet record and ask for a new packet
 #define RETIRE(FATE, WHY)                                                                                             \
@@ -645,13 +650,6 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
         if (fabsf(px) > P.gmax[0] || fabsf(py) > P.gmax[1] || fabsf(pz) > P.gmax[2]) tflag = true;                    \
         if (tflag) RETIRE(FATE_ESCAPED, 0);                                                                           \
         else state = ST_INTERACT;                                                                                     \
-    } while (0)
-    // straight piece ended on a surface: detectors, then probe across it (inttau2.f90:196-221)
-#define AFTER_TRACE(DL, EPS)                                                                                          \
-    do {                                                                                                              \
-        DETECT();                                                                                                     \
-        if (taurun >= tau || tflag) FINISH();                                                                         \
-        else { dstep = (DL) + 2.0f * (EPS); dlast = (EPS); qs = dstep; state = ST_CROSS; }                            \
     } while (0)
 #define NEXT_LOOP() /* `do while (taurun <= tau)` head, inttau2.f90:61 */                                             \
     do {                                                                                                              \
@@ -726,7 +724,7 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
                         // measurably changes the impact parameter inside curved bodies (packets refracted at grazing incidence
                         // end up beyond the critical angle and are trapped); the packet continues along the refracted ray here.
                         ADVANCE(dstep, ux, uy, uz);
-                        DETECT();
+                        if (HASDET) DETECT();
                         NEXT_LOOP();
                     } else {  // reflected :304-317
                         sx = px; sy = py; sz = pz;
@@ -789,114 +787,125 @@ __global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant
             }
         }
         if (__all_sync(__activemask(), state == ST_DONE)) break;
-        if (state > ST_CROSS) continue;  // cold or done lanes sit this sweep out
+        // cold or done lanes sit the sweep out
 
         // ===================================== sweep =====================================
-        const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
-                    qz = (float)(pzd + (double)qs * (double)uz);
-        const Sweep S = sweep_all(sc, qx, qy, qz, ux, uy, uz, layer);
-        ++c_sweeps;
-        if (++steps > P.max_steps) {
-            if (P.out_dbg) {
-                float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
-                g[0] = (float)state; g[1] = (float)phase; g[2] = S.amin; g[3] = S.bmin; g[4] = dstep; g[5] = qs; g[6] = (float)layer;
-                g[7] = (float)S.L; g[8] = taurun; g[9] = tau; g[10] = S.smin; g[11] = (float)bounces;
-            }
-            RETIRE(FATE_LOST, LOST_STEPS);
-            continue;
-        }
-        const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
-
-        // ===================================== transition =====================================
-        if (state == ST_MARCH) {
-            if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
-                launch = false;
-                layer = S.L;
-            }
-            if (layer == 0) {  // outside every SDF at launch: the reference would index array(0); engine guard
-                RETIRE(FATE_LOST, LOST_NO_LAYER);
-                continue;
-            }
-            if (phase != 0 && S.smin > 0.f) tflag = true;  // left all SDFs (:143-145, :188-191)
-            if (phase == 0 && S.amin < eps) {           // sitting on a boundary (:73-84)
-                dstep = S.amin + 2.0f * eps;
-                qs = dstep;
-                state = ST_BND_PROBE;
-            } else if (taurun >= tau || tflag) {
-                if (phase == 2) DETECT();  // end of the sphere-trace loop (:196-201); not at the loop top / after a nudge (:149)
-                FINISH();
-            } else if (S.amin >= eps) {  // sphere-trace step (:155-176) with the directional bound
-                phase = 2;
+        int post = POST_NONE;
+        bool det = false;       // a straight segment ended: test the detectors (one call site, below)
+        if (state <= ST_CROSS) {
+            const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
+                        qz = (float)(pzd + (double)qs * (double)uz);
+            const Sweep S = sweep_all(sc, qx, qy, qz, ux, uy, uz, layer);
+            ++c_sweeps;
+            const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
+            // ---------------- transition, part A (divergent, cheap): decide how far to move and what happens next
+            float adv = 0.f;     // signed distance to move along the direction
+            float wlen = -1.f;   // >= 0: update_grids over this length, from the position BEFORE the move, along +dir
+            float dtau = 0.f;    // optical depth spent by the move
+            float dl = 0.f;      // AFTER_TRACE: distance to the nearest surface at the segment end
+            if (++steps > P.max_steps) {
+                if (P.out_dbg) {
+                    float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
+                    g[0] = (float)state; g[1] = (float)phase; g[2] = S.amin; g[3] = S.bmin; g[4] = dstep; g[5] = qs; g[6] = (float)layer;
+                    g[7] = (float)S.L; g[8] = taurun; g[9] = tau; g[10] = S.smin; g[11] = (float)bounces;
+                }
+                RETIRE(FATE_LOST, LOST_STEPS);
+            } else if (state == ST_MARCH) {
+                if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
+                    launch = false;
+                    layer = S.L;
+                }
+                if (layer == 0) {  // outside every SDF at launch: the reference would index array(0); engine guard
+                    RETIRE(FATE_LOST, LOST_NO_LAYER);
+                } else {
+                    if (phase != 0 && S.smin > 0.f) tflag = true;  // left all SDFs (:143-145, :188-191)
+                    if (phase == 0 && S.amin < eps) {               // sitting on a boundary (:73-84)
+                        dstep = S.amin + 2.0f * eps;
+                        qs = dstep;
+                        state = ST_BND_PROBE;
+                    } else if (taurun >= tau || tflag) {
+                        det = (phase == 2);  // end of the sphere-trace loop (:196-201); not at the loop top / after a nudge (:149)
+                        post = POST_FINISH;
+                    } else if (S.amin >= eps) {  // sphere-trace step (:155-176) with the directional bound
+                        phase = 2;
+                        const float kap = sc.tops[layer - 1].kappa;
+                        // exact hit distances are shortened by a rounding margin so that the packet lands just INSIDE its layer
+                        // (|d| < eps), like the reference's approach from inside; never below the plain sphere-trace step
+                        const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
+                        if (taurun + s * kap < tau) {
+                            adv = s; wlen = s; dtau = s * kap;
+                            if (S.bexact) post = POST_AFTER_TRACE;  // landed ON the nearest surface: no confirmation sweep needed
+                        } else {
+                            const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
+                            adv = dd; wlen = dd; dtau = tau - taurun;
+                            det = true;
+                            post = POST_FINISH;
+                        }
+                    } else {
+                        dl = S.amin;
+                        post = POST_AFTER_TRACE;
+                    }
+                }
+            } else if (state == ST_BND_PROBE) {  // :86-131
                 const float kap = sc.tops[layer - 1].kappa;
-                // exact hit distances are shortened by a rounding margin so that the packet lands just INSIDE its layer
-                // (|d| < eps), like the reference's approach from inside; never below the plain sphere-trace step
-                const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
-                if (taurun + s * kap < tau) {
-                    taurun += s * kap;
-                    WALK(px, py, pz, s);
-                    ADVANCE(s, ux, uy, uz);
-                    if (S.bexact) AFTER_TRACE(0.0f, eps);  // landed ON the nearest surface: no confirmation sweep needed
+                const float t = dstep * kap;
+                const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
+                if (taurun + t < tau) {
+                    adv = sg * dstep; wlen = dstep; dtau = t;  // Q2: deposits along +dir even when stepping back
                 } else {
                     const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                    taurun = tau;
-                    WALK(px, py, pz, dd);
-                    ADVANCE(dd, ux, uy, uz);
-                    DETECT();
-                    FINISH();
+                    wlen = dd;
+                    if (sg > 0.f) dtau = t;   // Q1: position not advanced
+                    else adv = -dd;           // Q3: taurun not advanced
                 }
-            } else {
-                AFTER_TRACE(S.amin, eps);
+                det = true;
+                qs = 0.f;
+                state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
+            } else {  // ST_CROSS :220-337
+                if ((S.L == layer && S.amin < eps) || S.amin < 0.5f * eps) {
+                    // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
+                    // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment
+                    // doubles here (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) sweeps.
+                    // FP32: a probe point closer than eps/2 (~2 ulp of the coordinate) to ANY surface has unreliable signs, so
+                    // its layer classification is not trusted either; keep lengthening the probe.
+                    dstep += dlast;
+                    dlast = fminf(2.0f * dlast, 256.0f * eps);
+                    qs = dstep;
+                } else if (S.L == 0) {  // :237-241
+                    tflag = true;
+                    post = POST_FINISH;
+                } else if (sc.tops[layer - 1].n != sc.tops[S.L - 1].n) {
+                    new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
+                    state = ST_FRESNEL;
+                } else {  // :318-337
+                    layer = S.L;
+                    adv = dstep; wlen = dstep; dtau = dstep * sc.tops[layer - 1].kappa;
+                    det = true;
+                    post = POST_NEXT_LOOP;
+                }
             }
-        } else if (state == ST_BND_PROBE) {  // :86-131
-            const float kap = sc.tops[layer - 1].kappa;
-            const float t = dstep * kap;
-            const float fx = px, fy = py, fz = pz;
-            const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
-            if (taurun + t < tau) {
-                taurun += t;
-                ADVANCE(sg * dstep, ux, uy, uz);
-                WALK(fx, fy, fz, dstep);  // Q2: deposits along +dir even when stepping back
-            } else {
-                const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                if (sg > 0.f) taurun += t;          // Q1: position not advanced
-                else ADVANCE(-dd, ux, uy, uz);      // Q3: taurun not advanced
-                WALK(fx, fy, fz, dd);
-            }
-            DETECT();
-            qs = 0.f;
-            state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
-        } else {  // ST_CROSS :220-337
-            if ((S.L == layer && S.amin < eps) || S.amin < 0.5f * eps) {
-                // FP32: a probe point closer than eps/2 (~2 ulp of the coordinate) to ANY surface has unreliable signs, so its
-                // layer classification is not trusted either; keep lengthening the probe.
-                // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
-                // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment
-                // doubles here (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) sweeps.
-                dstep += dlast;
-                dlast = fminf(2.0f * dlast, 256.0f * eps);
-                qs = dstep;
-            } else if (S.L == 0) {  // :237-241
-                tflag = true;
-                FINISH();
-            } else if (sc.tops[layer - 1].n != sc.tops[S.L - 1].n) {
-                new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
-                state = ST_FRESNEL;
-            } else {  // :318-337
-                layer = S.L;
-                WALK(px, py, pz, dstep);
-                taurun += dstep * sc.tops[layer - 1].kappa;
-                ADVANCE(dstep, ux, uy, uz);
-                DETECT();
+            // ---------------- part B (common): update_grids, move, spend optical depth
+            if (wlen >= 0.f) WALK(px, py, pz, wlen);
+            if (adv != 0.f) ADVANCE(adv, ux, uy, uz);
+            taurun += dtau;
+            // ---------------- part C: what the move led to
+            if (post == POST_AFTER_TRACE) {  // straight piece ended on a surface: detectors, then probe across it (:196-221)
+                det = true;
+                if (taurun >= tau || tflag) post = POST_FINISH;
+                else { dstep = dl + 2.0f * eps; dlast = eps; qs = dstep; state = ST_CROSS; }
+            } else if (post == POST_NEXT_LOOP) {
                 NEXT_LOOP();
             }
         }
+        if (HASDET && det) DETECT();
+        if (post == POST_FINISH) FINISH();
     }
+
 #undef ADVANCE
 #undef WALK
 #undef DETECT
 #undef RETIRE
 #undef FINISH
-#undef AFTER_TRACE
 #undef NEXT_LOOP
 
     // ---- epilogue: flush CTA-private detector bins and per-thread counters

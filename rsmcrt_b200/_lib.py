@@ -100,7 +100,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    import os
+    path = Path(os.environ["SMCRT_LIB"]) if os.environ.get("SMCRT_LIB") else _build.LIB_PATH  # override: kernel-variant experiments
     if not path.exists():
         if not build_if_missing:
             raise RuntimeError(f"{path} is missing; run `python -m rsmcrt_b200.build` (no CPU fallback exists)")

@@ -582,13 +582,13 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
     auto kern = trace_persistent<PL, HD>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
     if (per_sm < 1) return set_err("scene does not fit in shared memory (%d bytes per CTA)", smem_bytes);
     // persistent grid: every SM full, no more; never more threads than packets
     long long blocks = (long long)D.sm_count * per_sm;
-    const long long need = (P.nphotons + 255) / 256;
+    const long long need = (P.nphotons + SMCRT_BLOCK - 1) / SMCRT_BLOCK;
     if (blocks > need) blocks = std::max<long long>(need, 1);
-    kern<<<(unsigned)blocks, 256, smem_bytes, D.stream>>>(P);
+    kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, D.stream>>>(P);
     CU(cudaGetLastError());
     return 0;
 }

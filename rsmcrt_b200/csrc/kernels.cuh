@@ -562,8 +562,14 @@ enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST =
 enum : int { POST_NONE = 0, POST_FINISH, POST_AFTER_TRACE, POST_NEXT_LOOP };
 enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYER = 4, LOST_EMIT = 5 };
 
+#ifndef SMCRT_BLOCK
+#define SMCRT_BLOCK 256      // threads per CTA
+#endif
+#ifndef SMCRT_MINBLOCKS
+#define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
+#endif
 template <bool PATHLEN, bool HASDET>
-__global__ void __launch_bounds__(256, 2) trace_persistent(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
         const int4* src = reinterpret_cast<const int4*>(P.blob);

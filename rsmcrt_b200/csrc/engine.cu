@@ -137,6 +137,7 @@ struct smcrt_ctx {
     double last_ms = 0;
     long long launches = 0;
     bool pending = false;
+    int touched_modes = 0;   // OR of the tally modes run since the last reset: only those grids are reduced
     long long dbg_pid = -1;
     float* dbg_log = nullptr;
     int dbg_cap = 0;
@@ -617,6 +618,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
     c->launches += 1;
+    c->touched_modes |= tally_mode;
     return 0;
 }
 
@@ -684,9 +686,13 @@ static int reduce_buffers(smcrt_ctx* c, int root_rank_or_dev) {
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceState& D = c->devs[g];
         CU(cudaSetDevice(D.dev));
-        NC(nccl::Reduce(D.jmean, D.jmean, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
-        NC(nccl::Reduce(D.absorb, D.absorb, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
-        NC(nccl::Reduce(D.emission, D.emission, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        // only the grids a run could have written (every rank runs the same modes, so the collectives match up)
+        if (c->touched_modes & SMCRT_TALLY_PATHLENGTH)
+            NC(nccl::Reduce(D.jmean, D.jmean, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        if (c->touched_modes & SMCRT_TALLY_ABSORB)
+            NC(nccl::Reduce(D.absorb, D.absorb, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        if (c->touched_modes & SMCRT_TALLY_EMISSION)
+            NC(nccl::Reduce(D.emission, D.emission, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
         NC(nccl::Reduce(D.det_bins, D.det_bins, (size_t)std::max<long long>(c->det_total, 1), nccl::ncclUint64, nccl::ncclSum,
                         root_rank_or_dev, D.comm, D.stream));
         NC(nccl::Reduce(D.counters, D.counters, (size_t)C_COUNT, nccl::ncclUint64, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
@@ -811,6 +817,7 @@ extern "C" int smcrt_fetch(smcrt_ctx* c, float* jmean, float* absorb, float* emi
 extern "C" int smcrt_reset_tallies(smcrt_ctx* c) {
     int rc = check_ready(c);
     if (rc) return rc;
+    c->touched_modes = 0;
     for (DeviceState& D : c->devs)
         if ((rc = zero_device_tallies(c, D))) return rc;
     return 0;

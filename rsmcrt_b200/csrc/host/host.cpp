@@ -682,6 +682,36 @@ void build_scene(Config& c) {
             S.add_top({prim_capsule(&nodes[3 * i1], &nodes[3 * i2], radii[i1] * res), 94.0, 231.0, 0.9, 1.37});
         }
         S.add_top({prim_box(0.32, 0.18, 0.26), 357.0, 0.458, 0.9, 1.37});
+    } else if (g == "jacques" || g == "skin" || g == "lens") {
+        // BUILDER-DEFINED geometries.  res/jacques.toml, res/skin.toml and res/lens.toml name geom_names that do not exist
+        // in this fork's dispatcher (src/setup.f90:33-60 -> error stop "no such routine"), so there is no reference
+        // scene to mirror.  They are defined here (documented in DESIGN.md §7) so that BASELINE configs 2-4 can run; parity
+        // for them is engine-vs-oracle only.
+        if (g == "jacques") {
+            // Jacques' classic semi-infinite-like tissue block: 2^3 cube, mua=1, mus=100, g=0.9, n=1.38, in air.
+            S.add_top({prim_box(2, 2, 2), 100.0, 1.0, 0.9, 1.38});
+            S.add_top({prim_box(2.02, 2.02, 2.02), 0.0, 0.0, 0.0, 1.0});
+        } else if (g == "skin") {
+            // five-layer skin model inside the +-0.05 cm cube of res/skin.toml, z from the top face downwards (cm):
+            // stratum corneum 0.002, living epidermis 0.008, papillary dermis 0.02, reticular dermis 0.05, hypodermis 0.02;
+            // per layer (mus, mua, g, n) at ~630 nm (order-of-magnitude literature values; builder-defined)
+            struct L { double t, mus, mua, g, n; };
+            const L layers[5] = {{0.002, 1000.0, 0.10, 0.86, 1.50}, {0.008, 450.0, 1.50, 0.80, 1.34}, {0.020, 300.0, 0.70, 0.90, 1.40},
+                                 {0.050, 200.0, 0.50, 0.95, 1.39}, {0.020, 150.0, 0.20, 0.75, 1.44}};
+            double top = 0.05;
+            for (const L& l : layers) {
+                Mat t = mat_invert(mat_translate(0.0, 0.0, top - 0.5 * l.t));
+                S.add_top({prim_box(0.1, 0.1, l.t, &t), l.mus, l.mua, l.g, l.n});
+                top -= l.t;
+            }
+            S.add_top({prim_box(0.102, 0.102, 0.102), 0.0, 0.0, 0.0, 1.0});  // air shell around the stack
+        } else {
+            // bi-convex lens: intersection of two spheres of radius 1.0 centred at z = +-0.8 (thickness 0.4, aperture radius 0.6),
+            // glass n = 1.5, non-scattering, in the 2^3 air box of res/lens.toml
+            Mat ta = mat_invert(mat_translate(0, 0, 0.8)), tb = mat_invert(mat_translate(0, 0, -0.8));
+            S.add_top({model_of(SMCRT_MODEL_INTERSECTION, {prim_sphere(1.0, &ta), prim_sphere(1.0, &tb)}, 0.0), 0.0, 0.0, 0.0, 1.5});
+            S.add_top({prim_box(2, 2, 2), 0.0, 0.0, 0.0, 1.0});
+        }
     } else if (g == "logo") {
         cfg_fail("need to uncomment inlcude line!");  // setup_logo is disabled in the reference (:328)
     } else {

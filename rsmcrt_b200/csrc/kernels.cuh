@@ -268,9 +268,10 @@ __device__ __forceinline__ void hg_scatter(float& dx_, float& dy_, float& dz_, f
 
 // ------------------------------------------------------------------------------------------------ voxels
 __device__ __forceinline__ bool in_grid(const KParams& P, float x, float y, float z) {
-    // update_voxels (src/inttau2.f90:587-614): cell = floor(n * X / (2 max)) + 1 valid  <=>  0 <= X*n/(2max) < n
-    const float fx = (x + P.gmax[0]) * P.inv_vox[0], fy = (y + P.gmax[1]) * P.inv_vox[1], fz = (z + P.gmax[2]) * P.inv_vox[2];
-    return fx >= 0.f && fx < (float)P.nxg && fy >= 0.f && fy < (float)P.nyg && fz >= 0.f && fz < (float)P.nzg;
+    // update_voxels (src/inttau2.f90:587-614): cell = floor(n (x + max) / (2 max)) + 1 is valid  <=>  -max <= x < max.
+    // Compared on the coordinate itself: the scaled form rounds up to n in FP32 for x within ~n ulp of the upper face, which
+    // would kill every packet that reaches a medium surface coinciding with the grid face before it can reflect.
+    return x >= -P.gmax[0] && x < P.gmax[0] && y >= -P.gmax[1] && y < P.gmax[1] && z >= -P.gmax[2] && z < P.gmax[2];
 }
 __device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y, float z) {
     int i = (int)floorf((x + P.gmax[0]) * P.inv_vox[0]);
@@ -306,8 +307,9 @@ __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
 __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
     // corner-origin coordinates
     const float X = (fx + P.gmax[0]), Y = (fy + P.gmax[1]), Z = (fz + P.gmax[2]);
-    int i = (int)floorf(X * P.inv_vox[0]), j = (int)floorf(Y * P.inv_vox[1]), k = (int)floorf(Z * P.inv_vox[2]);
-    if (i < 0 || i >= P.nxg || j < 0 || j >= P.nyg || k < 0 || k >= P.nzg) return true;  // :411-415
+    if (!in_grid(P, fx, fy, fz)) return true;  // :411-415
+    int i = min((int)floorf(X * P.inv_vox[0]), P.nxg - 1), j = min((int)floorf(Y * P.inv_vox[1]), P.nyg - 1),
+        k = min((int)floorf(Z * P.inv_vox[2]), P.nzg - 1);  // min: the scaled coordinate may round up to n just inside the face
     const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
     const float BIG = 3.0e38f;
     float tx = dx != 0.f ? (((float)(i + (sx > 0)) * P.vox[0]) - X) / dx : BIG;

@@ -1,0 +1,100 @@
+"""GPU-vs-oracle parity on the remaining BASELINE configs (jacques / skin / lens / vessels) and on compound SDF scenes
+(omg: smooth-union model; egg: revolution modifier).  For the builder-defined geometries the oracle is the
+only reference there is."""
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import RES, ROOT
+from rsmcrt_b200 import api as A
+
+pytestmark = pytest.mark.gpu
+
+
+def both(smcrt, oracle, engine, name, n, seed=11, mode=A.TALLY_ABSORB, **kw):
+    cfg = smcrt.Config.load(RES / name, **kw)
+    engine.apply(cfg)
+    osc = oracle.OracleScene.from_config(cfg)
+    g = engine.trace_packets(n, seed, tally_mode=mode)
+    out = engine.fetch(jmean=bool(mode & A.TALLY_PATHLENGTH), absorb=True)
+    o = osc.run(n, seed, per_packet=True, tally_mode=mode)
+    return cfg, g, out, o
+
+
+def ensemble_close(g, o, n):
+    """fate fractions and mean scatter counts agree within 4 sigma (independent-sample bound; same streams do better)."""
+    for f in (A.FATE_ABSORBED, A.FATE_ESCAPED):
+        pg, po = (g["fate"] == f).mean(), (o["fate"] == f).mean()
+        assert abs(pg - po) < 4 * np.sqrt(2 * 0.25 / n) + 1e-9
+    ng, no = g["nscatt"].astype(float), o["nscatt"].astype(float)
+    assert abs(ng.mean() - no.mean()) < 4 * np.sqrt((ng.var() + no.var()) / n) + 1e-9
+
+
+def test_jacques_block(engine, oracle, smcrt):
+    cfg, g, out, o = both(smcrt, oracle, engine, "jacques.toml", 20000)
+    assert out["counters"]["lost"] == 0 and (o["fate"] != A.FATE_LOST).all()
+    ensemble_close(g, o, 20000)
+    # absorbed-energy depth profile (uniform illumination from the top): coarse z bins, 4 sigma
+    zg = out["absorb"].sum(axis=(0, 1)).reshape(20, 20).sum(1)
+    zo = o["absorb"].sum(axis=(0, 1)).reshape(20, 20).sum(1).astype(float)
+    assert np.all(np.abs(zg - zo) < 4 * np.sqrt(zg + zo + 1) + 3)
+
+
+def test_skin_layers(engine, oracle, smcrt):
+    cfg, g, out, o = both(smcrt, oracle, engine, "skin_b200.toml", 20000)
+    assert out["counters"]["lost"] <= 2 and (o["fate"] == A.FATE_LOST).sum() <= 2
+    ensemble_close(g, o, 20000)
+    zg = out["absorb"].sum(axis=(0, 1)).reshape(20, 10).sum(1)
+    zo = o["absorb"].sum(axis=(0, 1)).reshape(20, 10).sum(1).astype(float)
+    assert np.all(np.abs(zg - zo) < 4 * np.sqrt(zg + zo + 1) + 3)
+    # internal reflections happen at the index steps between layers
+    assert out["counters"]["bounces"] > 0
+
+
+def test_lens_refraction(engine, oracle, smcrt):
+    """bi-convex lens = intersection(sphere, sphere): compound SDF (program interpreter + FP64 normal through the model)."""
+    mode = A.TALLY_PATHLENGTH
+    cfg, g, out, o = both(smcrt, oracle, engine, "lens.toml", 20000, mode=mode)
+    assert out["counters"]["lost"] <= 2
+    assert (g["fate"] == A.FATE_ESCAPED).mean() > 0.999
+    same = (g["events"] == o["events"])
+    assert same.mean() > 0.97  # same number of Fresnel events for (nearly) every packet
+    # the lens focuses the beam: compare the path-length fluence in coarse blocks
+    cg = out["jmean"].astype(float).reshape(10, 20, 10, 20, 10, 20).sum(axis=(1, 3, 5))
+    co = o["jmean"].astype(float).reshape(10, 20, 10, 20, 10, 20).sum(axis=(1, 3, 5))
+    assert abs(cg.sum() - co.sum()) < 0.005 * co.sum()
+    assert np.abs(cg - co).sum() < 0.03 * co.sum()
+    # exit points of identical histories coincide
+    d = np.abs(g["pos"] - o["pos"])[same].max(axis=1)
+    assert np.median(d) < 1e-4
+
+
+def test_vessels_capsules(engine, oracle, smcrt, tmp_path):
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_vessels
+    make_vessels.make(tmp_path, 240, 7)
+    cfg, g, out, o = both(smcrt, oracle, engine, "vessels.toml", 10000, res_dir=tmp_path)
+    assert cfg.scene.n_top == 241
+    assert out["counters"]["lost"] == 0
+    ensemble_close(g, o, 10000)
+    assert abs(out["absorb"].sum() - o["absorb"].sum()) < 4 * np.sqrt(2 * 0.25 * 10000)
+
+
+def test_omg_smooth_union(engine, oracle, smcrt):
+    cfg, g, out, o = both(smcrt, oracle, engine, "omg.toml", 10000)
+    assert out["counters"]["lost"] <= 2
+    ensemble_close(g, o, 10000)
+
+
+def test_egg_revolution(engine, oracle, smcrt):
+    text = (RES / "egg_test.toml").read_text().replace("nxg = 500", "nxg = 100").replace("nyg = 500", "nyg = 100").replace("nzg = 500", "nzg = 100")
+    text = text.replace("[geometry]", "[geometry]\nmus = [10.0, 1.0, 5.0]\nmua = [0.5, 0.1, 1.0]\nhgg = [0.8, 0.9, 0.7]\nn = [1.5, 1.35, 1.4]")
+    cfg = smcrt.Config.loads(text)
+    engine.apply(cfg)
+    osc = oracle.OracleScene.from_config(cfg)
+    n = 10000
+    g = engine.trace_packets(n, 3)
+    o = osc.run(n, 3, per_packet=True, grids=False)
+    assert (g["fate"] == A.FATE_LOST).sum() <= 2
+    ensemble_close(g, o, n)

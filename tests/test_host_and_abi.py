@@ -108,10 +108,15 @@ def test_shipped_configs_parse_and_build(smcrt):
     for name, (geom, ntop) in expect.items():
         cfg = smcrt.Config.load(RES / name)
         assert cfg.geom_name == geom and cfg.scene.n_top == ntop, name
-    # geometries that do not exist in the reference dispatcher either fail the same way
-    for name in ("jacques.toml", "skin.toml", "lens.toml"):
-        with pytest.raises(smcrt.SmcrtError):
-            smcrt.Config.load(RES / name)
+    # jacques / skin / lens do not exist in the reference dispatcher: builder-defined here
+    assert smcrt.Config.load(RES / "jacques.toml").scene.n_top == 2
+    lens = smcrt.Config.load(RES / "lens.toml").scene
+    assert lens.kind[lens.top_node[0]] == A.MODEL_INTERSECTION and lens.n[0] == 1.5
+    skin = smcrt.Config.load(RES / "skin_b200.toml").scene
+    assert skin.n_top == 6 and skin.params[:5, 2].sum() == pytest.approx(0.05)  # half thicknesses of the five layers
+    with pytest.raises(smcrt.SmcrtError) as e:  # the shipped skin.toml omits point1..3 (parse_source.f90:206-214)
+        smcrt.Config.load(RES / "skin.toml")
+    assert "point1" in str(e.value)
     with pytest.raises(smcrt.SmcrtError) as e:
         smcrt.Config.load(RES / "vessels.toml")  # needs res/{edges,nodes,radii}.dat
     assert "edges.dat" in str(e.value)

@@ -185,6 +185,10 @@ int smcrt_fetch(smcrt_ctx* ctx, float* jmean, float* absorb, float* emission, do
                 smcrt_counters* counters, int accumulate);
 /* zarray + detector reset (setup.f90:192-205, kernelsMod.f90:2418-2439) */
 int smcrt_reset_tallies(smcrt_ctx* ctx);
+/* Page-lock (cudaHostRegister) / release a host buffer that smcrt_fetch will be given repeatedly, e.g. the module arrays
+   jmean/absorb/emission of src/iarray.f90: device->host copies into pinned memory run at full PCIe/C2C bandwidth. Optional. */
+int smcrt_pin_host(void* ptr, uint64_t bytes);
+int smcrt_unpin_host(void* ptr);
 
 /* ---- multi-process (one rank per GPU) reduce, NCCL over NVLink ------------------------------ */
 /* rank 0 calls smcrt_comm_unique_id (128 bytes), the host broadcasts it (MPI / torch.distributed / file),

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "smcrt_launch_count": (C.c_int64, [C.c_void_p]),
     "smcrt_fetch": (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_double_p, C.POINTER(Counters), C.c_int]),
     "smcrt_reset_tallies": (C.c_int, [C.c_void_p]),
+    "smcrt_pin_host": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "smcrt_unpin_host": (C.c_int, [C.c_void_p]),
     "smcrt_comm_unique_id": (C.c_int, [C.c_char_p]),
     "smcrt_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "smcrt_comm_reduce": (C.c_int, [C.c_void_p, C.c_int]),

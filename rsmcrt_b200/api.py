@@ -265,6 +265,22 @@ class Engine:
         out["counters"] = cn.as_dict()
         return out
 
+    def fetch_into(self, absorb=None, jmean=None, emission=None, det_bins=None, accumulate=False):
+        """smcrt_fetch into caller-owned (ideally pinned, see pin_host) float32 / float64 buffers. -> counters dict."""
+        cn = Counters()
+        ptr = lambda a, t: None if a is None else _p(a, t)
+        check(self._L.smcrt_fetch(self._h, ptr(jmean, C.c_float), ptr(absorb, C.c_float), ptr(emission, C.c_float),
+                                  ptr(det_bins, C.c_double), C.byref(cn), int(accumulate)))
+        return cn.as_dict()
+
+    @staticmethod
+    def pin_host(a: np.ndarray):
+        check(_lib.load().smcrt_pin_host(a.ctypes.data, a.nbytes))
+
+    @staticmethod
+    def unpin_host(a: np.ndarray):
+        check(_lib.load().smcrt_unpin_host(a.ctypes.data))
+
     def reset_tallies(self):
         check(self._L.smcrt_reset_tallies(self._h))
 

@@ -492,6 +492,7 @@ extern "C" int smcrt_set_detectors(smcrt_ctx* c, int n, const int32_t* kind, con
             }
             default: return set_err("Invalid detector type. Valid types are [circle, annulus, camera]");
         }
+        D.q[13] = (float)((double)D.pos[0] * (double)D.dir[0] + (double)D.pos[1] * (double)D.dir[1] + (double)D.pos[2] * (double)D.dir[2]);
         D.offset = (int)off;
         hd[i] = HostDet{kind[i], nb, stored, count, off};
         off += count;
@@ -820,6 +821,16 @@ extern "C" int smcrt_reset_tallies(smcrt_ctx* c) {
     c->touched_modes = 0;
     for (DeviceState& D : c->devs)
         if ((rc = zero_device_tallies(c, D))) return rc;
+    return 0;
+}
+
+extern "C" int smcrt_pin_host(void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return set_err("smcrt_pin_host: null buffer");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int smcrt_unpin_host(void* ptr) {
+    CU(cudaHostUnregister(ptr));
     return 0;
 }
 

@@ -620,10 +620,12 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     do {                                                                                                              \
         for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                       \
             const DevDet* D_ = &sc.dets[i_];                                                                          \
-            /* plane side function g(x) = (p0 - x).n at both ends: a crossing needs g(start) >= 0 > g(end) */         \
-            const float gs_ = (D_->pos[0] - sx) * D_->dir[0] + (D_->pos[1] - sy) * D_->dir[1] + (D_->pos[2] - sz) * D_->dir[2]; \
-            const float ge_ = (D_->pos[0] - px) * D_->dir[0] + (D_->pos[1] - py) * D_->dir[1] + (D_->pos[2] - pz) * D_->dir[2]; \
-            if (D_->kind == 4 || (gs_ >= 0.f && ge_ < 0.f)) {                                                         \
+            /* cheap reject with the plane side function g(x) = p0.n - x.n (q[13] = p0.n): a crossing needs g(start) >= 0 > g(end). */ \
+            /* Conservative by a rounding margin; the exact watertight test is repeated inside detector_bin. */       \
+            const float nx_ = D_->dir[0], ny_ = D_->dir[1], nz_ = D_->dir[2], c_ = D_->q[13];                        \
+            const float gs_ = c_ - (sx * nx_ + sy * ny_ + sz * nz_), ge_ = c_ - (px * nx_ + py * ny_ + pz * nz_);     \
+            const float m_ = 4.0e-7f * (fabsf(c_) + fabsf(sx) + fabsf(sy) + fabsf(sz));                               \
+            if (D_->kind == 4 || (gs_ >= -m_ && ge_ < m_)) {                                                          \
                 const int b_ = detector_bin(D_, sx, sy, sz, ux, uy, uz, px, py, pz);                                  \
                 if (b_ > 0) {                                                                                         \
                     const float w_ = D_->kind == 4 ? 1.0f : weight;                                                   \

@@ -95,6 +95,9 @@ struct DeviceState {
     float *jmean = nullptr, *absorb = nullptr, *emission = nullptr;
     unsigned long long* det_bins = nullptr;
     unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last)
+    int* cull_start = nullptr;
+    int* cull_items = nullptr;
+    float* cull_far = nullptr;
     nccl::ncclComm_t comm = nullptr;
     int sm_count = 148;
     bool ran = false;
@@ -137,6 +140,11 @@ struct smcrt_ctx {
     double last_ms = 0;
     long long launches = 0;
     bool pending = false;
+    // culling grid (built at upload time for scenes with many top-level SDFs)
+    bool cull_on = false, cull_allowed = true, scene_lipschitz = true;
+    int cull_n[3] = {0, 0, 0};
+    double cull_lo[3] = {0, 0, 0}, cull_cell[3] = {1, 1, 1};
+    double cull_mean_list = 0;
     int touched_modes = 0;   // OR of the tally modes run since the last reset: only those grids are reduced
     long long dbg_pid = -1;
     float* dbg_log = nullptr;
@@ -161,6 +169,7 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
     if (n_gpus == 0) n_gpus = avail;
     if (n_gpus < 0 || n_gpus > avail) return set_err("smcrt_create: %d GPUs requested, %d visible", n_gpus, avail);
     smcrt_ctx* c = new smcrt_ctx();
+    c->cull_allowed = getenv("SMCRT_NO_CULL") == nullptr;  // A/B switch for the culling grid (tests, profiling)
     c->devs.resize(n_gpus);
     for (int g = 0; g < n_gpus; ++g) {
         DeviceState& D = c->devs[g];
@@ -205,6 +214,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
         cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters);
+        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far);
         if (D.ev0) cudaEventDestroy(D.ev0);
         if (D.ev1) cudaEventDestroy(D.ev1);
         if (D.stream) cudaStreamDestroy(D.stream);
@@ -217,6 +227,7 @@ extern "C" int smcrt_set_grid(smcrt_ctx* c, int nxg, int nyg, int nzg, double xm
     if (nxg < 1 || nyg < 1 || nzg < 1 || !(xmax > 0) || !(ymax > 0) || !(zmax > 0)) return set_err("smcrt_set_grid: invalid grid");
     c->nxg = nxg; c->nyg = nyg; c->nzg = nzg;
     c->gmax[0] = xmax; c->gmax[1] = ymax; c->gmax[2] = zmax;
+    c->scene_dirty = true;  // the culling grid spans the voxel-grid box
     const size_t bytes = (size_t)nxg * nyg * nzg * sizeof(float);
     for (DeviceState& D : c->devs) {
         free_grids(D);
@@ -379,6 +390,20 @@ extern "C" int smcrt_set_scene(smcrt_ctx* c, int n_nodes, const int32_t* kind, c
         }
         set_optics(T, mus[t], mua[t], hgg[t], n_ref[t]);
     }
+    // culling needs |d(p) - d(q)| <= |p - q|: true for every primitive and CSG/modifier of the reference except twist / bend
+    // (they warp space) and for rigid transforms only
+    bool lip = true;
+    for (int i = 0; i < n_nodes; ++i) {
+        if (kind[i] == SMCRT_MOD_TWIST || kind[i] == SMCRT_MOD_BEND) lip = false;
+        const double* m = xform + 16 * (size_t)i;
+        for (int a = 0; a < 3 && lip; ++a)
+            for (int b = 0; b < 3; ++b) {
+                double dot = 0;
+                for (int k = 0; k < 3; ++k) dot += m[a * 4 + k] * m[b * 4 + k];
+                if (std::fabs(dot - (a == b ? 1.0 : 0.0)) > 1e-9) lip = false;
+            }
+    }
+    c->scene_lipschitz = lip;
     c->prims.swap(prims); c->primsD.swap(primsD); c->prog.swap(prog); c->progD.swap(progD); c->tops.swap(tops);
     c->opt_mus.assign(mus, mus + n_top); c->opt_mua.assign(mua, mua + n_top);
     c->opt_hgg.assign(hgg, hgg + n_top); c->opt_n.assign(n_ref, n_ref + n_top);
@@ -522,6 +547,86 @@ extern "C" int smcrt_set_tolerances(smcrt_ctx* c, double eps0, double eps_rel, i
 
 // ---- upload ----------------------------------------------------------------------------------------------
 static int align16(int v) { return (v + 15) & ~15; }
+static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P);
+static const int CULL_MIN_TOPS = 8;  // below this the uniform sweep is cheaper than the indirection
+
+// Culling grid.  For every coarse cell: dc_j = d_j(centre) in FP64 on the GPU, h = half diagonal
+// (+ slack); 1-Lipschitz => d_j in [dc_j - h, dc_j + h] over the cell.
+//   A (can attain min|d|):           |dc_j| - h <= U,  U = min_k (|dc_k| + h)
+//   B (can be the innermost negative): dc_j - h < 0 and dc_j + h >= M,  M = max{ dc_k - h : dc_k + h < 0 }
+// list = A u B (ascending index, so the "ties -> lowest index" rule of maxloc survives); far = min over the rest of |dc_j| - h.
+static int build_cull(smcrt_ctx* c) {
+    c->cull_on = false;
+    const int nt = (int)c->tops.size();
+    for (DeviceState& D : c->devs) {
+        cudaSetDevice(D.dev);
+        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far);
+        D.cull_start = D.cull_items = nullptr; D.cull_far = nullptr;
+    }
+    if (!c->cull_allowed || !c->scene_lipschitz || nt < CULL_MIN_TOPS || c->nxg == 0) return 0;
+    int G = (int)std::lround(std::cbrt((double)nt) * 6.0);
+    G = std::min(std::max(G, 8), 40);
+    double ext = 0;
+    for (int a = 0; a < 3; ++a) {
+        const double pad = 0.005 * c->gmax[a] + 1e-9;
+        c->cull_n[a] = G;
+        c->cull_lo[a] = -c->gmax[a] - pad;
+        c->cull_cell[a] = 2.0 * (c->gmax[a] + pad) / G;
+        ext = std::max(ext, c->gmax[a]);
+    }
+    const long long ncell = (long long)G * G * G, npair = ncell * nt;
+    const double h = 0.5 * std::sqrt(c->cull_cell[0] * c->cull_cell[0] + c->cull_cell[1] * c->cull_cell[1] + c->cull_cell[2] * c->cull_cell[2]) *
+                         (1.0 + 1e-6) + 2e-5 * ext;  // slack: FP32 evaluation of positions and distances inside the sweep
+    DeviceState& D0 = c->devs[0];
+    CU(cudaSetDevice(D0.dev));
+    float* dmat = nullptr;
+    CU(cudaMalloc(&dmat, sizeof(float) * (size_t)npair));
+    KParams P;
+    fill_params(c, D0, P);
+    cull_eval_kernel<<<(unsigned)std::min<long long>((npair + 255) / 256, 148 * 16), 256, 0, D0.stream>>>(
+        P, npair, c->cull_lo[0], c->cull_lo[1], c->cull_lo[2], c->cull_cell[0], c->cull_cell[1], c->cull_cell[2], G, G, dmat);
+    cudaError_t ke = cudaGetLastError();
+    if (ke != cudaSuccess) { cudaFree(dmat); return set_err("cull_eval_kernel: %s", cudaGetErrorString(ke)); }
+    std::vector<float> dc((size_t)npair);
+    ke = cudaMemcpyAsync(dc.data(), dmat, sizeof(float) * (size_t)npair, cudaMemcpyDeviceToHost, D0.stream);
+    if (ke == cudaSuccess) ke = cudaStreamSynchronize(D0.stream);
+    cudaFree(dmat);
+    if (ke != cudaSuccess) return set_err("culling grid: %s", cudaGetErrorString(ke));
+    c->launches += 1;
+    std::vector<int> start((size_t)ncell + 1, 0), items;
+    std::vector<float> far((size_t)ncell);
+    items.reserve((size_t)ncell * 4);
+    for (long long cell = 0; cell < ncell; ++cell) {
+        const float* d = dc.data() + cell * nt;
+        double U = 1e300, M = -1e300;
+        for (int j = 0; j < nt; ++j) {
+            U = std::min(U, std::fabs((double)d[j]) + h);
+            if (d[j] + h < 0) M = std::max(M, (double)d[j] - h);
+        }
+        double f = 3.0e38;
+        for (int j = 0; j < nt; ++j) {
+            const bool A = std::fabs((double)d[j]) - h <= U;
+            const bool B = (d[j] - h < 0) && (d[j] + h >= M);
+            if (A || B) items.push_back(j);
+            else f = std::min(f, std::fabs((double)d[j]) - h);
+        }
+        start[cell + 1] = (int)items.size();
+        far[cell] = (float)f;
+    }
+    c->cull_mean_list = (double)items.size() / (double)ncell;
+    if (c->cull_mean_list > 0.6 * nt) return 0;  // nothing to gain on this scene
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaMalloc(&D.cull_start, sizeof(int) * start.size()));
+        CU(cudaMalloc(&D.cull_items, sizeof(int) * std::max<size_t>(items.size(), 1)));
+        CU(cudaMalloc(&D.cull_far, sizeof(float) * far.size()));
+        CU(cudaMemcpy(D.cull_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(D.cull_items, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(D.cull_far, far.data(), sizeof(float) * far.size(), cudaMemcpyHostToDevice));
+    }
+    c->cull_on = true;
+    return 0;
+}
 static int upload_scene(smcrt_ctx* c) {
     if (!c->scene_dirty) return 0;
     if (c->tops.empty()) return set_err("no scene set (smcrt_set_scene)");
@@ -548,7 +653,7 @@ static int upload_scene(smcrt_ctx* c) {
         if (!c->progD.empty()) CU(cudaMemcpy(D.progD, c->progD.data(), c->progD.size() * sizeof(DevInstrD), cudaMemcpyHostToDevice));
     }
     c->scene_dirty = false;
-    return 0;
+    return build_cull(c);
 }
 
 static const int SMEM_BIN_CAP = 8192;  // 64 KB of CTA-private Q40.24 bins at most
@@ -574,6 +679,14 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.det_bins = D.det_bins; P.det_total = (int)c->det_total;
     P.det_in_smem = (c->det_total > 0 && c->det_total <= SMEM_BIN_CAP) ? 1 : 0;
     P.counters = D.counters; P.next = D.counters + C_COUNT;
+    if (c->cull_on) {
+        P.cull_start = D.cull_start; P.cull_items = D.cull_items; P.cull_far = D.cull_far;
+        for (int a = 0; a < 3; ++a) {
+            P.cull_n[a] = c->cull_n[a];
+            P.cull_lo[a] = (float)c->cull_lo[a];
+            P.cull_inv[a] = (float)(1.0 / c->cull_cell[a]);
+        }
+    }
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     P.max_steps = (int)std::min<long long>(c->max_steps, 2000000000ll);
     return 0;

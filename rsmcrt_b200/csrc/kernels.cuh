@@ -23,6 +23,12 @@ struct KParams {
     int off_tops, off_prog, off_dets;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
     const DevInstrD* progD;
+    // culling grid: per coarse cell the candidate list of top-level SDFs; null = evaluate all
+    const int* cull_start;     // [ncell + 1]
+    const int* cull_items;     // top-level SDF indices (0-based), ascending inside a cell
+    const float* cull_far;     // [ncell] lower bound of |d| of every SDF NOT in the cell's list, for any point of the cell
+    int cull_n[3];
+    float cull_lo[3], cull_inv[3];  // cell = floor((x - lo) * inv)
     // voxel grid (src/grid.f90:14-25)
     int nxg, nyg, nzg;
     float gmax[3];     // half extents
@@ -151,30 +157,46 @@ __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc,
 // maxloc(ds, mask=ds<0): innermost surface wins, ties -> lowest index, none -> 0), value there, and the value of
 // SDF `layer` (1-based).   src/inttau2.f90:63-68,80-84,135-139,179-183,216-221,229-234
 struct Sweep {
-    float amin, smin, dL, dcur, bmin;
+    float amin, smin, dL, bmin;
     int L;
     bool bexact;
 };
-__device__ __forceinline__ Sweep sweep_all(const SceneView& sc, float x, float y, float z, float ux, float uy, float uz, int layer) {
-    Sweep s;
-    s.amin = SMCRT_BIG; s.smin = SMCRT_BIG; s.dL = -SMCRT_BIG; s.dcur = 0.f; s.L = 0; s.bmin = SMCRT_BIG; s.bexact = false;
-    const int n = sc.n_top;
-    for (int i = 0; i < n; ++i) {
-        float d, b;
-        bool ex;
-        const int mode = sc.tops[i].mode, first = sc.tops[i].first;
-        if (mode == 0) d = eval_prim_ray(sc.prims[first], x, y, z, ux, uy, uz, b, ex);
-        else {
-            d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[i].count, x, y, z);
-            b = fabsf(d);
-            ex = false;
-        }
-        s.amin = fminf(s.amin, fabsf(d));
-        s.smin = fminf(s.smin, d);
-        if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
-        if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
-        if (i + 1 == layer) s.dcur = d;
+__device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, Sweep& s) {
+    float d, b;
+    bool ex;
+    const int mode = sc.tops[i].mode, first = sc.tops[i].first;
+    if (mode == 0) d = eval_prim_ray(sc.prims[first], x, y, z, ux, uy, uz, b, ex);
+    else {
+        d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[i].count, x, y, z);
+        b = fabsf(d);
+        ex = false;
     }
+    s.amin = fminf(s.amin, fabsf(d));
+    s.smin = fminf(s.smin, d);
+    if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
+    if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
+}
+// Culled sweep: only the SDFs that can matter for a point of this coarse cell are evaluated.  The host builds, per cell, the
+// list of SDFs that can attain min|d| or be the innermost negative one somewhere in the cell (interval bounds from the value at
+// the cell centre and 1-Lipschitz continuity), plus `far`: a lower bound of |d| of all the others.  The min / argmax over the
+// list equals the min / argmax over all SDFs for every point of the cell, and a step is additionally capped by `far`.
+__device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc, float x, float y, float z, float ux, float uy, float uz) {
+    Sweep s;
+    s.amin = SMCRT_BIG; s.smin = SMCRT_BIG; s.dL = -SMCRT_BIG; s.L = 0; s.bmin = SMCRT_BIG; s.bexact = false;
+    if (P.cull_start) {
+        const int cx = (int)floorf((x - P.cull_lo[0]) * P.cull_inv[0]), cy = (int)floorf((y - P.cull_lo[1]) * P.cull_inv[1]),
+                  cz = (int)floorf((z - P.cull_lo[2]) * P.cull_inv[2]);
+        if (cx >= 0 && cx < P.cull_n[0] && cy >= 0 && cy < P.cull_n[1] && cz >= 0 && cz < P.cull_n[2]) {
+            const int c = cx + P.cull_n[0] * (cy + P.cull_n[1] * cz);
+            const int i0 = __ldg(P.cull_start + c), i1 = __ldg(P.cull_start + c + 1);
+            for (int k = i0; k < i1; ++k) sweep_one(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, s);
+            const float far = __ldg(P.cull_far + c);
+            if (far < s.bmin) { s.bmin = fmaxf(far, s.amin); s.bexact = false; }  // never step past an unlisted surface
+            return s;
+        }
+    }
+    const int n = sc.n_top;
+    for (int i = 0; i < n; ++i) sweep_one(sc, i, x, y, z, ux, uy, uz, s);
     return s;
 }
 
@@ -596,7 +618,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     // half an ulp of a coordinate is lost and rays grazing a wall stop converging.
     double pxd = 0, pyd = 0, pzd = 0;
     float px = 0, py = 0, pz = 0, ux = 0, uy = 0, uz = 1, sx = 0, sy = 0, sz = 0;  // position, direction, segment start
-    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f, dnew_L = 0.f, dnew_cur = 0.f;
+    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
     int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0;
     bool tflag = false, launch = false, have_pid = false;
     int phase = 0;  // of ST_MARCH: 0 = top of the tauint2 loop, 1 = re-evaluation after a boundary nudge, 2 = inside the sphere-trace loop
@@ -692,6 +714,10 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 // inttau2.f90:248-317: which surface is being crossed, its normal, Fresnel reflect/refract
                 const float ds_pos_new = eval_top_f(sc, new_layer - 1, px, py, pz);  // ds(new_layer)
                 const float ds_pos_cur = eval_top_f(sc, layer - 1, px, py, pz);      // ds(old_layer)
+                const float bx = (float)(pxd + (double)dstep * (double)ux), by = (float)(pyd + (double)dstep * (double)uy),
+                            bz = (float)(pzd + (double)dstep * (double)uz);          // the crossing probe point (same bits as the sweep's)
+                const float dnew_L = eval_top_f(sc, new_layer - 1, bx, by, bz);      // dsNew(new_layer)
+                const float dnew_cur = eval_top_f(sc, layer - 1, bx, by, bz);        // dsNew(old_layer)
                 int surf;
                 if (dnew_L < 0.f && ds_pos_new >= 0.f) surf = new_layer;
                 else if (dnew_cur >= 0.f && ds_pos_cur < 0.f) surf = layer;
@@ -805,7 +831,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
         if (state <= ST_CROSS) {
             const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
                         qz = (float)(pzd + (double)qs * (double)uz);
-            const Sweep S = sweep_all(sc, qx, qy, qz, ux, uy, uz, layer);
+            const Sweep S = sweep_all(P, sc, qx, qy, qz, ux, uy, uz);
             ++c_sweeps;
             const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
             // ---------------- transition, part A (divergent, cheap): decide how far to move and what happens next
@@ -885,7 +911,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                     tflag = true;
                     post = POST_FINISH;
                 } else if (sc.tops[layer - 1].n != sc.tops[S.L - 1].n) {
-                    new_layer = S.L; dnew_L = S.dL; dnew_cur = S.dcur;
+                    new_layer = S.L;
                     state = ST_FRESNEL;
                 } else {  // :318-337
                     layer = S.L;
@@ -930,6 +956,24 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(&P.counters[c], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ culling-grid set-up
+// One thread per (cell, top-level SDF): FP64 distance at the cell centre.  The host turns the matrix into candidate lists.
+__global__ void cull_eval_kernel(const __grid_constant__ KParams P, long long n_pairs, double lox, double loy, double loz, double dx, double dy,
+                                 double dz, int nx, int ny, float* out) {
+    SceneView sc;
+    sc.prims = reinterpret_cast<const DevPrim*>(P.blob);
+    sc.tops = reinterpret_cast<const DevTop*>(P.blob + P.off_tops);
+    sc.prog = reinterpret_cast<const DevInstr*>(P.blob + P.off_prog);
+    sc.dets = reinterpret_cast<const DevDet*>(P.blob + P.off_dets);
+    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % P.n_top);
+        const long long c = i / P.n_top;
+        const int cx = (int)(c % nx), cy = (int)((c / nx) % ny), cz = (int)(c / ((long long)nx * ny));
+        out[i] = (float)eval_top_d(P, sc, t, lox + (cx + 0.5) * dx, loy + (cy + 0.5) * dy, loz + (cz + 0.5) * dz);
     }
 }
 

@@ -141,7 +141,7 @@ struct smcrt_ctx {
     long long launches = 0;
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
-    bool cull_on = false, cull_allowed = true, scene_lipschitz = true;
+    bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
     int cull_n[3] = {0, 0, 0};
     double cull_lo[3] = {0, 0, 0}, cull_cell[3] = {1, 1, 1};
     double cull_mean_list = 0;
@@ -170,6 +170,8 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
     if (n_gpus < 0 || n_gpus > avail) return set_err("smcrt_create: %d GPUs requested, %d visible", n_gpus, avail);
     smcrt_ctx* c = new smcrt_ctx();
     c->cull_allowed = getenv("SMCRT_NO_CULL") == nullptr;  // A/B switch for the culling grid (tests, profiling)
+    // Event compaction is OPT-IN: measured slower than the plain persistent loop on every shipped scene
+    c->compact_allowed = getenv("SMCRT_COMPACT") != nullptr;
     c->devs.resize(n_gpus);
     for (int g = 0; g < n_gpus; ++g) {
         DeviceState& D = c->devs[g];
@@ -692,9 +694,9 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     return 0;
 }
 
-template <bool PL, bool HD>
+template <bool PL, bool HD, bool CP>
 static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
-    auto kern = trace_persistent<PL, HD>;
+    auto kern = trace_persistent<PL, HD, CP>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
@@ -722,12 +724,21 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
     CU(cudaSetDevice(D.dev));
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
-    const int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
+    int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
+    // event compaction pays when the sweep is cheap (few SDFs) and the divergent event code dominates
+    const bool compact = c->compact_allowed && (int)c->tops.size() <= 4 && c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;
+    P.xchg_off = (smem + 15) & ~15;
+    if (compact) smem = P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK;
     CU(cudaEventRecord(D.ev0, D.stream));
     const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
     int rc;
-    if (pl) rc = hd ? launch_trace<true, true>(P, D, smem) : launch_trace<true, false>(P, D, smem);
-    else rc = hd ? launch_trace<false, true>(P, D, smem) : launch_trace<false, false>(P, D, smem);
+    if (compact) {
+        if (pl) rc = hd ? launch_trace<true, true, true>(P, D, smem) : launch_trace<true, false, true>(P, D, smem);
+        else rc = hd ? launch_trace<false, true, true>(P, D, smem) : launch_trace<false, false, true>(P, D, smem);
+    } else {
+        if (pl) rc = hd ? launch_trace<true, true, false>(P, D, smem) : launch_trace<true, false, false>(P, D, smem);
+        else rc = hd ? launch_trace<false, true, false>(P, D, smem) : launch_trace<false, false, false>(P, D, smem);
+    }
     if (rc) return rc;
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;

@@ -55,6 +55,7 @@ struct KParams {
     float threshold, chance;
     float eps0, eps_rel;
     int max_steps;
+    int xchg_off;   // byte offset of the compaction scratch in dynamic shared memory (16-byte aligned)
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
     int* out_nscatt;
@@ -592,7 +593,9 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #ifndef SMCRT_MINBLOCKS
 #define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
 #endif
-template <bool PATHLEN, bool HASDET>
+constexpr int XCHG_WORDS = 26;  // 32-bit words of packet state exchanged by the compaction step
+
+template <bool PATHLEN, bool HASDET, bool COMPACT>
 __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
@@ -601,6 +604,11 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
         for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     unsigned long long* sbins = reinterpret_cast<unsigned long long*>(smem + P.blob_bytes);
+    // compaction scratch (COMPACT only): per-state totals (double buffered) and one slot of XCHG_WORDS words per thread
+    uint32_t* xtot = reinterpret_cast<uint32_t*>(smem + P.xchg_off);
+    uint32_t* xbuf = xtot + 16;
+    if (COMPACT && threadIdx.x < 16) xtot[threadIdx.x] = 0u;
+    uint32_t xiter = 0;
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
     __syncthreads();
@@ -822,7 +830,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 }
             }
         }
-        if (__all_sync(__activemask(), state == ST_DONE)) break;
+        if (!COMPACT && __all_sync(__activemask(), state == ST_DONE)) break;
         // cold or done lanes sit the sweep out
 
         // ===================================== sweep =====================================
@@ -935,6 +943,57 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
         }
         if (HASDET && det) DETECT();
         if (post == POST_FINISH) FINISH();
+
+        if (COMPACT) {
+            // ============================ event compaction ============================
+            // Counting sort of the CTA's packets by state through shared memory: afterwards the lanes of a warp are (mostly)
+            // in the same state, so the divergent cold blocks / transitions run with full warps.  Order inside a bucket is
+            // irrelevant.  Two barriers per iteration; the per-state totals are double buffered so that zeroing never races.
+            const unsigned full = 0xffffffffu;
+            uint32_t* tot = xtot + 8 * (xiter & 1u);
+            const unsigned same = __match_any_sync(full, state);
+            const int rank = __popc(same & ((1u << lane) - 1u));
+            const int lead = __ffs(same) - 1;
+            uint32_t woff = 0;
+            if (lane == lead) woff = atomicAdd(&tot[state], (uint32_t)__popc(same));
+            woff = __shfl_sync(full, woff, lead);
+            __syncthreads();  // (A) totals complete; everybody has consumed the previous exchange
+            if (threadIdx.x < 8) xtot[8 * ((xiter + 1u) & 1u) + threadIdx.x] = 0u;
+            uint32_t base = 0;
+#pragma unroll
+            for (int k = 0; k < ST_DONE; ++k) base += (k < state) ? tot[k] : 0u;
+            const bool all_done = tot[ST_DONE] == (uint32_t)blockDim.x;
+            uint32_t* w = xbuf + (base + woff + (uint32_t)rank);
+            const int B = blockDim.x;
+            w[0 * B] = (uint32_t)__double2loint(pxd); w[1 * B] = (uint32_t)__double2hiint(pxd);
+            w[2 * B] = (uint32_t)__double2loint(pyd); w[3 * B] = (uint32_t)__double2hiint(pyd);
+            w[4 * B] = (uint32_t)__double2loint(pzd); w[5 * B] = (uint32_t)__double2hiint(pzd);
+            w[6 * B] = __float_as_uint(ux); w[7 * B] = __float_as_uint(uy); w[8 * B] = __float_as_uint(uz);
+            w[9 * B] = __float_as_uint(sx); w[10 * B] = __float_as_uint(sy); w[11 * B] = __float_as_uint(sz);
+            w[12 * B] = __float_as_uint(tau); w[13 * B] = __float_as_uint(taurun); w[14 * B] = __float_as_uint(dstep);
+            w[15 * B] = __float_as_uint(qs); w[16 * B] = __float_as_uint(dlast); w[17 * B] = __float_as_uint(weight);
+            w[18 * B] = (uint32_t)layer | ((uint32_t)new_layer << 16);
+            w[19 * B] = (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u);
+            w[20 * B] = (uint32_t)bounces; w[21 * B] = (uint32_t)steps; w[22 * B] = (uint32_t)pk_nscatt;
+            w[23 * B] = (uint32_t)pid; w[24 * B] = (uint32_t)(pid >> 32); w[25 * B] = ev;
+            __syncthreads();  // (B) all slots written
+            if (all_done) break;
+            const uint32_t* r = xbuf + threadIdx.x;
+            pxd = __hiloint2double((int)r[1 * B], (int)r[0 * B]);
+            pyd = __hiloint2double((int)r[3 * B], (int)r[2 * B]);
+            pzd = __hiloint2double((int)r[5 * B], (int)r[4 * B]);
+            px = (float)pxd; py = (float)pyd; pz = (float)pzd;
+            ux = __uint_as_float(r[6 * B]); uy = __uint_as_float(r[7 * B]); uz = __uint_as_float(r[8 * B]);
+            sx = __uint_as_float(r[9 * B]); sy = __uint_as_float(r[10 * B]); sz = __uint_as_float(r[11 * B]);
+            tau = __uint_as_float(r[12 * B]); taurun = __uint_as_float(r[13 * B]); dstep = __uint_as_float(r[14 * B]);
+            qs = __uint_as_float(r[15 * B]); dlast = __uint_as_float(r[16 * B]); weight = __uint_as_float(r[17 * B]);
+            layer = (int)(r[18 * B] & 0xffffu); new_layer = (int)(r[18 * B] >> 16);
+            const uint32_t fl = r[19 * B];
+            state = (int)(fl & 15u); phase = (int)((fl >> 4) & 15u); tflag = (fl & 256u) != 0; launch = (fl & 512u) != 0; have_pid = (fl & 1024u) != 0;
+            bounces = (int)r[20 * B]; steps = (int)r[21 * B]; pk_nscatt = (int)r[22 * B];
+            pid = (unsigned long long)r[23 * B] | ((unsigned long long)r[24 * B] << 32); ev = r[25 * B];
+            ++xiter;
+        }
     }
 
 #undef ADVANCE

@@ -906,12 +906,15 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 qs = 0.f;
                 state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
             } else {  // ST_CROSS :220-337
-                if ((S.L == layer && S.amin < eps) || S.amin < 0.5f * eps) {
+                if (S.L != 0 && S.amin < eps) {
                     // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
                     // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment
                     // doubles here (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) sweeps.
-                    // FP32: a probe point closer than eps/2 (~2 ulp of the coordinate) to ANY surface has unreliable signs, so
-                    // its layer classification is not trusted either; keep lengthening the probe.
+                    // The reference creeps only while the probe is still in the old layer.  Here it creeps until the probe is at
+                    // least eps away from EVERY surface: (i) FP32 signs closer than ~2 ulp to a surface are rounding noise, so the
+                    // probe's layer classification is only trusted at a clear distance; (ii) the packet then lands
+                    // clear of the boundary and the next tauint2 loop does not start with the on-boundary nudge (2 sweeps saved
+                    // per oblique crossing).  The extra probe length is paid for in optical depth like the rest of the probe.
                     dstep += dlast;
                     dlast = fminf(2.0f * dlast, 256.0f * eps);
                     qs = dstep;

@@ -37,6 +37,9 @@ F_PRIM = {1: 25, 2: 37, 3: 28, 4: 70, 5: 23, 6: 47, 7: 47, 8: 80, 9: 45, 10: 23}
 F_FRESNEL, F_HG, F_DET_CIRCLE, F_VOXEL, F_EMIT = 45, 60, 30, 9, 20
 # flops/packet of the reference algorithm (oracle counters x the table above), as printed by N=1 runs of this file
 ALGORITHMIC_FLOPS = {"validation1.toml": 7399.0}
+# DRAM bytes (read + write) of ONE launch of the dominant kernel at the default packets/step, from the ncu --set full capture of
+# this command (profiles/r01_bench_top_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRAFFIC_BYTES = {("validation1.toml", 100_000_000): 73.4e6}
 
 
 def flops_per_sweep(scene) -> float:
@@ -335,7 +338,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                     "traffic": None,
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.scene, n_step)),
                      "note": "path is FP32/SFU-issue bound, not HBM or tensor (SURVEY 8d); achieved = packets/s x algorithmic flops/packet "
                              f"({w_flop:.0f}, from {w_basis} x frozen op table in bench.py); peak = 148 SM x 128 lanes x 2 x sm_max_mhz "
                              "(nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",

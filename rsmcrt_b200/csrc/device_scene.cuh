@@ -191,6 +191,7 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
 // layer and deposits are linear along a straight ray), in one step instead of O(log(1/eps)/(1-cos)).
 // Kinds without a closed form keep b = |d| (plain sphere tracing).  *exact tells whether b is an exact hit distance.
 #define SMCRT_BIG 3.0e38f
+__device__ __noinline__ float eval_prim_generic(const PrimT<float>& P, float x, float y, float z) { return eval_prim<float>(P, x, y, z); }
 __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz,
                                                float& bound, bool& exact) {
     float px, py, pz, vx = ux, vy = uy, vz = uz;
@@ -251,7 +252,7 @@ __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, f
         exact = true;
         return d;
     }
-    const float d = eval_prim<float>(P, x, y, z);
+    const float d = eval_prim_generic(P, x, y, z);  // out of line: keeps the hot loop small (I-cache)
     bound = fabsf(d);
     exact = false;
     return d;

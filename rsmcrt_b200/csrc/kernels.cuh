@@ -305,6 +305,8 @@ __device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y
 }
 // Warp-aggregated deposit: lanes of the converged group that hit the same voxel are summed with shuffles and
 // ONE red.global.add.f32 is issued per distinct voxel.
+// NB must stay inlined: __activemask() inside a called (noinline) function does not name the lanes that called it together,
+// and the aggregation then loses deposits (measured: wrong emission totals) besides being 25 % slower.
 __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
     const unsigned active = __activemask();
     const unsigned peers = __match_any_sync(active, vox);
@@ -477,12 +479,16 @@ __device__ __forceinline__ void xform_pos(const float T[12], const float l[3], f
     o[2] = T[8] * l[0] + T[9] * l[1] + T[10] * l[2] + T[11];
 }
 __device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]);
-__device__ __forceinline__ bool emit_packet(const KParams& P, float u0, float u1, float u2, float& x, float& y, float& z, float& dx,
-                                            float& dy, float& dz) {
+struct Emitted {
+    float x, y, z, dx, dy, dz;
+    bool ok;
+};
+__device__ __noinline__ Emitted emit_packet(const KParams& P, float u0, float u1, float u2) {  // out of line: all source kinds live here
     float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
-    const bool ok = emit_packet_v(P, u0, u1, u2, pos, dir);
-    x = pos[0]; y = pos[1]; z = pos[2]; dx = dir[0]; dy = dir[1]; dz = dir[2];
-    return ok;
+    Emitted e;
+    e.ok = emit_packet_v(P, u0, u1, u2, pos, dir);
+    e.x = pos[0]; e.y = pos[1]; e.z = pos[2]; e.dx = dir[0]; e.dy = dir[1]; e.dz = dir[2];
+    return e;
 }
 __device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]) {
     const float* sp = P.sp;
@@ -593,6 +599,17 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #ifndef SMCRT_MINBLOCKS
 #define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
 #endif
+// optional per-packet record of smcrt_trace_packets (out of line: cold)
+__device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, int nscatt, uint32_t ev, int steps,
+                                           float x, float y, float z) {
+    const long long k = (long long)(pid - P.id_offset);
+    P.out_fate[k] = fate;
+    if (P.out_nscatt) P.out_nscatt[k] = nscatt;
+    if (P.out_events) P.out_events[k] = fate == 3 ? -why : (int)ev;
+    if (P.out_sweeps) P.out_sweeps[k] = steps;
+    if (P.out_pos) { P.out_pos[3 * k] = x; P.out_pos[3 * k + 1] = y; P.out_pos[3 * k + 2] = z; }
+}
+
 constexpr int XCHG_WORDS = 26;  // 32-bit words of packet state exchanged by the compaction step
 
 template <bool PATHLEN, bool HASDET, bool COMPACT>
@@ -672,14 +689,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     // packet finished: publish the optional per-packet record and ask for a new packet
 #define RETIRE(FATE, WHY)                                                                                             \
     do {                                                                                                              \
-        if (P.out_fate) {                                                                                             \
-            const long long k_ = (long long)(pid - P.id_offset);                                                      \
-            P.out_fate[k_] = (FATE);                                                                                  \
-            if (P.out_nscatt) P.out_nscatt[k_] = pk_nscatt;                                                           \
-            if (P.out_events) P.out_events[k_] = (FATE) == FATE_LOST ? -(WHY) : (int)ev;                              \
-            if (P.out_sweeps) P.out_sweeps[k_] = steps;                                                               \
-            if (P.out_pos) { P.out_pos[3 * k_] = px; P.out_pos[3 * k_ + 1] = py; P.out_pos[3 * k_ + 2] = pz; }        \
-        }                                                                                                             \
+        if (P.out_fate) record_packet(P, pid, (FATE), (WHY), pk_nscatt, ev, steps, px, py, pz);                       \
         c_bounces += bounces;                                                                                         \
         if ((FATE) == FATE_LOST) ++c_lost;                                                                            \
         state = ST_EMIT; have_pid = false;                                                                            \
@@ -815,8 +825,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                     state = ST_MARCH; phase = 0;
                 }
             } else {  // ST_EMIT with a packet id: one emission attempt per iteration (rejections retry next iteration)
-                const bool ok = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]), px, py, pz, ux, uy, uz);
-                if (ok && in_grid(P, px, py, pz)) {
+                const Emitted em = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]));
+                px = em.x; py = em.y; pz = em.z; ux = em.dx; uy = em.dy; uz = em.dz;
+                if (em.ok && in_grid(P, px, py, pz)) {
                     pxd = px; pyd = py; pzd = pz;
                     if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, px, py, pz), 1.0f);
                     tau = -logf(u01_open0(w[3]));

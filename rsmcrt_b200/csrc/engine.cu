@@ -672,6 +672,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
         P.gmax[a] = (float)c->gmax[a];
         P.vox[a] = (float)(2.0 * c->gmax[a] / nn[a]);
         P.inv_vox[a] = (float)(nn[a] / (2.0 * c->gmax[a]));
+        P.hvox[a] = (float)(c->gmax[a] / nn[a]);
     }
     P.src_kind = c->src_kind; P.src_sub = c->src_sub; P.src_alt = c->src_alt;
     std::memcpy(P.sp, c->sp, sizeof P.sp);
@@ -689,6 +690,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
             P.cull_inv[a] = (float)(1.0 / c->cull_cell[a]);
         }
     }
+    P.dda_plain = getenv("SMCRT_DDA_AGG") ? 0 : 1;
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     P.max_steps = (int)std::min<long long>(c->max_steps, 2000000000ll);
     return 0;

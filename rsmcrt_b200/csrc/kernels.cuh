@@ -34,6 +34,7 @@ struct KParams {
     float gmax[3];     // half extents
     float vox[3];      // voxel edge 2*max/n
     float inv_vox[3];  // n/(2*max)
+    float hvox[3];     // half a voxel edge, max/n (centre-origin cell faces of the DDA)
     // source (src/photon.f90), transforms precomputed on the host
     int src_kind, src_sub, src_alt;
     float sp[24];
@@ -56,6 +57,7 @@ struct KParams {
     float eps0, eps_rel;
     int max_steps;
     int xchg_off;   // byte offset of the compaction scratch in dynamic shared memory (16-byte aligned)
+    int dda_plain;  // 1: path-length deposits use plain red.global (no warp aggregation)
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
     int* out_nscatt;
@@ -309,7 +311,7 @@ __device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y
 // and the aggregation then loses deposits (measured: wrong emission totals) besides being 25 % slower.
 __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
     const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, vox);
+    const unsigned peers = __match_any_sync(active, (unsigned long long)(grid + vox));  // the ADDRESS: lanes of different grids never merge
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     float sum = w;
@@ -330,29 +332,48 @@ __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
 // (Default build: only the end-of-step voxel matters, see the WALK macro of the kernel.)  Arguments by value: a pointer
 // argument would force the caller's state into local memory.
 __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
-    // corner-origin coordinates
-    const float X = (fx + P.gmax[0]), Y = (fy + P.gmax[1]), Z = (fz + P.gmax[2]);
     if (!in_grid(P, fx, fy, fz)) return true;  // :411-415
-    int i = min((int)floorf(X * P.inv_vox[0]), P.nxg - 1), j = min((int)floorf(Y * P.inv_vox[1]), P.nyg - 1),
-        k = min((int)floorf(Z * P.inv_vox[2]), P.nzg - 1);  // min: the scaled coordinate may round up to n just inside the face
-    const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
+    // Cell faces are taken centre-origin, face(i) = (2i - n) * (max / n), so their rounding error scales with the face's own
+    // coordinate and not with max: with the corner-origin form (x + max) a packet on the beam axis of a wide grid
+    // (|x| << max) sees face - x wrong by ulp(max), and dividing that by a small direction cosine gives an arbitrarily
+    // large NEGATIVE first crossing distance, which the loop below would deposit as path that was never travelled.
+    const float f3[3] = {fx, fy, fz}, d3[3] = {dx, dy, dz};
+    const int n3[3] = {P.nxg, P.nyg, P.nzg};
+    int c3[3];
+    float t3[3], dt3[3];
     const float BIG = 3.0e38f;
-    float tx = dx != 0.f ? (((float)(i + (sx > 0)) * P.vox[0]) - X) / dx : BIG;
-    float ty = dy != 0.f ? (((float)(j + (sy > 0)) * P.vox[1]) - Y) / dy : BIG;
-    float tz = dz != 0.f ? (((float)(k + (sz > 0)) * P.vox[2]) - Z) / dz : BIG;
-    const float dtx = dx != 0.f ? P.vox[0] / fabsf(dx) : BIG;
-    const float dty = dy != 0.f ? P.vox[1] / fabsf(dy) : BIG;
-    const float dtz = dz != 0.f ? P.vox[2] / fabsf(dz) : BIG;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float hv = P.hvox[a];
+        int c = (int)floorf(fmaf(f3[a], P.inv_vox[a], 0.5f * (float)n3[a]));
+        c = min(max(c, 0), n3[a] - 1);
+        if (c > 0 && f3[a] < (float)(2 * c - n3[a]) * hv) --c;                       // make the cell agree with its own faces
+        else if (c < n3[a] - 1 && f3[a] >= (float)(2 * c + 2 - n3[a]) * hv) ++c;
+        c3[a] = c;
+        const float face = (float)(2 * (c + (d3[a] > 0.f)) - n3[a]) * hv;
+        t3[a] = d3[a] != 0.f ? fmaxf((face - f3[a]) / d3[a], 0.f) : BIG;
+        dt3[a] = d3[a] != 0.f ? P.vox[a] / fabsf(d3[a]) : BIG;
+    }
+    int i = c3[0], j = c3[1], k = c3[2];
+    const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
+    float tx = t3[0], ty = t3[1], tz = t3[2];
+    const float dtx = dt3[0], dty = dt3[1], dtz = dt3[2];
     float t = 0.f;
     bool out = false;
+#ifdef SMCRT_DBG_WALK
+    if (P.dbg_log) printf("  dda x %.9g %.9g %.9g ijk %d %d %d t0 %.9g %.9g %.9g dt %.9g %.9g %.9g len %.9g\n", (double)fx, (double)fy, (double)fz, i, j, k,
+                          (double)tx, (double)ty, (double)tz, (double)dtx, (double)dty, (double)dtz, (double)len);
+#endif
     for (;;) {
         const float tn = fminf(tx, fminf(ty, tz));
         const long long v = (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
         if (tn >= len) {
-            deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
+            if (P.dda_plain) atomicAdd(P.jmean + v, fmaxf(len - t, 0.f) * weight);
+            else deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
             break;
         }
-        deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
+        if (P.dda_plain) atomicAdd(P.jmean + v, fmaxf(tn - t, 0.f) * weight);
+        else deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
         t = tn;
         if (tx <= ty && tx <= tz) { i += sx; tx += dtx; out = (i < 0 || i >= P.nxg); }
         else if (ty <= tz)        { j += sy; ty += dty; out = (j < 0 || j >= P.nyg); }
@@ -651,6 +672,14 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     uint32_t ev = 0;
     unsigned int c_nscatt = 0, c_sweeps = 0, c_bounces = 0, c_launched = 0, c_retries = 0, c_lost = 0, c_dethits = 0;  // per thread: < 2^32
 
+#ifdef SMCRT_DBG_WALK  // engine diagnostics (-DSMCRT_DBG_WALK): print every update_grids call of packet SMCRT_DEBUG_PID
+#define DBG_WALK(FX, FY, FZ, LEN)                                                                                     \
+    if (P.dbg_log && (long long)pid == P.dbg_pid)                                                                     \
+        printf("walk st=%d ph=%d layer=%d from %.9g %.9g %.9g dir %.9g %.9g %.9g len %.9g taurun %.9g tau %.9g\n", state, phase, \
+               layer, (double)(FX), (double)(FY), (double)(FZ), (double)ux, (double)uy, (double)uz, (double)(LEN), (double)taurun, (double)tau)
+#else
+#define DBG_WALK(FX, FY, FZ, LEN)
+#endif
 #define ADVANCE(S, VX, VY, VZ)                                                          \
     do {                                                                                \
         pxd += (double)(S) * (double)(VX); pyd += (double)(S) * (double)(VY); pzd += (double)(S) * (double)(VZ); \
@@ -659,6 +688,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     // update_grids (inttau2.f90:367-465) for the straight piece (FX,FY,FZ) + t*(ux,uy,uz), t in [0, LEN]
 #define WALK(FX, FY, FZ, LEN)                                                                                         \
     do {                                                                                                              \
+        DBG_WALK(FX, FY, FZ, LEN);                                                                                    \
         if (PATHLEN) { if (walk_dda(P, FX, FY, FZ, ux, uy, uz, LEN, weight)) tflag = true; }                          \
         else if (!in_grid(P, (FX) + ux * (LEN), (FY) + uy * (LEN), (FZ) + uz * (LEN))) tflag = true;                  \
     } while (0)

@@ -219,3 +219,32 @@ def test_default_mcrt_outputs(tmp_path, smcrt):
     # emission grid is normalised by nx*ny*nz/nphotons (writer.f90:25-52): all packets start in one voxel
     em = np.frombuffer((out / "emission" / "source_render.nrrd").read_bytes()[-40 * 50 * 60 * 4:], np.float32)
     assert abs(em.sum() - 40 * 50 * 60) < 1.0
+
+
+def test_validation1_pathlength_hot_column(engine, oracle, smcrt):
+    """-Dpathlength on the pencil-beam slab: ~600 voxel crossings per packet, all packets share the central column (the
+    hot-address case of SURVEY hard part 3).  Same streams -> the fluence profile along the beam agrees to FP32 accuracy."""
+    cfg, osc = _setup(smcrt, oracle, engine, "validation1.toml")
+    n, seed, mode = 50_000, 21, A.TALLY_ABSORB | A.TALLY_PATHLENGTH
+    engine.run(n, seed, tally_mode=mode)
+    g = engine.fetch(jmean=True, absorb=True)
+    o = osc.run(n, seed, tally_mode=mode)
+    jg, jo = g["jmean"].astype(np.float64), o["jmean"].astype(np.float64)
+    assert abs(jg.sum() - jo.sum()) < 2e-3 * jo.sum()
+    zg, zo = jg.sum(axis=(0, 1)), jo.sum(axis=(0, 1))          # 500 slabs along the beam
+    inside = zo > 0.05 * zo.max()
+    assert np.abs(zg - zo)[inside].max() < 0.02 * zo.max()
+    # the central column carries most of the path length in both
+    col_g, col_o = jg[249:251, 249:251, :].sum(), jo[249:251, 249:251, :].sum()
+    assert abs(col_g - col_o) < 0.01 * col_o
+    # independent seeds: batch z-scores on 25 coarse slabs of the central column (the 3-sigma bar)
+    G, O = [], []
+    for b in range(6):
+        engine.reset_tallies()
+        engine.run(20000, 100 + b, tally_mode=mode)
+        G.append(engine.fetch(jmean=True, absorb=False)["jmean"].astype(np.float64)[240:260, 240:260, :].sum(axis=(0, 1)).reshape(25, 20).sum(1))
+        O.append(osc.run(20000, 200 + b, tally_mode=mode)["jmean"].astype(np.float64)[240:260, 240:260, :].sum(axis=(0, 1)).reshape(25, 20).sum(1))
+    G, O = np.array(G), np.array(O)
+    z = (G.mean(0) - O.mean(0)) / np.sqrt(G.var(0, ddof=1) / 6 + O.var(0, ddof=1) / 6 + 1e-30)
+    live = O.mean(0) > 0
+    assert np.abs(z[live]).max() < 5.0

@@ -20,6 +20,7 @@ struct KParams {
     const unsigned char* blob;
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
+    int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
     int off_tops, off_prog, off_dets;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
     const DevInstrD* progD;
@@ -609,7 +610,7 @@ __device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float 
 // Cold states are resolved at the top of an iteration; each consumes exactly one Philox block, generated at ONE site:
 //   ST_FRESNEL   index-mismatch crossing (:248-317)        ST_INTERACT  scatter / absorb (kernelsMod.f90:1958-1974)
 //   ST_EMIT      launch a new packet (kernelsMod.f90:1937-1952)
-enum : int { ST_MARCH = 0, ST_BND_PROBE, ST_CROSS, ST_FRESNEL, ST_INTERACT, ST_EMIT, ST_DONE };
+enum : int { ST_MARCH = 0, ST_BND_PROBE, ST_CROSS, ST_FRESNEL, ST_INTERACT, ST_EMIT, ST_DONE, ST_HOLD /* within one iteration: waiting for FINISH */ };
 enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST = 3 };
 enum : int { POST_NONE = 0, POST_FINISH, POST_AFTER_TRACE, POST_NEXT_LOOP };
 enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYER = 4, LOST_EMIT = 5 };
@@ -734,11 +735,13 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
 #define NEXT_LOOP() /* `do while (taurun <= tau)` head, inttau2.f90:61 */                                             \
     do {                                                                                                              \
         qs = 0.f;                                                                                                     \
-        if (tflag || !(taurun <= tau)) FINISH();                                                                      \
-        else { state = ST_MARCH; phase = 0; }                                                                      \
+        if (tflag || !(taurun <= tau)) { post = POST_FINISH; state = ST_HOLD; }                                       \
+        else { state = ST_MARCH; phase = 0; }                                                                         \
     } while (0)
 
     for (;;) {
+        int post = POST_NONE;
+        bool det = false;  // camera scenes only: a straight piece ended and is a detector segment of its own (see DETECT site below)
         // ===================================== cold phase =====================================
         if (state == ST_EMIT && !have_pid) {  // claim a packet id: one atomic per warp for all lanes that need one
             const unsigned need = __ballot_sync(__activemask(), true);
@@ -795,6 +798,8 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                         g[5] = spurious ? 1.f : 0.f; g[6] = dstep; g[7] = px; g[8] = py; g[9] = pz; g[10] = ux; g[11] = uy; g[12] = uz;
                         g[13] = dnew_L; g[14] = ds_pos_new; g[15] = ds_pos_cur;
                     }
+                    // the straight segment that arrived here ends: detectors see it before the direction changes
+                    if (HASDET && !P.has_camera) DETECT();
                     Refl R;
                     if (spurious) { R.x = ux; R.y = uy; R.z = uz; R.R = 0.f; R.reflected = false; --ev; }
                     else R = reflect_refract(ux, uy, uz, N, sc.tops[layer - 1].n, sc.tops[new_layer - 1].n, u01(w[0]));
@@ -808,7 +813,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                         // measurably changes the impact parameter inside curved bodies (packets refracted at grazing incidence
                         // end up beyond the critical angle and are trapped); the packet continues along the refracted ray here.
                         ADVANCE(dstep, ux, uy, uz);
-                        if (HASDET) DETECT();
+                        det = true;
                         NEXT_LOOP();
                     } else {  // reflected :304-317
                         sx = px; sy = py; sz = pz;
@@ -875,8 +880,6 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
         // cold or done lanes sit the sweep out
 
         // ===================================== sweep =====================================
-        int post = POST_NONE;
-        bool det = false;       // a straight segment ended: test the detectors (one call site, below)
         if (state <= ST_CROSS) {
             const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
                         qz = (float)(pzd + (double)qs * (double)uz);
@@ -967,9 +970,30 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                     state = ST_FRESNEL;
                 } else {  // :318-337
                     layer = S.L;
-                    adv = dstep; wlen = dstep; dtau = dstep * sc.tops[layer - 1].kappa;
+                    const float kap = sc.tops[layer - 1].kappa;
+                    const float tc = taurun + dstep * kap;  // optical depth after the crossing piece
                     det = true;
-                    post = POST_NEXT_LOOP;
+                    if (!(tc <= tau) || !(S.amin >= eps) || P.has_camera) {
+                        adv = dstep; wlen = dstep; dtau = dstep * kap;
+                        post = POST_NEXT_LOOP;
+                    } else {
+                        // The accepted probe IS the packet's next position (same bits) and the direction is kept, so this sweep
+                        // is also the one the reference takes at the top of its next loop (:63-68).  The crossing piece and the
+                        // first sphere-trace step of the new layer are taken as ONE straight move: one update_grids walk, one
+                        // detector segment, one sweep saved per equal-index crossing.
+                        qs = 0.f;
+                        state = ST_MARCH; phase = 2;
+                        const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
+                        if (tc + s * kap < tau) {
+                            adv = dstep + s; wlen = adv; dtau = adv * kap;
+                            if (S.bexact) post = POST_AFTER_TRACE;
+                            else det = false;  // mid-trace: the detector segment stays open
+                        } else {
+                            const float dd = kap > 0.f ? (tau - tc) / kap : 0.f;
+                            adv = dstep + dd; wlen = adv; dtau = tau - taurun;
+                            post = POST_FINISH;
+                        }
+                    }
                 }
             }
             // ---------------- part B (common): update_grids, move, spend optical depth
@@ -985,7 +1009,12 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 NEXT_LOOP();
             }
         }
-        if (HASDET && det) DETECT();
+        // record_hit (inttau2.f90:126-131,196-201,298-303,330-335).  The reference tests the detectors after every straight
+        // piece; pieces that share a direction form ONE straight segment and a plane crossing is found on the union exactly
+        // when it is found on one of the pieces (watertight end-point test), so the segment is kept open until the direction
+        // changes (Fresnel block) or tauint2 returns.  A camera counts segments (detector_base.f90:222-229): with one in the
+        // scene every piece is tested on its own, as in the reference.
+        if (HASDET && (P.has_camera ? det : post == POST_FINISH)) DETECT();
         if (post == POST_FINISH) FINISH();
 
         if (COMPACT) {

@@ -394,73 +394,69 @@ __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, floa
 // change of the plane side function g(x) = (p0 - x).n between the segment's two stored end points: a crossing is
 // recorded iff g(start) >= 0 and g(end) < 0.  Consecutive segments share their end point bit-for-bit, so every
 // crossing is seen exactly once ("watertight"), which is what the reference's FP64 arithmetic achieves implicitly.
-__device__ __forceinline__ bool plane_cross(const float n[3], const float p0[3], const float s[3], const float d[3],
-                                            const float e[3], float& t) {
-    const float denom = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
-    if (!(denom > 1e-6f)) return false;  // intersectPlane: src/geometryMod.f90:234
-    const float gs = (p0[0] - s[0]) * n[0] + (p0[1] - s[1]) * n[1] + (p0[2] - s[2]) * n[2];
-    const float ge = (p0[0] - e[0]) * n[0] + (p0[1] - e[1]) * n[1] + (p0[2] - e[2]) * n[2];
-    t = gs / denom;
-    return gs >= 0.f && ge < 0.f;
-}
-__device__ __forceinline__ float hit_radius(const float p0[3], const float s[3], const float d[3], float t) {
-    const float vx = s[0] + d[0] * t - p0[0], vy = s[1] + d[1] * t - p0[1], vz = s[2] + d[2] * t - p0[2];
-    return sqrtf(vx * vx + vy * vy + vz * vz);
-}
 __device__ __forceinline__ int nint_pos(float v) { return (int)floorf(v + 0.5f); }  // Fortran nint for v >= 0
-__device__ __noinline__ int detector_bin(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
-                                         float e1, float e2) {
+// Plane detectors (circle, annulus, fibre): crossing test + radial distance of the hit point from the detector centre.
+// `denom` = n.l is returned for the fibre's acceptance chain.
+__device__ __forceinline__ bool det_plane_hit(const DevDet& D, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
+                                              float e1, float e2, float& r, float& denom) {
+    denom = D.dir[0] * d0 + D.dir[1] * d1 + D.dir[2] * d2;
+    const float gs = (D.pos[0] - s0) * D.dir[0] + (D.pos[1] - s1) * D.dir[1] + (D.pos[2] - s2) * D.dir[2];
+    const float ge = (D.pos[0] - e0) * D.dir[0] + (D.pos[1] - e1) * D.dir[1] + (D.pos[2] - e2) * D.dir[2];
+    if (!(denom > 1e-6f) || !(gs >= 0.f) || !(ge < 0.f)) return false;  // intersectPlane: src/geometryMod.f90:234
+    const float t = gs / denom;
+    const float vx = s0 + d0 * t - D.pos[0], vy = s1 + d1 * t - D.pos[1], vz = s2 + d2 * t - D.pos[2];
+    r = sqrtf(vx * vx + vy * vy + vz * vz);
+    return true;
+}
+__device__ __forceinline__ int det_bin_circle(const DevDet& D, float r) {  // :147-164
+    return r <= D.q[0] ? min(nint_pos(r / D.q[1]) + 1, D.nbins) : 0;
+}
+__device__ __noinline__ int det_bin_annulus_fibre(const DevDet* Dp, float r, float denom) {
     const DevDet& D = *Dp;
-    const float s[3] = {s0, s1, s2}, d[3] = {d0, d1, d2}, e[3] = {e0, e1, e2};
-    float t = 0.f;
-    switch (D.kind) {
-        case 1: {  // circle :147-164
-            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
-            const float r = hit_radius(D.pos, s, d, t);
-            if (!(r <= D.q[0])) return 0;
-            return min(nint_pos(r / D.q[1]) + 1, D.nbins);
-        }
-        case 2: {  // annulus :212-244: not inside r1, inside r2
-            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
-            const float r = hit_radius(D.pos, s, d, t);
-            if (r <= D.q[0] || !(r <= D.q[1])) return 0;
-            return max(min(nint_pos((r - D.q[0]) / D.q[2]) + 1, D.nbins), 1);
-        }
-        case 3: {  // fibre: 4f relay in the thin-lens approximation :323-393
-            if (!plane_cross(D.dir, D.pos, s, d, e, t)) return 0;
-            const float r = hit_radius(D.pos, s, d, t);
-            if (!(r <= D.q[0])) return 0;
-            float costt = fminf(D.dir[0] * d[0] + D.dir[1] * d[1] + D.dir[2] * d[2], 1.0f);
-            const float sintt = sqrtf(1.0f - costt * costt);
-            float gradient = sintt / costt;
-            float radius = r;
-            gradient = -radius / D.q[1] + gradient;
-            radius = radius + gradient * D.q[3];
-            if (radius > D.q[4]) return 0;
-            radius = radius + gradient * D.q[5];
-            if (radius > D.q[6]) return 0;
-            gradient = -radius / D.q[2] + gradient;
-            radius = radius + gradient * D.q[7];
-            const float angle = fabsf(atanf(gradient)) * (360.0f / TWOPI_F);
-            if (angle > D.q[8] || radius > D.q[9]) return 0;
-            return min(nint_pos(fabsf(radius) / D.q[10]) + 1, D.nbins);
-        }
-        case 4: {  // camera :447-469 + record_hit_2D_sub (no pointSep test, bins the segment START, adds 1)
-            const float dn = d[0] * D.dir[0] + d[1] * D.dir[1] + d[2] * D.dir[2];
-            const float tt = ((D.pos[0] - s[0]) * D.dir[0] + (D.pos[1] - s[1]) * D.dir[1] + (D.pos[2] - s[2]) * D.dir[2]) / dn;
-            if (!(tt >= 0.f)) return 0;
-            const float vx = s[0] + tt * d[0] - D.pos[0], vy = s[1] + tt * d[1] - D.pos[1], vz = s[2] + tt * d[2] - D.pos[2];
-            const float p1 = (vx * D.q[0] + vy * D.q[1] + vz * D.q[2]) / D.q[6];
-            const float p2 = (vx * D.q[3] + vy * D.q[4] + vz * D.q[5]) / D.q[7];
-            if (!(p1 < D.q[6] && p1 > 0.f && p2 < D.q[7] && p2 > 0.f)) return 0;
-            const float bx = s[2] + D.q[10], by = s[1] + D.q[11];  // sic: hitpoint%pos%z + this%pos%x
-            int ix = min((int)(bx / D.q[8]) + 1, D.nbins), iy = min((int)(by / D.q[9]) + 1, D.nbins);
-            if (ix < 1) ix = D.nbins;
-            if (iy < 1) iy = D.nbins;
-            return ix + (iy - 1) * D.nbins;
-        }
+    if (D.kind == 2) {  // annulus :212-244: not inside r1, inside r2
+        if (r <= D.q[0] || !(r <= D.q[1])) return 0;
+        return max(min(nint_pos((r - D.q[0]) / D.q[2]) + 1, D.nbins), 1);
     }
-    return 0;
+    // fibre: 4f relay in the thin-lens approximation :323-393
+    if (!(r <= D.q[0])) return 0;
+    const float costt = fminf(denom, 1.0f);
+    const float sintt = sqrtf(1.0f - costt * costt);
+    float gradient = sintt / costt;
+    float radius = r;
+    gradient = -radius / D.q[1] + gradient;
+    radius = radius + gradient * D.q[3];
+    if (radius > D.q[4]) return 0;
+    radius = radius + gradient * D.q[5];
+    if (radius > D.q[6]) return 0;
+    gradient = -radius / D.q[2] + gradient;
+    radius = radius + gradient * D.q[7];
+    const float angle = fabsf(atanf(gradient)) * (360.0f / TWOPI_F);
+    if (angle > D.q[8] || radius > D.q[9]) return 0;
+    return min(nint_pos(fabsf(radius) / D.q[10]) + 1, D.nbins);
+}
+// camera :447-469 + record_hit_2D_sub (no pointSep test, bins the segment START, adds 1)
+__device__ __noinline__ int det_bin_camera(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2) {
+    const DevDet& D = *Dp;
+    const float dn = d0 * D.dir[0] + d1 * D.dir[1] + d2 * D.dir[2];
+    const float tt = ((D.pos[0] - s0) * D.dir[0] + (D.pos[1] - s1) * D.dir[1] + (D.pos[2] - s2) * D.dir[2]) / dn;
+    if (!(tt >= 0.f)) return 0;
+    const float vx = s0 + tt * d0 - D.pos[0], vy = s1 + tt * d1 - D.pos[1], vz = s2 + tt * d2 - D.pos[2];
+    const float p1 = (vx * D.q[0] + vy * D.q[1] + vz * D.q[2]) / D.q[6];
+    const float p2 = (vx * D.q[3] + vy * D.q[4] + vz * D.q[5]) / D.q[7];
+    if (!(p1 < D.q[6] && p1 > 0.f && p2 < D.q[7] && p2 > 0.f)) return 0;
+    const float bx = s2 + D.q[10], by = s1 + D.q[11];  // sic: hitpoint%pos%z + this%pos%x
+    int ix = min((int)(bx / D.q[8]) + 1, D.nbins), iy = min((int)(by / D.q[9]) + 1, D.nbins);
+    if (ix < 1) ix = D.nbins;
+    if (iy < 1) iy = D.nbins;
+    return ix + (iy - 1) * D.nbins;
+}
+// One straight segment against one detector -> 1-based flat bin, 0 on miss (the kernel's DETECT site and the probe kernel)
+__device__ __forceinline__ int detector_bin(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
+                                            float e1, float e2) {
+    if (Dp->kind == 4) return det_bin_camera(Dp, s0, s1, s2, d0, d1, d2);
+    float r, denom;
+    if (!det_plane_hit(*Dp, s0, s1, s2, d0, d1, d2, e0, e1, e2, r, denom)) return 0;
+    return Dp->kind == 1 ? det_bin_circle(*Dp, r) : det_bin_annulus_fibre(Dp, r, denom);
 }
 
 // ------------------------------------------------------------------------------------------------ emitters
@@ -698,18 +694,19 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
     do {                                                                                                              \
         for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                       \
             const DevDet* D_ = &sc.dets[i_];                                                                          \
-            /* cheap reject with the plane side function g(x) = p0.n - x.n (q[13] = p0.n): a crossing needs g(start) >= 0 > g(end). */ \
-            /* Conservative by a rounding margin; the exact watertight test is repeated inside detector_bin. */       \
-            const float nx_ = D_->dir[0], ny_ = D_->dir[1], nz_ = D_->dir[2], c_ = D_->q[13];                        \
-            const float gs_ = c_ - (sx * nx_ + sy * ny_ + sz * nz_), ge_ = c_ - (px * nx_ + py * ny_ + pz * nz_);     \
-            const float m_ = 4.0e-7f * (fabsf(c_) + fabsf(sx) + fabsf(sy) + fabsf(sz));                               \
-            if (D_->kind == 4 || (gs_ >= -m_ && ge_ < m_)) {                                                          \
+            {                                                                                                         \
                 const int b_ = detector_bin(D_, sx, sy, sz, ux, uy, uz, px, py, pz);                                  \
                 if (b_ > 0) {                                                                                         \
                     const float w_ = D_->kind == 4 ? 1.0f : weight;                                                   \
                     const unsigned long long q_ = (unsigned long long)__float2ll_rn(w_ * DET_FIX);                    \
                     const int slot_ = D_->offset + b_ - 1;                                                            \
-                    if (P.det_in_smem) atomicAdd(&sbins[slot_], q_);                                                  \
+                    if (P.det_in_smem) { /* two native 32-bit ATOMS.ADD with carry (a 64-bit shared add is a CAS spin loop) */ \
+                        unsigned int* w32_ = reinterpret_cast<unsigned int*>(&sbins[slot_]);                          \
+                        const unsigned int ql_ = (unsigned int)q_, qh_ = (unsigned int)(q_ >> 32);                    \
+                        const unsigned int old_ = atomicAdd(w32_, ql_);                                               \
+                        const unsigned int up_ = qh_ + ((old_ + ql_ < old_) ? 1u : 0u);                               \
+                        if (up_) atomicAdd(w32_ + 1, up_);                                                            \
+                    }                                                                                                 \
                     else atomicAdd(&P.det_bins[slot_], q_);                                                           \
                     ++c_dethits;                                                                                      \
                 }                                                                                                     \

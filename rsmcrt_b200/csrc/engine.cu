@@ -85,10 +85,18 @@ static int load() {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ context
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tune_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // brackets of the three register-budget trial launches
+    int tuning = -1;  // >= 0: trial launches in flight for variant key `tuning` (read back in smcrt_wait)
     unsigned char* blob = nullptr;
     DevPrimD* primsD = nullptr;
     DevInstrD* progD = nullptr;
@@ -142,6 +150,9 @@ struct smcrt_ctx {
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
     bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
+    // register-budget choice per kernel variant [pathlength][detectors]: 0 = not timed yet, else MINBLOCKS (2, 3 or 4)
+    int tuned_mb[2][2] = {{0, 0}, {0, 0}};
+    uint64_t scene_hash = 0, det_hash = 0;  // tuned_mb is kept while the scene and detectors stay bit-identical
     int cull_n[3] = {0, 0, 0};
     double cull_lo[3] = {0, 0, 0}, cull_cell[3] = {1, 1, 1};
     double cull_mean_list = 0;
@@ -192,6 +203,8 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
         D.sm_count = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&D.ev0) != cudaSuccess || cudaEventCreate(&D.ev1) != cudaSuccess ||
+            cudaEventCreate(&D.tune_ev[0]) != cudaSuccess || cudaEventCreate(&D.tune_ev[1]) != cudaSuccess ||
+            cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
             cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess ||
             cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess) {
             delete c;
@@ -219,6 +232,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far);
         if (D.ev0) cudaEventDestroy(D.ev0);
         if (D.ev1) cudaEventDestroy(D.ev1);
+        for (cudaEvent_t e : D.tune_ev) if (e) cudaEventDestroy(e);
         if (D.stream) cudaStreamDestroy(D.stream);
     }
     delete c;
@@ -407,6 +421,13 @@ extern "C" int smcrt_set_scene(smcrt_ctx* c, int n_nodes, const int32_t* kind, c
     }
     c->scene_lipschitz = lip;
     c->prims.swap(prims); c->primsD.swap(primsD); c->prog.swap(prog); c->progD.swap(progD); c->tops.swap(tops);
+    {  // a different scene invalidates the register-budget choice (same bytes: e.g. a driver re-sending its scene every call)
+        uint64_t h = fnv1a(1469598103934665603ull, c->primsD.data(), c->primsD.size() * sizeof(DevPrimD));
+        h = fnv1a(h, c->progD.data(), c->progD.size() * sizeof(DevInstrD));
+        h = fnv1a(h, c->tops.data(), c->tops.size() * sizeof(DevTop));
+        if (h != c->scene_hash) std::memset(c->tuned_mb, 0, sizeof c->tuned_mb);
+        c->scene_hash = h;
+    }
     c->opt_mus.assign(mus, mus + n_top); c->opt_mua.assign(mua, mua + n_top);
     c->opt_hgg.assign(hgg, hgg + n_top); c->opt_n.assign(n_ref, n_ref + n_top);
     c->scene_dirty = true;
@@ -526,6 +547,11 @@ extern "C" int smcrt_set_detectors(smcrt_ctx* c, int n, const int32_t* kind, con
         if (off > (1ll << 30)) return set_err("smcrt_set_detectors: too many detector bins");
     }
     c->dets.swap(dets); c->hdets.swap(hd); c->det_total = off;
+    {
+        const uint64_t h = fnv1a(1469598103934665603ull, c->dets.data(), c->dets.size() * sizeof(DevDet));
+        if (h != c->det_hash) std::memset(c->tuned_mb, 0, sizeof c->tuned_mb);
+        c->det_hash = h;
+    }
     c->scene_dirty = true;
     for (DeviceState& D : c->devs) {
         CU(cudaSetDevice(D.dev));
@@ -697,9 +723,9 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     return 0;
 }
 
-template <bool PL, bool HD, bool CP>
-static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
-    auto kern = trace_persistent<PL, HD, CP>;
+template <bool PL, bool HD, bool CP, int MB>
+static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
+    auto kern = trace_persistent<PL, HD, CP, MB>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
@@ -708,9 +734,23 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes) {
     long long blocks = (long long)D.sm_count * per_sm;
     const long long need = (P.nphotons + SMCRT_BLOCK - 1) / SMCRT_BLOCK;
     if (blocks > need) blocks = std::max<long long>(need, 1);
+    if (dry) return 0;  // the attribute/occupancy queries above have loaded the kernel (lazy module loading)
     kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, D.stream>>>(P);
     CU(cudaGetLastError());
     return 0;
+}
+template <bool PL, bool HD>
+static int launch_mb(bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
+    if (compact) return launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
+    switch (mb) {
+        case 2: return launch_trace<PL, HD, false, 2>(P, D, smem_bytes, dry);
+        case 4: return launch_trace<PL, HD, false, 4>(P, D, smem_bytes, dry);
+        default: return launch_trace<PL, HD, false, 3>(P, D, smem_bytes, dry);
+    }
+}
+static int launch_variant(bool pl, bool hd, bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry = false) {
+    if (pl) return hd ? launch_mb<true, true>(compact, mb, P, D, smem_bytes, dry) : launch_mb<true, false>(compact, mb, P, D, smem_bytes, dry);
+    return hd ? launch_mb<false, true>(compact, mb, P, D, smem_bytes, dry) : launch_mb<false, false>(compact, mb, P, D, smem_bytes, dry);
 }
 
 static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
@@ -734,18 +774,38 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     if (compact) smem = P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK;
     CU(cudaEventRecord(D.ev0, D.stream));
     const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
-    int rc;
-    if (compact) {
-        if (pl) rc = hd ? launch_trace<true, true, true>(P, D, smem) : launch_trace<true, false, true>(P, D, smem);
-        else rc = hd ? launch_trace<false, true, true>(P, D, smem) : launch_trace<false, false, true>(P, D, smem);
-    } else {
-        if (pl) rc = hd ? launch_trace<true, true, false>(P, D, smem) : launch_trace<true, false, false>(P, D, smem);
-        else rc = hd ? launch_trace<false, true, false>(P, D, smem) : launch_trace<false, false, false>(P, D, smem);
+    // Register budget: the first large run of a scene spends three equal slices of its own packets on the three
+    // budgets, bracketed by events; smcrt_wait reads the times and later runs use the fastest.  No packet is traced twice:
+    // streams depend on (seed, id) only, so a run split into id ranges is the same run.
+    static const char* force_s = getenv("SMCRT_MINBLOCKS_FORCE");
+    const int forced = force_s ? atoi(force_s) : 0;
+    int mb = forced ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] : 3);
+    int n_launch = 1;
+    const long long TUNE_MIN = 8ll << 20;
+    if (!forced && !compact && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
+        const long long slice = std::min<long long>(std::max<long long>(nphotons / 32, 1ll << 20), 1ll << 22);
+        for (int k = 0; k < 3; ++k) {  // load the three kernels first: the load would otherwise sit inside the event brackets
+            int rc = launch_variant(pl, hd, false, 2 + k, P, D, smem, true);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < 3; ++k) {
+            KParams Q = P;
+            Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
+            CU(cudaEventRecord(D.tune_ev[k], D.stream));
+            int rc = launch_variant(pl, hd, false, 2 + k, Q, D, smem);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
+        }
+        CU(cudaEventRecord(D.tune_ev[3], D.stream));
+        D.tuning = (pl ? 2 : 0) | (hd ? 1 : 0);
+        P.nphotons -= 3 * slice; P.id_offset += (unsigned long long)(3 * slice);
+        n_launch = 4;
     }
+    int rc = launch_variant(pl, hd, compact, mb, P, D, smem);
     if (rc) return rc;
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
-    c->launches += 1;
+    c->launches += n_launch;
     c->touched_modes |= tally_mode;
     return 0;
 }
@@ -790,6 +850,17 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             float t = 0;
             CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
             ms = std::max(ms, (double)t);
+        }
+        if (D.tuning >= 0) {  // the three trial slices of run_on_device: keep the fastest register budget
+            float best = 0.f;
+            int arg = 1;
+            for (int k = 0; k < 3; ++k) {
+                float t = 0;
+                CU(cudaEventElapsedTime(&t, D.tune_ev[k], D.tune_ev[k + 1]));
+                if (k == 0 || t < best) { best = t; arg = k; }
+            }
+            c->tuned_mb[(D.tuning >> 1) & 1][D.tuning & 1] = 2 + arg;
+            D.tuning = -1;
         }
     }
     if (c->pending) c->last_ms = ms;

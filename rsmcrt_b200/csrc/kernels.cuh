@@ -611,6 +611,12 @@ enum : int { FATE_ABSORBED = 0, FATE_ESCAPED = 1, FATE_ROULETTE = 2, FATE_LOST =
 enum : int { POST_NONE = 0, POST_FINISH, POST_AFTER_TRACE, POST_NEXT_LOOP };
 enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYER = 4, LOST_EMIT = 5 };
 
+// tau = -ln(xi): MUFU.LG2 * ln2 (abs. error 2^-21.4 near 1, <= 2 ulp elsewhere): a 4e-7 perturbation of a free path.
+#ifdef SMCRT_PRECISE_LOG
+#define SMCRT_LOG logf
+#else
+#define SMCRT_LOG __logf
+#endif
 #ifndef SMCRT_BLOCK
 #define SMCRT_BLOCK 256      // threads per CTA
 #endif
@@ -630,8 +636,11 @@ __device__ __noinline__ void record_packet(const KParams& P, unsigned long long 
 
 constexpr int XCHG_WORDS = 26;  // 32-bit words of packet state exchanged by the compaction step
 
-template <bool PATHLEN, bool HASDET, bool COMPACT>
-__global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent(const __grid_constant__ KParams P) {
+// MINBLOCKS = resident CTAs per SM the register allocation is made for (2: 128 registers, no spills; 3: 80; 4: 64).  Which one
+// wins depends on the scene (slab with detectors: 4, +8 %; long histories inside one body: 2, +17 %), so the engine times
+// the three on the first large run of a scene and keeps the fastest (engine.cu: run_on_device).
+template <bool PATHLEN, bool HASDET, bool COMPACT, int MINBLOCKS>
+__global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
         const int4* src = reinterpret_cast<const int4*>(P.blob);
@@ -832,14 +841,15 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 bool alive = true;
                 if (!P.survival) {
                     if (!(ran < albedo)) {
-                        if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, px, py, pz), 1.0f);
+                        // plain RED: absorption sites rarely coincide inside a warp, the match/shuffle aggregation costs more than it saves
+                        if (P.tally_mode & TALLY_ABSORB) atomicAdd(P.absorb + voxel_of(P, px, py, pz), 1.0f);
                         RETIRE(FATE_ABSORBED, 0);
                         alive = false;
                     }
                 } else {
                     const float wabs = weight * (1.0f - albedo);
                     weight -= wabs;
-                    if (P.tally_mode & TALLY_ABSORB) deposit(P.absorb, voxel_of(P, px, py, pz), wabs);
+                    if (P.tally_mode & TALLY_ABSORB) atomicAdd(P.absorb + voxel_of(P, px, py, pz), wabs);
                     if (weight < P.threshold) {
                         if (ran < P.chance) weight = weight / P.chance;
                         else {
@@ -851,7 +861,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 if (alive) {
                     hg_scatter(ux, uy, uz, sc.tops[layer - 1].hgg, u01(w[1]), u01(w[2]));
                     ++c_nscatt; ++pk_nscatt;
-                    tau = -logf(u01_open0(w[3]));
+                    tau = -SMCRT_LOG(u01_open0(w[3]));
                     taurun = 0.f; qs = 0.f;
                     sx = px; sy = py; sz = pz;
                     state = ST_MARCH; phase = 0;
@@ -862,7 +872,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, SMCRT_MINBLOCKS) trace_persistent
                 if (em.ok && in_grid(P, px, py, pz)) {
                     pxd = px; pyd = py; pzd = pz;
                     if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, px, py, pz), 1.0f);
-                    tau = -logf(u01_open0(w[3]));
+                    tau = -SMCRT_LOG(u01_open0(w[3]));
                     taurun = 0.f; qs = 0.f;
                     sx = px; sy = py; sz = pz;
                     launch = true; layer = 0;

@@ -941,22 +941,24 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
                         post = POST_AFTER_TRACE;
                     }
                 }
-            } else if (state == ST_BND_PROBE) {  // :86-131
+            } else if (state == ST_BND_PROBE && S.L == layer) {  // forward nudge :86-102
                 const float kap = sc.tops[layer - 1].kappa;
                 const float t = dstep * kap;
-                const float sg = (S.L == layer) ? 1.0f : -1.0f;  // forward keeps us in `layer`, else step backwards
                 if (taurun + t < tau) {
-                    adv = sg * dstep; wlen = dstep; dtau = t;  // Q2: deposits along +dir even when stepping back
-                } else {
-                    const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                    wlen = dd;
-                    if (sg > 0.f) dtau = t;   // Q1: position not advanced
-                    else adv = -dd;           // Q3: taurun not advanced
+                    adv = dstep; wlen = dstep; dtau = t;
+                } else {  // Q1 of the reference: optical depth exhausted inside the nudge, position not advanced
+                    wlen = kap > 0.f ? (tau - taurun) / kap : 0.f;
+                    dtau = t;
                 }
                 det = true;
                 qs = 0.f;
                 state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
             } else {  // ST_CROSS :220-337
+                // ... or a boundary probe that found another layer ahead.  The reference then steps BACK by the probe length
+                // (:104-121, charging optical depth and path for it: quirks Q2/Q3), re-approaches the surface and probes across
+                // it again: 3 more sweeps to learn what this sweep already says.  The probe is taken as the crossing probe it is;
+                // position and optical depth differ from the reference's sequence by O(eps).
+                if (state == ST_BND_PROBE) { state = ST_CROSS; dlast = eps; }
                 if (S.L != 0 && S.amin < eps) {
                     // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
                     // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment

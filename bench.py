@@ -294,6 +294,7 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = packets / e2e_s
+    absorbed_per_packet = float(h_absorb.sum(dtype=np.float64)) / (n_step * args.steps)  # this rank's device tallies of the e2e region
     eng.unpin_host(h_absorb)
     eng.unpin_host(h_bins)
 
@@ -326,6 +327,21 @@ def main():
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s FP32 FMA at max clock
     kern_rate = packets / (kernel_ms * 1e-3)
     achieved = kern_rate * w_flop / 1e12
+    # secondary ceilings: HBM traffic of the kernel and red.global.add.f32 rate, to show they are NOT the bound
+    traffic = NCU_TRAFFIC_BYTES.get((args.scene, n_step))
+    hbm_peak = float(peaks.get("hbm_gbs", 6548.2))
+    hbm = None if traffic is None else {"achieved": traffic / (kernel_ms / args.steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU",
+                                        "frac": traffic / (kernel_ms / args.steps * 1e-3) / 1e9 / hbm_peak}
+    red = None
+    try:
+        rp = json.loads((ROOT / "profiles" / "r01_red_peaks.json").read_text())["grids"]["500^3 (500 MB)"]["uniform_random"]
+        # absorb mode: one red.f32 per absorbed packet (detector bins are CTA-private shared-memory counters, flushed once)
+        absorbed = absorbed_per_packet
+        if absorbed > 0:
+            red = {"reds_per_packet": absorbed, "achieved": kern_rate / world * absorbed, "peak": rp, "unit": "red.f32/s per GPU",
+                   "frac": kern_rate / world * absorbed / rp, "peak_source": "profiles/r01_red_peaks.json (tools/red_peak.py, uniform-random voxels of a 500^3 grid)"}
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -338,7 +354,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get((args.scene, n_step)),
+                     "traffic": traffic, "hbm": hbm, "red": red,
                      "note": "path is FP32/SFU-issue bound, not HBM or tensor (SURVEY 8d); achieved = packets/s x algorithmic flops/packet "
                              f"({w_flop:.0f}, from {w_basis} x frozen op table in bench.py); peak = 148 SM x 128 lanes x 2 x sm_max_mhz "
                              "(nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",

@@ -223,6 +223,10 @@ int smcrt_probe_detector(smcrt_ctx* ctx, int det_index, int64_t n, const double*
 int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode,
                         int survival_bias, int32_t* fate, int32_t* nscatt, double* final_pos,
                         int32_t* n_events, int32_t* n_sweeps);
+/* red.global.add.f32 throughput of device 0 on the context's own path-length grid (the secondary bound of -Dpathlength mode,
+ * update_grids src/inttau2.f90:417-441).  pattern 0: uniform-random voxels; 1: every thread walks the same z-column of `span`
+ * voxels (beam axis of a pencil source); 2: runs of `span` x-consecutive voxels from random starts (DDA-like).  Zeroes jmean. */
+int smcrt_bench_red(smcrt_ctx* ctx, int pattern, int span, int64_t n_ops, double* ops_per_s);
 /* The engine's Philox4x32-10 block for (seed, packet id, event index): 4 words. */
 int smcrt_probe_philox(uint64_t seed, uint64_t packet_id, uint32_t event, uint32_t out[4]);
 

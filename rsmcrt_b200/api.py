@@ -343,6 +343,12 @@ class Engine:
                                            _p(hit, C.c_int32), _p(b, C.c_int32)))
         return hit, b
 
+    def bench_red(self, pattern, span=333, n_ops=1 << 30):
+        """red.global.add.f32 operations per second on this context's path-length grid (smcrt_bench_red)."""
+        out = C.c_double(0.0)
+        check(self._L.smcrt_bench_red(self._h, int(pattern), int(span), int(n_ops), C.byref(out)))
+        return out.value
+
     def trace_packets(self, n, seed, id_offset=0, tally_mode=TALLY_ABSORB, survival_bias=False):
         fate, nsc, ev, sw = (np.zeros(n, np.int32) for _ in range(4))
         pos = np.zeros((n, 3))

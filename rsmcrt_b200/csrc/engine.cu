@@ -1207,6 +1207,31 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     if (final_pos && down_f(p, final_pos, 3 * n)) return PROBE_FAIL();
     return 0;
 }
+extern "C" int smcrt_bench_red(smcrt_ctx* c, int pattern, int span, int64_t n_ops, double* ops_per_s) {
+    if (!c || !ops_per_s) return set_err("smcrt_bench_red: null argument");
+    if (c->nxg == 0) return set_err("smcrt_bench_red: no grid set (smcrt_set_grid)");
+    if (pattern < 0 || pattern > 2 || span < 1 || n_ops < 1) return set_err("smcrt_bench_red: invalid arguments");
+    if (c->pending) return set_err("smcrt_bench_red: a run is pending");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    const long long nvox = (long long)c->nxg * c->nyg * c->nzg, stride = (long long)c->nxg * c->nyg;
+    if (span > c->nzg) span = c->nzg;
+    if (nvox <= span) return set_err("smcrt_bench_red: grid too small");
+    const int threads = 256, blocks = D.sm_count * 8;
+    const int per_thread = (int)std::max<long long>(1, n_ops / ((long long)threads * blocks));
+    red_bench_kernel<<<blocks, threads, 0, D.stream>>>(D.jmean, nvox, stride, span, pattern, std::min(per_thread, 64));  // warm-up
+    CU(cudaEventRecord(D.ev0, D.stream));
+    red_bench_kernel<<<blocks, threads, 0, D.stream>>>(D.jmean, nvox, stride, span, pattern, per_thread);
+    CU(cudaEventRecord(D.ev1, D.stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, D.ev0, D.ev1));
+    *ops_per_s = (double)per_thread * threads * blocks / (ms * 1e-3);
+    CU(cudaMemsetAsync(D.jmean, 0, sizeof(float) * nvox, D.stream));  // the benchmark scribbles on the path-length grid
+    CU(cudaStreamSynchronize(D.stream));
+    return 0;
+}
 extern "C" int smcrt_probe_philox(uint64_t seed, uint64_t packet_id, uint32_t event, uint32_t out[4]) {
     philox4x32_10(event, (uint32_t)packet_id, (uint32_t)(packet_id >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), out);
     return 0;

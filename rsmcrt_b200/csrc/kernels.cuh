@@ -1188,4 +1188,26 @@ __global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det
     }
 }
 
+// red.global.add.f32 throughput microbenchmark (the secondary bound of path-length mode).
+//   pattern 0: every thread walks its own pseudo-random voxel sequence over the whole grid (L2/HBM scatter)
+//   pattern 1: every thread walks the SAME column of `span` voxels (stride nx*ny: the beam axis of a pencil source)
+//   pattern 2: DDA-like: each thread walks `span` consecutive voxels along x from a random start (sector-local runs)
+__global__ void red_bench_kernel(float* grid, long long nvox, long long stride, int span, int pattern, int ops_per_thread) {
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long h = (tid + 1) * 0x9E3779B97F4A7C15ull;
+    long long v = 0;
+    for (int i = 0; i < ops_per_thread; ++i) {
+        if (pattern == 0) {
+            h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
+            v = (long long)(h % (unsigned long long)nvox);
+        } else if (pattern == 1) {
+            v = (nvox / 2 / stride) % stride + (long long)((i + (int)(tid & 1023)) % span) * stride;
+        } else {
+            if (i % span == 0) { h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31; v = (long long)(h % (unsigned long long)(nvox - span)); }
+            else ++v;
+        }
+        atomicAdd(grid + v, 1.0f);
+    }
+}
+
 }  // namespace smcrt_dev

@@ -223,6 +223,17 @@ int smcrt_probe_detector(smcrt_ctx* ctx, int det_index, int64_t n, const double*
 int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_offset, int tally_mode,
                         int survival_bias, int32_t* fate, int32_t* nscatt, double* final_pos,
                         int32_t* n_events, int32_t* n_sweeps);
+/* Batched point sources in ONE launch: the body of the escape-function drivers cart_calc_escape_sym / cyl_calc_escape_sym
+ * (src/kernelsMod.f90:533-642, 959-1071), which call run_MCRT once per symmetry-grid cell with set_photon(cell centre).
+ * pos: n_src x 3 emission points (already rotated/shifted by the caller, :576-585).  Per source, as in the reference:
+ * layer = maxloc(d, mask = d < 0) (:592-596, returned in layer_out if non-NULL); layer == 0 or kappa(layer) == 0 -> no packets,
+ * totals 0 (:599-609); else nphotons_per_source packets from an isotropic point source (photon.f90:311-359).
+ * det_totals: n_src x n_det (source-major), the sum of each detector's bins (total_dect); escapeSymmetry = total / nphotons (:617).
+ * Voxel tallies accumulate over all sources, like repeated run_MCRT calls.  Packet ids: source k of the ACTIVE list owns
+ * [id_offset + k*nphotons_per_source, +nphotons_per_source).  Blocking. */
+int smcrt_run_sources(smcrt_ctx* ctx, int64_t n_src, const double* pos, int64_t nphotons_per_source, uint64_t seed,
+                      int64_t id_offset, int tally_mode, int survival_bias, double threshold, double chance,
+                      double* det_totals, int32_t* layer_out);
 /* red.global.add.f32 throughput of device 0 on the context's own path-length grid (the secondary bound of -Dpathlength mode,
  * update_grids src/inttau2.f90:417-441).  pattern 0: uniform-random voxels; 1: every thread walks the same z-column of `span`
  * voxels (beam axis of a pencil source); 2: runs of `span` x-consecutive voxels from random starts (DDA-like).  Zeroes jmean. */

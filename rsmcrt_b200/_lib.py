@@ -63,6 +63,8 @@ PROTOTYPES = {
     "smcrt_probe_detector": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p]),
     "smcrt_trace_packets": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, c_int32_p, c_int32_p,
                                       c_double_p, c_int32_p, c_int32_p]),
+    "smcrt_run_sources": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                    C.c_double, c_double_p, c_int32_p]),
     "smcrt_bench_red": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double)]),
     "smcrt_probe_philox": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, c_uint32_p]),
     # smcrt_host.h

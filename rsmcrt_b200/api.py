@@ -207,6 +207,7 @@ class Engine:
     def set_detectors(self, kind, params, nbins):
         k, p, nb = _i32(kind), _f64(params), _i32(nbins)
         n = len(k)
+        self._n_det = n
         check(self._L.smcrt_set_detectors(self._h, n, _p(k, C.c_int32) if n else None, _p(p, C.c_double) if n else None,
                                           _p(nb, C.c_int32) if n else None))
 
@@ -219,6 +220,7 @@ class Engine:
         self.grid_shape = (nx, ny, nz)
         self.n_voxels = nx * ny * nz
         self.n_top = cfg.scene.n_top
+        self._n_det = int(self._L.smcrt_config_n_detectors(cfg._h))
 
     # ---- run ---------------------------------------------------------------------------------------
     def run(self, nphotons, seed, id_offset=0, tally_mode=TALLY_ABSORB, survival_bias=False, threshold=-1.0, chance=-1.0):
@@ -342,6 +344,16 @@ class Engine:
         check(self._L.smcrt_probe_detector(self._h, det_index, n, _p(start, C.c_double), _p(dir, C.c_double), _p(seg_len, C.c_double),
                                            _p(hit, C.c_int32), _p(b, C.c_int32)))
         return hit, b
+
+    def run_sources(self, positions, nphotons_per_source, seed, id_offset=0, tally_mode=TALLY_ABSORB, survival_bias=False,
+                    threshold=-1.0, chance=-1.0):
+        """Batched isotropic point sources (escape-function drivers). -> (det_totals (n_src, n_det), layer (n_src,))."""
+        pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        tot = np.zeros((len(pos), max(getattr(self, "_n_det", 0), 1)))
+        layer = np.zeros(len(pos), np.int32)
+        check(self._L.smcrt_run_sources(self._h, len(pos), _p(pos, C.c_double), int(nphotons_per_source), int(seed), int(id_offset),
+                                        int(tally_mode), int(survival_bias), threshold, chance, _p(tot, C.c_double), _p(layer, C.c_int32)))
+        return tot, layer
 
     def bench_red(self, pattern, span=333, n_ops=1 << 30):
         """red.global.add.f32 operations per second on this context's path-length grid (smcrt_bench_red)."""

@@ -96,6 +96,10 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t tune_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // brackets of the three register-budget trial launches
+    const float* src_table = nullptr;  // set for the duration of smcrt_run_sources
+    unsigned long long* src_tot = nullptr;
+    unsigned long long src_id0 = 0;
+    long long per_src = 0;
     int tuning = -1;  // >= 0: trial launches in flight for variant key `tuning` (read back in smcrt_wait)
     unsigned char* blob = nullptr;
     DevPrimD* primsD = nullptr;
@@ -702,6 +706,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
         P.hvox[a] = (float)(c->gmax[a] / nn[a]);
     }
     P.src_kind = c->src_kind; P.src_sub = c->src_sub; P.src_alt = c->src_alt;
+    P.src_table = D.src_table; P.src_tot = D.src_tot; P.src_id0 = D.src_id0; P.per_src = D.per_src;
     std::memcpy(P.sp, c->sp, sizeof P.sp);
     std::memcpy(P.Tpos, c->Tpos, sizeof P.Tpos);
     std::memcpy(P.Tdir, c->Tdir, sizeof P.Tdir);
@@ -1206,6 +1211,80 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     }
     if (final_pos && down_f(p, final_pos, 3 * n)) return PROBE_FAIL();
     return 0;
+}
+// Batched point sources: the body of the escape-function drivers (cart/cyl_calc_escape_sym, src/kernelsMod.f90:533-642,
+// 959-1071) for MANY grid cells in one launch.  Per source the reference does: layer = maxloc(d, mask=d<0) at the position;
+// layer == 0 or kappa(layer) == 0 -> escape = 0 without running; else run_MCRT with an isotropic point source there and
+// escape(det) = total_dect / nphotons.  Here every active source owns nphotons_per_source consecutive packet ids.
+extern "C" int smcrt_run_sources(smcrt_ctx* c, int64_t n_src, const double* pos, int64_t nphotons_per_source, uint64_t seed,
+                                 int64_t id_offset, int tally_mode, int survival_bias, double threshold, double chance,
+                                 double* det_totals, int32_t* layer_out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (n_src < 1 || !pos || nphotons_per_source < 1 || !det_totals) return set_err("smcrt_run_sources: invalid arguments");
+    if (c->pending) return set_err("smcrt_run_sources: a run is pending");
+    const int n_top = (int)c->tops.size(), n_det = (int)c->dets.size();
+    if (n_det < 1) return set_err("smcrt_run_sources: no detectors set");
+    // layer of every source position (FP64 SDF evaluation on the device, same code as smcrt_probe_sdf)
+    std::vector<double> dist((size_t)n_src * n_top);
+    rc = smcrt_probe_sdf(c, 0, n_src, pos, dist.data(), nullptr);
+    if (rc) return rc;
+    std::vector<int64_t> active;
+    std::vector<float> table;
+    for (int64_t i = 0; i < n_src; ++i) {
+        int layer = 0;
+        double best = 0.0;
+        for (int t = 0; t < n_top; ++t) {  // maxloc(distances, mask = distances < 0): first maximum wins
+            const double d = dist[(size_t)i * n_top + t];
+            if (d < 0.0 && (layer == 0 || d > best)) { layer = t + 1; best = d; }
+        }
+        if (layer_out) layer_out[i] = layer;
+        bool inside = true;
+        for (int a = 0; a < 3; ++a) inside = inside && pos[3 * i + a] >= -c->gmax[a] && pos[3 * i + a] < c->gmax[a];
+        if (layer != 0 && inside && c->tops[layer - 1].kappa != 0.f) {
+            active.push_back(i);
+            for (int a = 0; a < 3; ++a) table.push_back((float)pos[3 * i + a]);
+        }
+    }
+    std::fill(det_totals, det_totals + (size_t)n_src * n_det, 0.0);
+    if (active.empty()) return 0;
+    // isotropic point emitter; the position comes from the table
+    const int keep_kind = c->src_kind, keep_sub = c->src_sub, keep_alt = c->src_alt;
+    c->src_kind = SMCRT_SRC_POINT;
+    const int G = (int)c->devs.size();
+    const long long n_act = (long long)active.size(), total = n_act * nphotons_per_source;
+    std::vector<DevBuf> tab(G), tot(G);
+    int err = 0;
+    for (int g = 0; g < G && !err; ++g) {
+        DeviceState& D = c->devs[g];
+        if (cudaSetDevice(D.dev) != cudaSuccess || tab[g].alloc(table.size() * 4) || tot[g].alloc((size_t)n_act * n_det * 8) ||
+            cudaMemcpyAsync(tab[g].p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, D.stream) != cudaSuccess ||
+            cudaMemsetAsync(tot[g].p, 0, (size_t)n_act * n_det * 8, D.stream) != cudaSuccess) {
+            err = set_err("smcrt_run_sources: device buffers: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        D.src_table = tab[g].as<float>(); D.src_tot = tot[g].as<unsigned long long>();
+        D.src_id0 = (unsigned long long)id_offset; D.per_src = nphotons_per_source;
+        const long long lo = (long long)((__int128)total * g / G), hi = (long long)((__int128)total * (g + 1) / G);
+        D.ran = false;
+        if (hi > lo) err = run_on_device(c, D, hi - lo, seed, id_offset + lo, tally_mode, survival_bias, threshold, chance, nullptr, nullptr, nullptr, nullptr);
+    }
+    c->pending = true;
+    const int wrc = smcrt_wait(c);
+    std::vector<unsigned long long> h((size_t)n_act * n_det);
+    for (int g = 0; g < G; ++g) {
+        DeviceState& D = c->devs[g];
+        if (!err && !wrc && D.src_tot) {
+            if (cudaSetDevice(D.dev) != cudaSuccess || cudaMemcpy(h.data(), D.src_tot, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+                err = set_err("smcrt_run_sources: download: %s", cudaGetErrorString(cudaGetLastError()));
+            else
+                for (long long k = 0; k < n_act; ++k)
+                    for (int d = 0; d < n_det; ++d) det_totals[(size_t)active[k] * n_det + d] += (double)h[(size_t)k * n_det + d] / 16777216.0;
+        }
+        D.src_table = nullptr; D.src_tot = nullptr; D.per_src = 0; D.src_id0 = 0;
+    }
+    c->src_kind = keep_kind; c->src_sub = keep_sub; c->src_alt = keep_alt;
+    return err ? err : wrc;
 }
 extern "C" int smcrt_bench_red(smcrt_ctx* c, int pattern, int span, int64_t n_ops, double* ops_per_s) {
     if (!c || !ops_per_s) return set_err("smcrt_bench_red: null argument");

@@ -38,6 +38,12 @@ struct KParams {
     float hvox[3];     // half a voxel edge, max/n (centre-origin cell faces of the DDA)
     // source (src/photon.f90), transforms precomputed on the host
     int src_kind, src_sub, src_alt;
+    // batched point sources (smcrt_run_sources; the escape-function drivers, kernelsMod.f90:533-642,959-1071): packet id ->
+    // source index (id - src_id0) / per_src, position from src_table, detector hits summed per (source, detector)
+    const float* src_table;           // n_src x 3, nullptr = the single source of smcrt_set_source
+    unsigned long long* src_tot;      // n_src x n_det Q40.24 totals
+    unsigned long long src_id0;
+    long long per_src;
     float sp[24];
     float Tpos[12];  // local emit position -> world (row-vector affine folded to 3x4)
     float Tdir[9];   // local emit direction -> world (3x3)
@@ -709,7 +715,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
                     const float w_ = D_->kind == 4 ? 1.0f : weight;                                                   \
                     const unsigned long long q_ = (unsigned long long)__float2ll_rn(w_ * DET_FIX);                    \
                     const int slot_ = D_->offset + b_ - 1;                                                            \
-                    if (P.det_in_smem) { /* two native 32-bit ATOMS.ADD with carry (a 64-bit shared add is a CAS spin loop) */ \
+                    if (P.src_tot)                                                                                    \
+                        atomicAdd(&P.src_tot[((pid - P.src_id0) / (unsigned long long)P.per_src) * sc.n_det + i_], q_);       \
+                    else if (P.det_in_smem) { /* two native 32-bit ATOMS.ADD with carry (a 64-bit shared add is a CAS spin loop) */ \
                         unsigned int* w32_ = reinterpret_cast<unsigned int*>(&sbins[slot_]);                          \
                         const unsigned int ql_ = (unsigned int)q_, qh_ = (unsigned int)(q_ >> 32);                    \
                         const unsigned int old_ = atomicAdd(w32_, ql_);                                               \
@@ -869,6 +877,10 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             } else {  // ST_EMIT with a packet id: one emission attempt per iteration (rejections retry next iteration)
                 const Emitted em = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]));
                 px = em.x; py = em.y; pz = em.z; ux = em.dx; uy = em.dy; uz = em.dz;
+                if (P.src_table) {
+                    const float* sp_ = P.src_table + 3ull * ((pid - P.src_id0) / (unsigned long long)P.per_src);
+                    px = sp_[0]; py = sp_[1]; pz = sp_[2];
+                }
                 if (em.ok && in_grid(P, px, py, pz)) {
                     pxd = px; pyd = py; pzd = pz;
                     if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, px, py, pz), 1.0f);

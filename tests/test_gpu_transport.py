@@ -271,3 +271,26 @@ def test_register_budget_trial_is_the_same_job(engine, oracle, smcrt):
     engine.apply(cfg)
     engine.reset_tallies(); engine.run(n, 5)
     assert engine.launch_count - l0 == 6
+
+
+def test_run_sources_matches_one_run_per_source(engine, oracle, smcrt):
+    """smcrt_run_sources = the escape-function drivers' loop body (kernelsMod.f90:533-642) for many cells in one launch:
+    per-source detector totals equal those of one ordinary point-source run per position with the same packet ids."""
+    cfg, osc = _setup(smcrt, oracle, engine, "test_dects.toml")   # scat_test sphere, 3 detectors incl. a camera
+    pos = np.array([[0.0, 0.0, 0.0], [0.3, -0.2, 0.4], [5.0, 0.0, 0.0],      # third: outside every SDF or the grid -> layer 0
+                    [-0.5, 0.5, -0.1], [0.0, 0.0, 0.95]])
+    n_per, seed = 20000, 77
+    tot, layer = engine.run_sources(pos, n_per, seed)
+    assert layer[2] == 0 and (tot[2] == 0).all() and (layer[[0, 1, 3, 4]] > 0).all()
+    kind, dp, nb, _ = cfg.detectors
+    offs = np.concatenate([[0], np.cumsum([(b + 1) if k != 4 else (b + 1) ** 2 for k, b in zip(kind, nb)])])
+    act = [i for i in range(len(pos)) if layer[i] > 0]
+    for k, i in enumerate(act):
+        engine.set_detectors(kind, dp, nb)                         # zeroes the detector tallies
+        sp = np.zeros(24); sp[0:3] = pos[i]; sp[5] = 1.0
+        engine.set_source(A.SRC_POINT, 0, sp)
+        engine.run(n_per, seed, id_offset=k * n_per)
+        bins = engine.fetch(absorb=False)["det_bins"]
+        ref = np.array([bins[offs[d]:offs[d + 1]].sum() for d in range(len(kind))])
+        assert np.allclose(tot[i], ref, rtol=0, atol=1e-6), (i, tot[i], ref)
+    assert tot[act].sum() > 0

@@ -47,6 +47,17 @@ int smcrt_config_scene(const smcrt_config* cfg, int32_t* kind, int32_t* first_ch
 /* push grid + scene + source + detectors into an engine context (what setup() leaves in module state) */
 int smcrt_config_apply(const smcrt_config* cfg, smcrt_ctx* ctx);
 
+/* ---- driver arithmetic ------------------------------------------------------------------------ */
+/* inverse_evaluate (src/kernelsMod.f90:1753-1787): error = -mean_i |total_i / nphotons - target_i| over the detectors whose
+   target is not -1 ("no target").  totals: per-detector sums of bins (total_dect).  Returns -1 when no detector has a target
+   (the reference divides by zero there). */
+int smcrt_inverse_evaluate(int n_det, const double* totals, const double* targets, int64_t nphotons, double* error);
+/* escape-function grid cell centre (cart_calc_escape_sym, src/kernelsMod.f90:576-585): ((i - 0.5) / n) * 2 max - max for the
+   1-based cell (m, n, o), then the two row-vector rotations and the shift.  rot_z / rot_off: 4x4 as stored by the reference
+   (column-major, vec .dot. mat), may be NULL (identity). */
+int smcrt_escape_cell_centre(int m, int n, int o, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax,
+                             const double* rot_z, const double* rot_off, const double* grid_pos, double* out_xyz);
+
 /* ---- output layer (src/writer.f90) ---------------------------------------------------------- */
 /* normalise_fluence (writer.f90:25-52): array *= nx*ny*nz / nphotons, evaluated like the reference */
 int smcrt_normalise_fluence(float* array, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, int64_t nphotons);

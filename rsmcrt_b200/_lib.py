@@ -85,6 +85,9 @@ PROTOTYPES = {
     "smcrt_config_scene": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p,
                                      c_double_p, c_double_p, c_double_p, c_double_p]),
     "smcrt_config_apply": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "smcrt_inverse_evaluate": (C.c_int, [C.c_int, c_double_p, c_double_p, C.c_int64, c_double_p]),
+    "smcrt_escape_cell_centre": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                           c_double_p, c_double_p, c_double_p, c_double_p]),
     "smcrt_normalise_fluence": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64]),
     "smcrt_write_nrrd_f32": (C.c_int, [C.c_char_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "smcrt_write_detectors": (C.c_int, [C.c_void_p, c_double_p, C.c_char_p]),

@@ -887,6 +887,33 @@ int smcrt_config_apply(const smcrt_config* cfg, smcrt_ctx* ctx) {
 
 // normalise_fluence, src/writer.f90:25-52.  The factor mixes real32 literals (2._sp) with real64 extents;
 // Fortran promotes to real64, and array*factor is real32*real64 -> real64 -> stored real32.
+int smcrt_inverse_evaluate(int n_det, const double* totals, const double* targets, int64_t nphotons, double* error) {
+    if (n_det < 0 || (n_det > 0 && (!totals || !targets)) || !error || nphotons < 1) return fail("smcrt_inverse_evaluate: invalid arguments");
+    double e = 0.0;
+    int counter = 0;
+    for (int i = 0; i < n_det; ++i)
+        if (targets[i] != -1.0) {
+            e += std::fabs(totals[i] / (double)nphotons - targets[i]);
+            ++counter;
+        }
+    if (counter == 0) return fail("smcrt_inverse_evaluate: no detector has a target value");
+    *error = -e / counter;
+    return 0;
+}
+int smcrt_escape_cell_centre(int m, int n, int o, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax,
+                             const double* rot_z, const double* rot_off, const double* grid_pos, double* out_xyz) {
+    if (!out_xyz || nxg < 1 || nyg < 1 || nzg < 1) return fail("smcrt_escape_cell_centre: invalid arguments");
+    double v[3] = {(((double)m - 0.5) / nxg) * 2.0 * xmax - xmax, (((double)n - 0.5) / nyg) * 2.0 * ymax - ymax,
+                   (((double)o - 0.5) / nzg) * 2.0 * zmax - zmax};
+    for (const double* M : {rot_z, rot_off})
+        if (M) {  // vec .dot. mat (src/vector_class.f90:292-304): row vector times the matrix, translation in row 4
+            double r[3];
+            for (int j = 0; j < 3; ++j) r[j] = v[0] * M[0 + 4 * j] + v[1] * M[1 + 4 * j] + v[2] * M[2 + 4 * j] + M[3 + 4 * j];
+            v[0] = r[0]; v[1] = r[1]; v[2] = r[2];
+        }
+    for (int a = 0; a < 3; ++a) out_xyz[a] = v[a] + (grid_pos ? grid_pos[a] : 0.0);
+    return 0;
+}
 int smcrt_normalise_fluence(float* array, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, int64_t nphotons) {
     const double num = (2.0 * xmax * 2.0 * ymax * 2.0 * zmax);
     const double den = ((double)(int32_t)nphotons * (2.0 * xmax / nxg) * (2.0 * ymax / nyg) * (2.0 * zmax / nzg));

@@ -217,3 +217,33 @@ def test_metadata_is_a_toml_dump_of_the_dict(smcrt):
     d = tomllib.loads(meta)
     assert d["mua%   1"] == 10.0 and d["mus%   1"] == 90.0 and d["BoxDimensions%   3"] == 0.02
     assert d["focus_type"] == "gaussian" and d["units"] == "cm"
+
+
+def test_inverse_evaluate(smcrt):
+    """src/kernelsMod.f90:1753-1787: -mean |total/N - target| over detectors with a target (-1 = none)."""
+    lib = smcrt.load()
+    totals = np.array([500.0, 250.0, 1000.0])
+    targets = np.array([0.4, -1.0, 0.9])
+    err = C.c_double(0)
+    assert lib.smcrt_inverse_evaluate(3, totals.ctypes.data_as(C.POINTER(C.c_double)), targets.ctypes.data_as(C.POINTER(C.c_double)), 1000,
+                                      C.byref(err)) == 0
+    assert err.value == pytest.approx(-(abs(0.5 - 0.4) + abs(1.0 - 0.9)) / 2)
+    none = np.array([-1.0, -1.0, -1.0])
+    assert lib.smcrt_inverse_evaluate(3, totals.ctypes.data_as(C.POINTER(C.c_double)), none.ctypes.data_as(C.POINTER(C.c_double)), 1000,
+                                      C.byref(err)) != 0
+
+
+def test_escape_cell_centre(smcrt):
+    """src/kernelsMod.f90:576-591: voxel centre of the symmetry grid, two row-vector rotations, shift."""
+    lib = smcrt.load()
+    P = C.POINTER(C.c_double)
+    out = np.zeros(3)
+    pos = np.array([0.1, 0.2, 0.3])
+    assert lib.smcrt_escape_cell_centre(1, 2, 4, 4, 4, 4, 1.0, 2.0, 4.0, None, None, pos.ctypes.data_as(P), out.ctypes.data_as(P)) == 0
+    assert np.allclose(out, [-0.75 + 0.1, -0.5 + 0.2, 3.0 + 0.3])
+    # a rotation about z by 90 degrees stored like the reference's rotate_z (row-vector convention, translation in row 4)
+    rz = np.zeros((4, 4)); rz[0, 1] = 1.0; rz[1, 0] = -1.0; rz[2, 2] = 1.0; rz[3, 3] = 1.0   # v.M: (x, y) -> (-y, x)
+    M = np.asfortranarray(rz)
+    assert lib.smcrt_escape_cell_centre(1, 2, 4, 4, 4, 4, 1.0, 2.0, 4.0, M.ctypes.data_as(P), None, None, out.ctypes.data_as(P)) == 0
+    v = np.array([-0.75, -0.5, 3.0, 1.0]) @ rz
+    assert np.allclose(out, v[:3])

@@ -1173,6 +1173,7 @@ extern "C" int smcrt_trace_packets(smcrt_ctx* c, int64_t n, uint64_t seed, int64
     const char* dbg_path = getenv("SMCRT_DEBUG_LOST");  // engine diagnostics: dump the state of step-capped packets
     if (dbg_path && (dbg.alloc(48 * n) || cudaMemset(dbg.p, 0, 48 * n) != cudaSuccess)) return PROBE_FAIL();
     CU(cudaMemset(f.p, 0xff, 4 * n));
+    CU(cudaMemset(s.p, 0, 4 * n));  // the kernel increments the scatter count in place
     rc = run_on_device(c, D, n, seed, id_offset, tally_mode, survival_bias, -1, -1, f.as<int>(), s.as<int>(), e.as<int>(), p.as<float>(), w.as<int>(), dbg_path ? dbg.as<float>() : nullptr);
     if (rc) return rc;
     CU(cudaStreamSynchronize(D.stream));

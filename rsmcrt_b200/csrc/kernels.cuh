@@ -630,11 +630,10 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
 #endif
 // optional per-packet record of smcrt_trace_packets (out of line: cold)
-__device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, int nscatt, uint32_t ev, int steps,
+__device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, uint32_t ev, int steps,
                                            float x, float y, float z) {
     const long long k = (long long)(pid - P.id_offset);
     P.out_fate[k] = fate;
-    if (P.out_nscatt) P.out_nscatt[k] = nscatt;
     if (P.out_events) P.out_events[k] = fate == 3 ? -why : (int)ev;
     if (P.out_sweeps) P.out_sweeps[k] = steps;
     if (P.out_pos) { P.out_pos[3 * k] = x; P.out_pos[3 * k + 1] = y; P.out_pos[3 * k + 2] = z; }
@@ -677,12 +676,13 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
     double pxd = 0, pyd = 0, pzd = 0;
     float px = 0, py = 0, pz = 0, ux = 0, uy = 0, uz = 1, sx = 0, sy = 0, sz = 0;  // position, direction, segment start
     float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
-    int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0, pk_nscatt = 0;
+    int layer = 0, new_layer = 0, state = ST_EMIT, bounces = 0, steps = 0;
     bool tflag = false, launch = false, have_pid = false;
     int phase = 0;  // of ST_MARCH: 0 = top of the tauint2 loop, 1 = re-evaluation after a boundary nudge, 2 = inside the sphere-trace loop
     unsigned long long pid = 0;
     uint32_t ev = 0;
-    unsigned int c_nscatt = 0, c_sweeps = 0, c_bounces = 0, c_launched = 0, c_retries = 0, c_lost = 0, c_dethits = 0;  // per thread: < 2^32
+    // per-thread event counters (< 2^32 each); the rare ones (bounces, emit retries, lost) go straight to the global counters
+    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
 
 #ifdef SMCRT_DBG_WALK  // engine diagnostics (-DSMCRT_DBG_WALK): print every update_grids call of packet SMCRT_DEBUG_PID
 #define DBG_WALK(FX, FY, FZ, LEN)                                                                                     \
@@ -734,9 +734,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
     // packet finished: publish the optional per-packet record and ask for a new packet
 #define RETIRE(FATE, WHY)                                                                                             \
     do {                                                                                                              \
-        if (P.out_fate) record_packet(P, pid, (FATE), (WHY), pk_nscatt, ev, steps, px, py, pz);                       \
-        c_bounces += bounces;                                                                                         \
-        if ((FATE) == FATE_LOST) ++c_lost;                                                                            \
+        if (P.out_fate) record_packet(P, pid, (FATE), (WHY), ev, steps, px, py, pz);                                  \
+        if (bounces) atomicAdd(&P.counters[C_BOUNCES], (unsigned long long)bounces);                                  \
+        if ((FATE) == FATE_LOST) atomicAdd(&P.counters[C_LOST], 1ull);                                                \
         state = ST_EMIT; have_pid = false;                                                                            \
     } while (0)
     // end of tauint2 (inttau2.f90:354-362) + loop test of kernelsMod.f90:1958
@@ -768,8 +768,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             else {
                 pid = P.id_offset + k;
                 have_pid = true;
-                ev = 0; bounces = 0; steps = 0; pk_nscatt = 0; weight = 1.0f; tflag = false;
-                ++c_launched;
+                ev = 0; bounces = 0; steps = 0; weight = 1.0f; tflag = false;
             }
         }
         if (state >= ST_FRESNEL && state <= ST_EMIT) {
@@ -868,7 +867,8 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
                 }
                 if (alive) {
                     hg_scatter(ux, uy, uz, sc.tops[layer - 1].hgg, u01(w[1]), u01(w[2]));
-                    ++c_nscatt; ++pk_nscatt;
+                    ++c_nscatt;
+                    if (P.out_nscatt) ++P.out_nscatt[pid - P.id_offset];  // smcrt_trace_packets only (zeroed by the host)
                     tau = -SMCRT_LOG(u01_open0(w[3]));
                     taurun = 0.f; qs = 0.f;
                     sx = px; sy = py; sz = pz;
@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
                     launch = true; layer = 0;
                     state = ST_MARCH; phase = 0;
                 } else {  // emitter rejection / start voxel outside the grid (kernelsMod.f90:1939-1943, quirk Q6)
-                    ++c_retries;
+                    atomicAdd(&P.counters[C_RETRIES], 1ull);
                     if (ev > 100000u) RETIRE(FATE_LOST, LOST_EMIT);
                 }
             }
@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             w[15 * B] = __float_as_uint(qs); w[16 * B] = __float_as_uint(dlast); w[17 * B] = __float_as_uint(weight);
             w[18 * B] = (uint32_t)layer | ((uint32_t)new_layer << 16);
             w[19 * B] = (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u);
-            w[20 * B] = (uint32_t)bounces; w[21 * B] = (uint32_t)steps; w[22 * B] = (uint32_t)pk_nscatt;
+            w[20 * B] = (uint32_t)bounces; w[21 * B] = (uint32_t)steps;
             w[23 * B] = (uint32_t)pid; w[24 * B] = (uint32_t)(pid >> 32); w[25 * B] = ev;
             __syncthreads();  // (B) all slots written
             if (all_done) break;
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             layer = (int)(r[18 * B] & 0xffffu); new_layer = (int)(r[18 * B] >> 16);
             const uint32_t fl = r[19 * B];
             state = (int)(fl & 15u); phase = (int)((fl >> 4) & 15u); tflag = (fl & 256u) != 0; launch = (fl & 512u) != 0; have_pid = (fl & 1024u) != 0;
-            bounces = (int)r[20 * B]; steps = (int)r[21 * B]; pk_nscatt = (int)r[22 * B];
+            bounces = (int)r[20 * B]; steps = (int)r[21 * B];
             pid = (unsigned long long)r[23 * B] | ((unsigned long long)r[24 * B] << 32); ev = r[25 * B];
             ++xiter;
         }
@@ -1102,7 +1102,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
-    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, c_bounces, c_launched, c_retries, c_lost, 0ull, c_dethits};
+    // every id below nphotons was claimed exactly once
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[C_LAUNCHED], (unsigned long long)P.nphotons);
+    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits};
 #pragma unroll
     for (int c = 0; c < C_COUNT; ++c) {
         unsigned long long v = cs[c];

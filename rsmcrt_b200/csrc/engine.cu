@@ -95,7 +95,7 @@ struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t tune_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // brackets of the three register-budget trial launches
+    cudaEvent_t tune_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
     const float* src_table = nullptr;  // set for the duration of smcrt_run_sources
     unsigned long long* src_tot = nullptr;
     unsigned long long src_id0 = 0;
@@ -154,7 +154,7 @@ struct smcrt_ctx {
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
     bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
-    // register-budget choice per kernel variant [pathlength][detectors]: 0 = not timed yet, else MINBLOCKS (2, 3 or 4)
+    // kernel-variant choice per tally configuration [pathlength][detectors]: 0 = not timed yet, else 1 + index into VARIANTS
     int tuned_mb[2][2] = {{0, 0}, {0, 0}};
     uint64_t scene_hash = 0, det_hash = 0;  // tuned_mb is kept while the scene and detectors stay bit-identical
     int cull_n[3] = {0, 0, 0};
@@ -209,6 +209,7 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
             cudaEventCreate(&D.ev0) != cudaSuccess || cudaEventCreate(&D.ev1) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[0]) != cudaSuccess || cudaEventCreate(&D.tune_ev[1]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
+            cudaEventCreate(&D.tune_ev[4]) != cudaSuccess || cudaEventCreate(&D.tune_ev[5]) != cudaSuccess ||
             cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess ||
             cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess) {
             delete c;
@@ -746,7 +747,7 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes, bool d
 }
 template <bool PL, bool HD>
 static int launch_mb(bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
-    if (compact) return launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
+    if (compact) return mb == 4 ? launch_trace<PL, HD, true, 4>(P, D, smem_bytes, dry) : launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
     switch (mb) {
         case 2: return launch_trace<PL, HD, false, 2>(P, D, smem_bytes, dry);
         case 4: return launch_trace<PL, HD, false, 4>(P, D, smem_bytes, dry);
@@ -772,41 +773,48 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
     CU(cudaSetDevice(D.dev));
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
-    int smem = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
-    // event compaction pays when the sweep is cheap (few SDFs) and the divergent event code dominates
-    const bool compact = c->compact_allowed && (int)c->tops.size() <= 4 && c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;
-    P.xchg_off = (smem + 15) & ~15;
-    if (compact) smem = P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK;
+    const int smem_plain = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
+    P.xchg_off = (smem_plain + 15) & ~15;
+    const int smem_compact = P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK;
     CU(cudaEventRecord(D.ev0, D.stream));
     const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
-    // Register budget: the first large run of a scene spends three equal slices of its own packets on the three
-    // budgets, bracketed by events; smcrt_wait reads the times and later runs use the fastest.  No packet is traced twice:
-    // streams depend on (seed, id) only, so a run split into id ranges is the same run.
-    static const char* force_s = getenv("SMCRT_MINBLOCKS_FORCE");
-    const int forced = force_s ? atoi(force_s) : 0;
-    int mb = forced ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] : 3);
+    // Kernel variant: register budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers) x event
+    // compaction on/off.  Which one wins depends on the scene, so the first large run of a scene spends equal slices of its
+    // own packets on the candidates, bracketed by events; smcrt_wait reads the times and later runs use the fastest.  No
+    // packet is traced twice: streams depend on (seed, id) only, so a run split into id ranges is the same run.
+    struct Variant { bool compact; int mb; };
+    static const Variant VARIANTS[5] = {{false, 2}, {false, 3}, {false, 4}, {true, 3}, {true, 4}};
+    static const char* force_mb = getenv("SMCRT_MINBLOCKS_FORCE");
+    static const char* force_var = getenv("SMCRT_VARIANT_FORCE");
+    const bool compact_ok = c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;
+    int forced = -1;
+    if (force_var) forced = std::min(std::max(atoi(force_var), 0), 4);
+    else if (c->compact_allowed) forced = 3;  // SMCRT_COMPACT=1
+    else if (force_mb) forced = std::min(std::max(atoi(force_mb), 2), 4) - 2;
+    int var = forced >= 0 ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] - 1 : 1);
+    if (VARIANTS[var].compact && !compact_ok) var = 1;
     int n_launch = 1;
     const long long TUNE_MIN = 8ll << 20;
-    if (!forced && !compact && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
-        const long long slice = std::min<long long>(std::max<long long>(nphotons / 32, 1ll << 20), 1ll << 22);
-        for (int k = 0; k < 3; ++k) {  // load the three kernels first: the load would otherwise sit inside the event brackets
-            int rc = launch_variant(pl, hd, false, 2 + k, P, D, smem, true);
+    if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
+        const long long slice = std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 22);
+        for (int k = 0; k < 5; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
+            int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, P, D, VARIANTS[k].compact ? smem_compact : smem_plain, true);
             if (rc) return rc;
         }
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 5; ++k) {
             KParams Q = P;
             Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
             CU(cudaEventRecord(D.tune_ev[k], D.stream));
-            int rc = launch_variant(pl, hd, false, 2 + k, Q, D, smem);
+            int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, Q, D, VARIANTS[k].compact ? smem_compact : smem_plain);
             if (rc) return rc;
             CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
         }
-        CU(cudaEventRecord(D.tune_ev[3], D.stream));
+        CU(cudaEventRecord(D.tune_ev[5], D.stream));
         D.tuning = (pl ? 2 : 0) | (hd ? 1 : 0);
-        P.nphotons -= 3 * slice; P.id_offset += (unsigned long long)(3 * slice);
-        n_launch = 4;
+        P.nphotons -= 5 * slice; P.id_offset += (unsigned long long)(5 * slice);
+        n_launch = 6;
     }
-    int rc = launch_variant(pl, hd, compact, mb, P, D, smem);
+    int rc = launch_variant(pl, hd, VARIANTS[var].compact, VARIANTS[var].mb, P, D, VARIANTS[var].compact ? smem_compact : smem_plain);
     if (rc) return rc;
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
@@ -856,15 +864,15 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
             ms = std::max(ms, (double)t);
         }
-        if (D.tuning >= 0) {  // the three trial slices of run_on_device: keep the fastest register budget
+        if (D.tuning >= 0) {  // the trial slices of run_on_device: keep the fastest kernel variant
             float best = 0.f;
             int arg = 1;
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 5; ++k) {
                 float t = 0;
                 CU(cudaEventElapsedTime(&t, D.tune_ev[k], D.tune_ev[k + 1]));
                 if (k == 0 || t < best) { best = t; arg = k; }
             }
-            c->tuned_mb[(D.tuning >> 1) & 1][D.tuning & 1] = 2 + arg;
+            c->tuned_mb[(D.tuning >> 1) & 1][D.tuning & 1] = 1 + arg;
             D.tuning = -1;
         }
     }
@@ -877,6 +885,10 @@ extern "C" int smcrt_run(smcrt_ctx* c, int64_t nphotons, uint64_t seed, int64_t 
     int rc = smcrt_run_async(c, nphotons, seed, id_offset, tally_mode, survival_bias, threshold, chance);
     if (rc) return rc;
     return smcrt_wait(c);
+}
+extern "C" int smcrt_kernel_variant(const smcrt_ctx* c, int tally_mode) {
+    if (!c) return -1;
+    return c->tuned_mb[(tally_mode & SMCRT_TALLY_PATHLENGTH) ? 1 : 0][c->dets.empty() ? 0 : 1] - 1;
 }
 extern "C" double smcrt_last_run_ms(const smcrt_ctx* c) { return c ? c->last_ms : 0.0; }
 extern "C" int64_t smcrt_launch_count(const smcrt_ctx* c) { return c ? c->launches : 0; }

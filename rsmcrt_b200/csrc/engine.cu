@@ -95,7 +95,7 @@ struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t tune_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
+    cudaEvent_t tune_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
     const float* src_table = nullptr;  // set for the duration of smcrt_run_sources
     unsigned long long* src_tot = nullptr;
     unsigned long long src_id0 = 0;
@@ -210,6 +210,7 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
             cudaEventCreate(&D.tune_ev[0]) != cudaSuccess || cudaEventCreate(&D.tune_ev[1]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[4]) != cudaSuccess || cudaEventCreate(&D.tune_ev[5]) != cudaSuccess ||
+            cudaEventCreate(&D.tune_ev[6]) != cudaSuccess ||
             cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess ||
             cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess) {
             delete c;
@@ -725,7 +726,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     }
     P.dda_plain = getenv("SMCRT_DDA_AGG") ? 0 : 1;
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
-    P.max_steps = (int)std::min<long long>(c->max_steps, 2000000000ll);
+    P.max_steps = (int)std::min<long long>(c->max_steps, 1900000ll);  // the compaction step packs sweep count and event index (<= sweeps + 100000 emit retries) into 21 bits each
     return 0;
 }
 
@@ -747,7 +748,13 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes, bool d
 }
 template <bool PL, bool HD>
 static int launch_mb(bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
-    if (compact) return mb == 4 ? launch_trace<PL, HD, true, 4>(P, D, smem_bytes, dry) : launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
+    if (compact) {
+        switch (mb) {
+            case 2: return launch_trace<PL, HD, true, 2>(P, D, smem_bytes, dry);
+            case 4: return launch_trace<PL, HD, true, 4>(P, D, smem_bytes, dry);
+            default: return launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
+        }
+    }
     switch (mb) {
         case 2: return launch_trace<PL, HD, false, 2>(P, D, smem_bytes, dry);
         case 4: return launch_trace<PL, HD, false, 4>(P, D, smem_bytes, dry);
@@ -783,12 +790,13 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     // own packets on the candidates, bracketed by events; smcrt_wait reads the times and later runs use the fastest.  No
     // packet is traced twice: streams depend on (seed, id) only, so a run split into id ranges is the same run.
     struct Variant { bool compact; int mb; };
-    static const Variant VARIANTS[5] = {{false, 2}, {false, 3}, {false, 4}, {true, 3}, {true, 4}};
+    constexpr int NVAR = 6;
+    static const Variant VARIANTS[NVAR] = {{false, 2}, {false, 3}, {false, 4}, {true, 3}, {true, 4}, {true, 2}};
     static const char* force_mb = getenv("SMCRT_MINBLOCKS_FORCE");
     static const char* force_var = getenv("SMCRT_VARIANT_FORCE");
     const bool compact_ok = c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;
     int forced = -1;
-    if (force_var) forced = std::min(std::max(atoi(force_var), 0), 4);
+    if (force_var) forced = std::min(std::max(atoi(force_var), 0), NVAR - 1);
     else if (c->compact_allowed) forced = 3;  // SMCRT_COMPACT=1
     else if (force_mb) forced = std::min(std::max(atoi(force_mb), 2), 4) - 2;
     int var = forced >= 0 ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] - 1 : 1);
@@ -797,11 +805,11 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     const long long TUNE_MIN = 8ll << 20;
     if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
         const long long slice = std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 22);
-        for (int k = 0; k < 5; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
+        for (int k = 0; k < NVAR; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
             int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, P, D, VARIANTS[k].compact ? smem_compact : smem_plain, true);
             if (rc) return rc;
         }
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < NVAR; ++k) {
             KParams Q = P;
             Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
             CU(cudaEventRecord(D.tune_ev[k], D.stream));
@@ -809,10 +817,10 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
             if (rc) return rc;
             CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
         }
-        CU(cudaEventRecord(D.tune_ev[5], D.stream));
+        CU(cudaEventRecord(D.tune_ev[NVAR], D.stream));
         D.tuning = (pl ? 2 : 0) | (hd ? 1 : 0);
-        P.nphotons -= 5 * slice; P.id_offset += (unsigned long long)(5 * slice);
-        n_launch = 6;
+        P.nphotons -= NVAR * slice; P.id_offset += (unsigned long long)(NVAR * slice);
+        n_launch = NVAR + 1;
     }
     int rc = launch_variant(pl, hd, VARIANTS[var].compact, VARIANTS[var].mb, P, D, VARIANTS[var].compact ? smem_compact : smem_plain);
     if (rc) return rc;
@@ -867,7 +875,7 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
         if (D.tuning >= 0) {  // the trial slices of run_on_device: keep the fastest kernel variant
             float best = 0.f;
             int arg = 1;
-            for (int k = 0; k < 5; ++k) {
+            for (int k = 0; k < 6; ++k) {
                 float t = 0;
                 CU(cudaEventElapsedTime(&t, D.tune_ev[k], D.tune_ev[k + 1]));
                 if (k == 0 || t < best) { best = t; arg = k; }

@@ -639,13 +639,13 @@ __device__ __noinline__ void record_packet(const KParams& P, unsigned long long 
     if (P.out_pos) { P.out_pos[3 * k] = x; P.out_pos[3 * k + 1] = y; P.out_pos[3 * k + 2] = z; }
 }
 
-constexpr int XCHG_WORDS = 26;  // 32-bit words of packet state exchanged by the compaction step
+constexpr int XCHG_WORDS = 22;  // 32-bit words of packet state exchanged by the compaction step (at most)
 
 // MINBLOCKS = resident CTAs per SM the register allocation is made for (2: 128 registers, no spills; 3: 80; 4: 64).  Which one
 // wins depends on the scene (slab with detectors: 4, +8 %; long histories inside one body: 2, +17 %), so the engine times
 // the three on the first large run of a scene and keeps the fastest (engine.cu: run_on_device).
 template <bool PATHLEN, bool HASDET, bool COMPACT, int MINBLOCKS>
-__global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
         const int4* src = reinterpret_cast<const int4*>(P.blob);
@@ -1059,17 +1059,20 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             const bool all_done = tot[ST_DONE] == (uint32_t)blockDim.x;
             uint32_t* w = xbuf + (base + woff + (uint32_t)rank);
             const int B = blockDim.x;
+            // packet state: 18 words + 3 (segment start, detector scenes) + 1 (weight, survival biasing).  qs is implied by the
+            // state, the event index shares a word with the flags (ev <= 100000 < 2^17), steps (< 2^21) one with bounces (<= 1001)
             w[0 * B] = (uint32_t)__double2loint(pxd); w[1 * B] = (uint32_t)__double2hiint(pxd);
             w[2 * B] = (uint32_t)__double2loint(pyd); w[3 * B] = (uint32_t)__double2hiint(pyd);
             w[4 * B] = (uint32_t)__double2loint(pzd); w[5 * B] = (uint32_t)__double2hiint(pzd);
             w[6 * B] = __float_as_uint(ux); w[7 * B] = __float_as_uint(uy); w[8 * B] = __float_as_uint(uz);
-            w[9 * B] = __float_as_uint(sx); w[10 * B] = __float_as_uint(sy); w[11 * B] = __float_as_uint(sz);
-            w[12 * B] = __float_as_uint(tau); w[13 * B] = __float_as_uint(taurun); w[14 * B] = __float_as_uint(dstep);
-            w[15 * B] = __float_as_uint(qs); w[16 * B] = __float_as_uint(dlast); w[17 * B] = __float_as_uint(weight);
-            w[18 * B] = (uint32_t)layer | ((uint32_t)new_layer << 16);
-            w[19 * B] = (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u);
-            w[20 * B] = (uint32_t)bounces; w[21 * B] = (uint32_t)steps;
-            w[23 * B] = (uint32_t)pid; w[24 * B] = (uint32_t)(pid >> 32); w[25 * B] = ev;
+            w[9 * B] = __float_as_uint(tau); w[10 * B] = __float_as_uint(taurun); w[11 * B] = __float_as_uint(dstep);
+            w[12 * B] = __float_as_uint(dlast);
+            w[13 * B] = (uint32_t)layer | ((uint32_t)new_layer << 16);
+            w[14 * B] = (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u) | (ev << 11);
+            w[15 * B] = (uint32_t)steps | ((uint32_t)bounces << 21);
+            w[16 * B] = (uint32_t)pid; w[17 * B] = (uint32_t)(pid >> 32);
+            if (HASDET) { w[18 * B] = __float_as_uint(sx); w[19 * B] = __float_as_uint(sy); w[20 * B] = __float_as_uint(sz); }
+            if (P.survival) w[21 * B] = __float_as_uint(weight);
             __syncthreads();  // (B) all slots written
             if (all_done) break;
             const uint32_t* r = xbuf + threadIdx.x;
@@ -1078,14 +1081,17 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, MINBLOCKS) trace_persistent(const
             pzd = __hiloint2double((int)r[5 * B], (int)r[4 * B]);
             px = (float)pxd; py = (float)pyd; pz = (float)pzd;
             ux = __uint_as_float(r[6 * B]); uy = __uint_as_float(r[7 * B]); uz = __uint_as_float(r[8 * B]);
-            sx = __uint_as_float(r[9 * B]); sy = __uint_as_float(r[10 * B]); sz = __uint_as_float(r[11 * B]);
-            tau = __uint_as_float(r[12 * B]); taurun = __uint_as_float(r[13 * B]); dstep = __uint_as_float(r[14 * B]);
-            qs = __uint_as_float(r[15 * B]); dlast = __uint_as_float(r[16 * B]); weight = __uint_as_float(r[17 * B]);
-            layer = (int)(r[18 * B] & 0xffffu); new_layer = (int)(r[18 * B] >> 16);
-            const uint32_t fl = r[19 * B];
+            tau = __uint_as_float(r[9 * B]); taurun = __uint_as_float(r[10 * B]); dstep = __uint_as_float(r[11 * B]);
+            dlast = __uint_as_float(r[12 * B]);
+            layer = (int)(r[13 * B] & 0xffffu); new_layer = (int)(r[13 * B] >> 16);
+            const uint32_t fl = r[14 * B];
             state = (int)(fl & 15u); phase = (int)((fl >> 4) & 15u); tflag = (fl & 256u) != 0; launch = (fl & 512u) != 0; have_pid = (fl & 1024u) != 0;
-            bounces = (int)r[20 * B]; steps = (int)r[21 * B];
-            pid = (unsigned long long)r[23 * B] | ((unsigned long long)r[24 * B] << 32); ev = r[25 * B];
+            ev = fl >> 11;
+            steps = (int)(r[15 * B] & 0x1fffffu); bounces = (int)(r[15 * B] >> 21);
+            pid = (unsigned long long)r[16 * B] | ((unsigned long long)r[17 * B] << 32);
+            if (HASDET) { sx = __uint_as_float(r[18 * B]); sy = __uint_as_float(r[19 * B]); sz = __uint_as_float(r[20 * B]); }
+            if (P.survival) weight = __uint_as_float(r[21 * B]);
+            qs = (state == ST_BND_PROBE || state == ST_CROSS) ? dstep : 0.f;
             ++xiter;
         }
     }

@@ -251,19 +251,22 @@ def test_validation1_pathlength_hot_column(engine, oracle, smcrt):
 
 
 def test_register_budget_trial_is_the_same_job(engine, oracle, smcrt):
-    """The first large run of a scene spends five slices of its own packets on the five kernel variants (6 launches) and later
+    """The first large run of a scene spends six slices of its own packets on the six kernel variants (7 launches) and later
     runs use the fastest (1 launch).  A run split into id ranges is the same run: the integer tallies are bit-identical."""
+    import os
+    if any(os.environ.get(k) for k in ("SMCRT_VARIANT_FORCE", "SMCRT_MINBLOCKS_FORCE", "SMCRT_COMPACT")):
+        pytest.skip("kernel variant forced by the environment")
     cfg, _ = _setup(smcrt, oracle, engine, "validation1.toml")
     n = 9_000_000
     l0 = engine.launch_count
     engine.run(n, 5)
     a = engine.fetch()
-    assert engine.launch_count - l0 == 6
-    assert 0 <= engine.kernel_variant() <= 4
+    assert engine.launch_count - l0 == 7
+    assert 0 <= engine.kernel_variant() <= 5
     engine.reset_tallies()
     engine.run(n, 5)
     b = engine.fetch()
-    assert engine.launch_count - l0 == 7
+    assert engine.launch_count - l0 == 8
     assert a["counters"]["launched"] == b["counters"]["launched"] == n
     assert a["counters"]["nscatt"] == b["counters"]["nscatt"]
     assert np.array_equal(a["det_bins"], b["det_bins"])          # Q40.24 fixed point: order independent
@@ -271,7 +274,7 @@ def test_register_budget_trial_is_the_same_job(engine, oracle, smcrt):
     # re-sending the identical scene keeps the choice; a different scene drops it
     engine.apply(cfg)
     engine.reset_tallies(); engine.run(n, 5)
-    assert engine.launch_count - l0 == 8
+    assert engine.launch_count - l0 == 9
 
 
 def test_run_sources_matches_one_run_per_source(engine, oracle, smcrt):

@@ -236,8 +236,9 @@ def main():
         return float(t.item())
 
     # ---------------- warm-up (kernel, and the NCCL communicator: its first collective builds the NVLink channels)
+    # full-size steps: the first large run of a scene is where the engine times its kernel variants (smcrt_kernel_variant)
     for w in range(args.warmup):
-        eng.run(max(n_step // 20, 100_000), seed, id_offset=0, tally_mode=mode)
+        eng.run(n_step, seed, id_offset=0, tally_mode=mode)
     if world > 1:
         eng.comm_reduce(0)
     eng.reset_tallies()
@@ -274,7 +275,7 @@ def main():
     eng.reset_tallies()
     h2d = scene.kind.nbytes + scene.first_child.nbytes + scene.n_child.nbytes + scene.xform.nbytes + scene.params.nbytes + \
         scene.top_node.nbytes + 4 * scene.mus.nbytes + 24 * 8 + (kind.nbytes + dp.nbytes + nb.nbytes)
-    d2h = nv * 4 + eng.det_bins_total * 8 + 8 * 8
+    d2h_actual = 0
     src_k, src_s, src_p = cfg.source
     # host result buffers of the caller (the reference's module arrays), page-locked once outside the timed region
     h_absorb = np.zeros(nv, np.float32)
@@ -289,12 +290,15 @@ def main():
         eng.set_source(src_k, src_s, src_p)
         eng.set_detectors(kind, dp, nb)            # (also zeroes the detector tallies, like the escape driver's reset)
         eng.run(n_step, seed + 1, id_offset=off, tally_mode=mode)
-        cn = eng.fetch_into(absorb=h_absorb, det_bins=h_bins)   # device -> host: absorb grid, detector bins, counters
+        # device -> host, the sequence of the Fortran shim: module arrays += device tallies, then reset
+        cn = eng.fetch_into(absorb=h_absorb, det_bins=h_bins, accumulate=True)
+        d2h_actual += eng.last_fetch_bytes
+        eng.reset_tallies()
         _ = float(h_bins.sum()) + cn["nscatt"]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = packets / e2e_s
-    absorbed_per_packet = float(h_absorb.sum(dtype=np.float64)) / (n_step * args.steps)  # this rank's device tallies of the e2e region
+    absorbed_per_packet = float(h_absorb.sum(dtype=np.float64)) / (n_step * args.steps)  # host array accumulated over the e2e steps
     eng.unpin_host(h_absorb)
     eng.unpin_host(h_bins)
 
@@ -349,9 +353,11 @@ def main():
         "config": {"workload": f"res/{args.scene} (BASELINE configs[1]: slab validation, pencil beam, 500^3 grid, 2 circle detectors)",
                    "packets_per_step_per_gpu": n_step, "tally_mode": mode, "parallelism": f"packets sharded over {world} GPU(s), NCCL reduce at end",
                    "l2_note": "no HBM-resident input stream: scene (<1 KB) lives in shared memory; tally grid 500 MB > L2",
-                   "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms},
+                   "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms, "kernel_variant": eng.kernel_variant(mode)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_actual // args.steps),
+                "d2h_note": "absorb grid read back as (index, value) pairs of its non-zero voxels after a device-side scan (smcrt_fetch); "
+                            f"the dense array would be {nv * 4} bytes"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                      "traffic": traffic, "hbm": hbm, "red": red,

@@ -183,6 +183,10 @@ int64_t smcrt_launch_count(const smcrt_ctx* ctx);
    (the reference's `jmeanGLOBAL = jmean` after in-place accumulation), else overwrite. */
 int smcrt_fetch(smcrt_ctx* ctx, float* jmean, float* absorb, float* emission, double* det_bins,
                 smcrt_counters* counters, int accumulate);
+/* Device -> host bytes the last smcrt_fetch moved.  A grid whose non-zero voxels are few (< 1/64 of the grid; e.g. a pencil
+ * beam in a wide slab) is read back as (index, value) pairs after one scan on the device instead of as the whole array;
+ * the result in the caller's array is identical.  SMCRT_NO_SPARSE_FETCH=1 disables it. */
+uint64_t smcrt_last_fetch_bytes(const smcrt_ctx* ctx);
 /* zarray + detector reset (setup.f90:192-205, kernelsMod.f90:2418-2439) */
 int smcrt_reset_tallies(smcrt_ctx* ctx);
 /* Page-lock (cudaHostRegister) / release a host buffer that smcrt_fetch will be given repeatedly, e.g. the module arrays

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "smcrt_probe_detector": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p]),
     "smcrt_trace_packets": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, c_int32_p, c_int32_p,
                                       c_double_p, c_int32_p, c_int32_p]),
+    "smcrt_last_fetch_bytes": (C.c_uint64, [C.c_void_p]),
     "smcrt_kernel_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "smcrt_run_sources": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double,
                                     C.c_double, c_double_p, c_int32_p]),

@@ -355,6 +355,10 @@ class Engine:
                                         int(tally_mode), int(survival_bias), threshold, chance, _p(tot, C.c_double), _p(layer, C.c_int32)))
         return tot, layer
 
+    @property
+    def last_fetch_bytes(self):
+        return int(self._L.smcrt_last_fetch_bytes(self._h))
+
     def kernel_variant(self, tally_mode=TALLY_ABSORB):
         """-1 until the first large run has timed the candidates; then 0..4 (smcrt_kernel_variant)."""
         return int(self._L.smcrt_kernel_variant(self._h, int(tally_mode)))

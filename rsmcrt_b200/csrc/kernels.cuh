@@ -1208,6 +1208,34 @@ __global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det
     }
 }
 
+// Sparse read-back of a tally grid (smcrt_fetch): (index, value) pairs of the non-zero voxels, unordered.  A pencil-beam slab run
+// touches ~2000 of 1.25e8 voxels; the scan reads the grid once at HBM speed and the host copy shrinks from 500 MB to a few KB.
+// Gives up (cursor > cap) as soon as the grid turns out to be dense; the caller then copies it whole.
+__global__ void nnz_pack_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ idx, float* __restrict__ val,
+                                unsigned long long* cursor, unsigned long long cap) {
+    const long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+            if (*reinterpret_cast<volatile unsigned long long*>(cursor) > cap) return;
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (e[k] != 0.f) {
+                    const unsigned long long at = atomicAdd(cursor, 1ull);
+                    if (at < cap) { idx[at] = (unsigned int)(4 * i + k); val[at] = e[k]; }
+                }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n4 << 2; i < n; ++i)
+            if (g[i] != 0.f) {
+                const unsigned long long at = atomicAdd(cursor, 1ull);
+                if (at < cap) { idx[at] = (unsigned int)i; val[at] = g[i]; }
+            }
+}
+
 // red.global.add.f32 throughput microbenchmark (the secondary bound of path-length mode).
 //   pattern 0: every thread walks its own pseudo-random voxel sequence over the whole grid (L2/HBM scatter)
 //   pattern 1: every thread walks the SAME column of `span` voxels (stride nx*ny: the beam axis of a pencil source)

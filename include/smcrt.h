@@ -207,6 +207,11 @@ int smcrt_comm_reduce(smcrt_ctx* ctx, int root);
    (pos = n x 3 doubles) with the engine's FP32 device code.  normal (n x 3, may be NULL) is only written
    for a single SDF (replaces calcNormal, sdf_base.f90:166-190). */
 int smcrt_probe_sdf(smcrt_ctx* ctx, int top_index, int64_t n, const double* pos, double* dist, double* normal);
+/* The directional step bound of top-level SDF `top_index` (engine-specific; replaces the `min |d|` step of inttau2.f90:155-176
+ * for bodies with a closed-form ray intersection): dist = signed distance at pos, bound >= |dist| = how far the packet may move
+ * along dir without crossing this body's surface (1e30 = never), exact = 1 when bound IS the along-ray distance to the surface. */
+int smcrt_probe_ray(smcrt_ctx* ctx, int top_index, int64_t n, const double* pos, const double* dir, double* dist, double* bound,
+                    int32_t* exact);
 /* reflect_refract with a supplied uniform (surfaces.f90:14-127): in dir/nrm n x 3, n1,n2,xi n; out new dir,
    R (Fresnel coefficient), rflag. */
 int smcrt_probe_fresnel(smcrt_ctx* ctx, int64_t n, const double* dir, const double* nrm, const double* n1,

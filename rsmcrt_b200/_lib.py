@@ -56,6 +56,7 @@ PROTOTYPES = {
     "smcrt_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "smcrt_comm_reduce": (C.c_int, [C.c_void_p, C.c_int]),
     "smcrt_probe_sdf": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
+    "smcrt_probe_ray": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "smcrt_probe_fresnel": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       c_double_p, c_double_p, c_int32_p]),
     "smcrt_probe_scatter": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),

@@ -345,6 +345,16 @@ class Engine:
                                            _p(hit, C.c_int32), _p(b, C.c_int32)))
         return hit, b
 
+    def probe_ray(self, top_index, pos, dirs):
+        """-> (dist, bound, exact) of the directional step bound (smcrt_probe_ray)."""
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        n = len(pos)
+        d, b, ex = np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+        check(self._L.smcrt_probe_ray(self._h, int(top_index), n, _p(pos, C.c_double), _p(dirs, C.c_double), _p(d, C.c_double),
+                                      _p(b, C.c_double), _p(ex, C.c_int32)))
+        return d, b, ex
+
     def run_sources(self, positions, nphotons_per_source, seed, id_offset=0, tally_mode=TALLY_ABSORB, survival_bias=False,
                     threshold=-1.0, chance=-1.0):
         """Batched isotropic point sources (escape-function drivers). -> (det_totals (n_src, n_det), layer (n_src,))."""

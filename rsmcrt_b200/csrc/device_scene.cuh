@@ -183,6 +183,74 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
     return T(1e30);
 }
 
+#define SMCRT_BIG 3.0e38f
+// Capsule / segment (kinds 7 / 6) with its along-ray hit distance.  A capsule is convex (segment (+) ball), so the ray meets it in
+// ONE interval [Tin, Tout] = [min in_i, max out_i] over the non-empty intervals of its three convex parts: the finite cylinder
+// around a-b and the two end spheres.  Roots use the cancellation-free forms of the sphere code (rejection-form discriminant,
+// {w, C/w} root pair).  The bound is shortened by a few ulp and NOT flagged exact: the next sweep confirms the landing.
+__device__ __noinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px, float py, float pz, float vx, float vy, float vz) {
+    const float* q = P.p;
+    const float r = P.kind == 6 ? 0.1f : q[6];
+    const float pax = px - q[0], pay = py - q[1], paz = pz - q[2];
+    const float bax = q[3] - q[0], bay = q[4] - q[1], baz = q[5] - q[2];
+    const float baba = bax * bax + bay * bay + baz * baz;
+    const float inv = baba > 0.f ? 1.0f / baba : 0.f;  // a == b: a sphere (the reference divides by zero)
+    const float baoa = pax * bax + pay * bay + paz * baz, bard = vx * bax + vy * bay + vz * baz;
+    // signed distance (src/sdfs/sdfs.f90:628-648)
+    const float h = fminf(fmaxf(baoa * inv, 0.f), 1.f);
+    const float ex = pax - bax * h, ey = pay - bay * h, ez = paz - baz * h;
+    const float d = sqrtf(ex * ex + ey * ey + ez * ez) - r;
+    float tin = SMCRT_BIG, tout = -SMCRT_BIG;
+    // end spheres
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float ox = k ? px - q[3] : pax, oy = k ? py - q[4] : pay, oz = k ? pz - q[5] : paz;
+        const float b = ox * vx + oy * vy + oz * vz;
+        const float rx = ox - b * vx, ry = oy - b * vy, rz = oz - b * vz;
+        const float disc = r * r - (rx * rx + ry * ry + rz * rz);
+        if (disc >= 0.f) {
+            const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+            const float c = (len - r) * (len + r);
+            const float w = -(b + copysignf(sqrtf(disc), b));
+            const float t1 = w, t2 = (w != 0.f) ? c / w : w;
+            tin = fminf(tin, fminf(t1, t2));
+            tout = fmaxf(tout, fmaxf(t1, t2));
+        }
+    }
+    // finite cylinder: (infinite cylinder about the axis) intersected with the slab 0 <= y(t) = baoa + t bard <= baba
+    if (baba > 0.f) {
+        const float fo = baoa * inv, fv = bard * inv;
+        const float opx = pax - bax * fo, opy = pay - bay * fo, opz = paz - baz * fo;   // perpendicular parts
+        const float vpx = vx - bax * fv, vpy = vy - bay * fv, vpz = vz - baz * fv;
+        const float A = vpx * vpx + vpy * vpy + vpz * vpz;
+        const float B = opx * vpx + opy * vpy + opz * vpz;
+        const float cx = opy * vpz - opz * vpy, cy = opz * vpx - opx * vpz, cz = opx * vpy - opy * vpx;
+        const float disc = A * r * r - (cx * cx + cy * cy + cz * cz);   // A r^2 - |op x vp|^2  (Lagrange identity)
+        const float lenop = sqrtf(opx * opx + opy * opy + opz * opz);
+        float c1 = SMCRT_BIG, c2 = -SMCRT_BIG;
+        if (A > 1e-12f) {
+            if (disc >= 0.f) {
+                const float C = (lenop - r) * (lenop + r);
+                const float w = -(B + copysignf(sqrtf(disc), B));
+                const float t1 = w / A, t2 = (w != 0.f) ? C / w : t1;
+                c1 = fminf(t1, t2); c2 = fmaxf(t1, t2);
+            }
+        } else if (lenop <= r) { c1 = -SMCRT_BIG; c2 = SMCRT_BIG; }  // parallel to the axis, inside the tube
+        float s1 = -SMCRT_BIG, s2 = SMCRT_BIG;
+        if (fabsf(bard) > 1e-20f) {
+            const float ta = -baoa / bard, tb = (baba - baoa) / bard;
+            s1 = fminf(ta, tb); s2 = fmaxf(ta, tb);
+        } else if (baoa < 0.f || baoa > baba) { s1 = SMCRT_BIG; s2 = -SMCRT_BIG; }
+        const float lo = fmaxf(c1, s1), hi = fminf(c2, s2);
+        if (lo <= hi) { tin = fminf(tin, lo); tout = fmaxf(tout, hi); }
+    }
+    float t = SMCRT_BIG;
+    if (tout > 0.f && tin <= tout) t = tin > 0.f ? tin : tout;
+    // a few ulp short of the root: the landing is confirmed (and finished) by the ordinary sphere-trace step
+    if (t < SMCRT_BIG) t = t - (2e-6f * t + 4e-7f * (fabsf(px) + fabsf(py) + fabsf(pz)));
+    return make_float2(d, fmaxf(fabsf(d), t));  // a miss leaves t = SMCRT_BIG: this body does not limit the step
+}
+
 // Distance AND directional step bound of one primitive (FP32 transport path).
 // The reference advances by min_i |d_i| (sphere tracing, src/inttau2.f90:155-192): |d_i| is a lower bound of the distance
 // to surface i in ANY direction.  Along the packet's own ray a tighter bound exists for the primitives with a closed-form
@@ -190,7 +258,6 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
 // by min_i max(|d_i|, t_i) visits the same boundary points with the same optical depth (kappa is constant inside a
 // layer and deposits are linear along a straight ray), in one step instead of O(log(1/eps)/(1-cos)).
 // Kinds without a closed form keep b = |d| (plain sphere tracing).  *exact tells whether b is an exact hit distance.
-#define SMCRT_BIG 3.0e38f
 __device__ __noinline__ float eval_prim_generic(const PrimT<float>& P, float x, float y, float z) { return eval_prim<float>(P, x, y, z); }
 __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz,
                                                float& bound, bool& exact) {
@@ -251,6 +318,12 @@ __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, f
         bound = fmaxf(fabsf(d), (t > 0.f && t < SMCRT_BIG) ? t : SMCRT_BIG);
         exact = true;
         return d;
+    }
+    if (P.kind == 7 || P.kind == 6) {
+        const float2 r = eval_capsule_ray(P, px, py, pz, vx, vy, vz);
+        bound = r.y;
+        exact = false;
+        return r.x;
     }
     const float d = eval_prim_generic(P, x, y, z);  // out of line: keeps the hot loop small (I-cache)
     bound = fabsf(d);

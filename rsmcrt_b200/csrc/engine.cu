@@ -1178,6 +1178,27 @@ extern "C" int smcrt_probe_sdf(smcrt_ctx* c, int top_index, int64_t n, const dou
     if (want_n && down_f(bn, normal, 3 * (size_t)n)) return PROBE_FAIL();
     return 0;
 }
+extern "C" int smcrt_probe_ray(smcrt_ctx* c, int top_index, int64_t n, const double* pos, const double* dir, double* dist, double* bound,
+                               int32_t* exact) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (top_index < 1 || top_index > (int)c->tops.size() || !pos || !dir || !dist || !bound) return set_err("smcrt_probe_ray: invalid arguments");
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    KParams P;
+    fill_params(c, D, P);
+    DevBuf bp, bv, bd, bb, be;
+    if (up_f(bp, pos, 3 * (size_t)n) || up_f(bv, dir, 3 * (size_t)n) || bd.alloc(n * 4) || bb.alloc(n * 4) || be.alloc(n * 4)) return PROBE_FAIL();
+    CU(cudaFuncSetAttribute(probe_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->blob_bytes));
+    probe_ray_kernel<<<grid_for(n), 256, c->blob_bytes, D.stream>>>(P, top_index, n, bp.as<float>(), bv.as<float>(), bd.as<float>(),
+                                                                     bb.as<float>(), be.as<int>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    c->launches += 1;
+    if (down_f(bd, dist, n) || down_f(bb, bound, n)) return PROBE_FAIL();
+    if (exact) CU(cudaMemcpy(exact, be.p, 4 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
 extern "C" int smcrt_probe_fresnel(smcrt_ctx* c, int64_t n, const double* dir, const double* nrm, const double* n1, const double* n2,
                                    const double* xi, double* dir_out, double* refl_coeff, int32_t* rflag) {
     if (!c) return set_err("null ctx");

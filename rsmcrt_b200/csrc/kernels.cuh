@@ -1164,6 +1164,32 @@ __global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_inde
             for (int t = 0; t < P.n_top; ++t) dist[i * P.n_top + t] = eval_top_f(sc, t, x, y, z);
     }
 }
+// directional step bound of one top-level SDF: what sweep_one feeds into the step decision (distance, bound, exact flag)
+__global__ void probe_ray_kernel(const __grid_constant__ KParams P, int top_index, long long n, const float* pos, const float* dir,
+                                 float* dist, float* bound, int* exact) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(smem)[i] = reinterpret_cast<const int4*>(P.blob)[i];
+    __syncthreads();
+    SceneView sc;
+    sc.prims = reinterpret_cast<const DevPrim*>(smem);
+    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
+    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
+    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
+    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = top_index - 1;
+        float d, b;
+        bool ex;
+        const int mode = sc.tops[t].mode, first = sc.tops[t].first;
+        if (mode == 0) d = eval_prim_ray(sc.prims[first], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], b, ex);
+        else {
+            d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[t].count, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+            b = fabsf(d); ex = false;
+        }
+        dist[i] = d; bound[i] = b; exact[i] = ex ? 1 : 0;
+    }
+}
 __global__ void probe_fresnel_kernel(long long n, const float* dir, const float* nrm, const float* n1, const float* n2,
                                      const float* xi, float* dir_out, float* R, int* rflag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -49,6 +49,47 @@ def test_sdf_normals(engine, oracle):
         assert np.allclose(np.linalg.norm(n[stable], axis=1), 1.0, atol=1e-6)
 
 
+def test_directional_step_bounds(engine, oracle):
+    """The engine steps by a per-body bound along the ray instead of min|d| (sphere, box, plane: exact hit distance; capsule and
+    segment: a few ulp short of it).  For every body: bound >= |d|; the FP64 SDF of the oracle keeps its sign all along
+    [0, bound); and where the bound is a hit distance the end point lies on the surface."""
+    scene = zoo_scene(oracle)
+    engine.set_grid(20, 20, 20, 1.0, 1.0, 1.0)
+    engine.set_scene(scene)
+    osc = oracle.OracleScene(scene)
+    rng = np.random.default_rng(11)
+    n = 20000
+    pos = rng.uniform(-1.2, 1.2, size=(n, 3)).astype(np.float32).astype(np.float64)
+    dirs = random_dirs(rng, n).astype(np.float32).astype(np.float64)
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    with_ray = {1: "sphere", 2: "box", 6: "segment", 7: "capsule", 10: "plane"}
+    for top in range(1, 11):   # the ten bare primitives of the zoo
+        d, b, ex = engine.probe_ray(top, pos, dirs)
+        d0 = osc.sdf(top, pos)
+        assert np.all(b >= np.abs(d) * (1 - 1e-6) - 1e-7)
+        if top not in with_ray:
+            assert np.allclose(b, np.abs(d), rtol=1e-6, atol=1e-7) and not ex.any()
+            continue
+        finite = b < 1e29
+        assert finite.mean() > 0.005, with_ray[top]
+        # no surface is crossed before the bound: the sign of the FP64 distance is that of the start all along the move
+        for f in (0.25, 0.5, 0.75, 0.97):
+            s = np.where(finite, b * f, 5.0 * f)
+            dm = osc.sdf(top, pos + dirs * s[:, None])
+            clear = np.abs(d0) > 1e-5
+            assert np.all((np.sign(dm) == np.sign(d0)) | ~clear | (np.abs(dm) < 2e-5)), (with_ray[top], f)
+        # and where a hit distance is reported the end point is on the surface (capsule/segment: a few ulp short of it)
+        end = osc.sdf(top, pos[finite] + dirs[finite] * b[finite, None])
+        tol = 3e-6 * (1.0 + b[finite]) + (2e-5 if top in (6, 7) else 0.0)
+        hit = b[finite] > np.abs(d[finite]) * (1 + 1e-5)
+        assert np.all(np.abs(end[hit]) <= tol[hit] * 4), (with_ray[top], np.abs(end[hit]).max())
+        if top in (6, 7):
+            assert np.all(np.sign(end[hit]) == np.sign(d0[finite][hit])) or np.abs(end[hit]).max() < 5e-6  # short of the surface, same side
+            assert not ex.any()
+        else:
+            assert ex.all()
+
+
 def test_fresnel(engine, oracle):
     rng = np.random.default_rng(3)
     n = 300_000

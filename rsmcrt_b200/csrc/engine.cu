@@ -107,7 +107,7 @@ struct DeviceState {
     DevInstrD* progD = nullptr;
     float *jmean = nullptr, *absorb = nullptr, *emission = nullptr;
     unsigned long long* det_bins = nullptr;
-    unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last)
+    unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last) + 2 x 6 time stamps of the variant trial
     // sparse read-back scratch (smcrt_fetch): device pair list + cursor, pinned host mirror
     unsigned int* nz_idx = nullptr;
     float* nz_val = nullptr;
@@ -220,8 +220,8 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
             cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[4]) != cudaSuccess || cudaEventCreate(&D.tune_ev[5]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[6]) != cudaSuccess ||
-            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess ||
-            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1)) != cudaSuccess) {
+            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 12)) != cudaSuccess ||
+            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 12)) != cudaSuccess) {
             delete c;
             return set_err("smcrt_create: resource allocation failed on device %d: %s", D.dev, cudaGetErrorString(cudaGetLastError()));
         }
@@ -658,6 +658,19 @@ static int build_cull(smcrt_ctx* c) {
     std::vector<int> start((size_t)ncell + 1, 0), items;
     std::vector<float> far((size_t)ncell);
     items.reserve((size_t)ncell * 4);
+    // Evaluation order inside a cell: by code path (primitive kind / transform class), rarest class first, so that the lanes of a
+    // warp -- each walking the list of its own cell -- meet the same kind of primitive at the same loop index (a scene of one
+    // box and forty spheres: box first, then spheres).  The maxloc tie rule is kept by an explicit index compare in sweep_one.
+    std::vector<int> cls(nt), cls_count(1024, 0);
+    for (int j = 0; j < nt; ++j) {
+        const DevTop& T = c->tops[j];
+        cls[j] = T.mode ? 1023 : std::min(c->prims[T.first].kind * 4 + c->prims[T.first].xf, 1022);
+        ++cls_count[cls[j]];
+    }
+    auto by_class = [&](int a, int b) {
+        if (cls[a] != cls[b]) return cls_count[cls[a]] != cls_count[cls[b]] ? cls_count[cls[a]] < cls_count[cls[b]] : cls[a] < cls[b];
+        return a < b;
+    };
     for (long long cell = 0; cell < ncell; ++cell) {
         const float* d = dc.data() + cell * nt;
         double U = 1e300, M = -1e300;
@@ -672,6 +685,7 @@ static int build_cull(smcrt_ctx* c) {
             if (A || B) items.push_back(j);
             else f = std::min(f, std::fabs((double)d[j]) - h);
         }
+        std::sort(items.begin() + start[cell], items.end(), by_class);
         start[cell + 1] = (int)items.size();
         far[cell] = (float)f;
     }
@@ -832,14 +846,16 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     int n_launch = 1;
     const long long TUNE_MIN = 8ll << 20;
     if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
-        const long long slice = std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 22);
+        const long long slice = std::min<long long>(std::max<long long>(nphotons / 48, 1ll << 20), 1ll << 23);  // long enough that the tail of one slow packet (~5 ms) does not decide
         for (int k = 0; k < NVAR; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
             int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, P, D, VARIANTS[k].compact ? smem_compact : smem_plain, true);
             if (rc) return rc;
         }
+        CU(cudaMemsetAsync(D.counters + C_COUNT + 1, 0, sizeof(unsigned long long) * 12, D.stream));
         for (int k = 0; k < NVAR; ++k) {
             KParams Q = P;
             Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
+            Q.tstamp = D.counters + C_COUNT + 1 + 2 * k;
             CU(cudaEventRecord(D.tune_ev[k], D.stream));
             int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, Q, D, VARIANTS[k].compact ? smem_compact : smem_plain);
             if (rc) return rc;
@@ -901,11 +917,17 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             ms = std::max(ms, (double)t);
         }
         if (D.tuning >= 0) {  // the trial slices of run_on_device: keep the fastest kernel variant
-            float best = 0.f;
+            // Ranked by the time from kernel start until the packet pool ran EMPTY (device time stamps): the events around a
+            // slice also contain its tail -- the few longest histories finishing alone -- which is the same few milliseconds for
+            // every variant and every run length, and would decide a trial of short slices by luck.
+            unsigned long long ts[12] = {0};
+            CU(cudaMemcpy(ts, D.counters + C_COUNT + 1, sizeof ts, cudaMemcpyDeviceToHost));
+            double best = 0;
             int arg = 1;
             for (int k = 0; k < 6; ++k) {
-                float t = 0;
-                CU(cudaEventElapsedTime(&t, D.tune_ev[k], D.tune_ev[k + 1]));
+                float te = 0;
+                CU(cudaEventElapsedTime(&te, D.tune_ev[k], D.tune_ev[k + 1]));
+                const double t = ts[2 * k + 1] > ts[2 * k] ? 1e-6 * (double)(ts[2 * k + 1] - ts[2 * k]) : (double)te;
                 if (k == 0 || t < best) { best = t; arg = k; }
             }
             c->tuned_mb[(D.tuning >> 1) & 1][D.tuning & 1] = 1 + arg;

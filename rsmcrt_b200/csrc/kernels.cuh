@@ -56,6 +56,7 @@ struct KParams {
     int det_in_smem;
     unsigned long long* counters;  // [nscatt, sweeps, bounces, launched, retries, lost, n_top*sweeps(unused), det_hits]
     unsigned long long* next;      // work counter
+    unsigned long long* tstamp;    // variant trial only: [0] = %globaltimer at kernel start, [1] = when the last packet id is claimed
     long long nphotons;
     unsigned long long id_offset;
     uint32_t seed_lo, seed_hi;
@@ -109,6 +110,12 @@ __device__ __forceinline__ float u01_open0(uint32_t w) {                        
     return __fmul_rn(__fadd_rn(__uint2float_rn(w), 1.0f), 2.3283064365386963e-10f);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------ scene view
 struct SceneView {
     const DevPrim* prims;
@@ -130,7 +137,7 @@ __device__ __forceinline__ double eval_top_d(const KParams& P, const SceneView& 
 }
 // calcNormal (src/sdfs/sdf_base.f90:166-190): tetrahedral 4-tap gradient with h = 1e-6, in FP64 like the
 // reference (h is far below FP32 resolution); only executed at refractive-index-mismatch crossings.
-__device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
+__device__ __forceinline__ double3 surface_normal_fd(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
     const double h = 1e-6;
     const double f1 = eval_top_d(P, sc, t, X + h, Y - h, Z - h);
     const double f2 = eval_top_d(P, sc, t, X - h, Y - h, Z + h);
@@ -146,8 +153,8 @@ __device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView
 // which pumps packets into whispering-gallery orbits of (unions of) spheres ~100x faster than the reference does.  One
 // Newton step of the FP64 distance along the ray puts the packet on the surface to ~1e-12 before the normal is taken.
 // Returns the signed distance moved along the ray (|t| <= tmax).
-__device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
-                                          double uz, double tmax) {
+__device__ __forceinline__ double polish_hit_newton(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
+                                                    double uz, double tmax) {
     const double h = 1e-6;
     double moved = 0.0;
 #pragma unroll 1
@@ -163,6 +170,67 @@ __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc,
     return moved;
 }
 
+// Boundary hit geometry of a Fresnel event: the along-ray move that puts the packet ON surface `t` (polish_hit) and the outward
+// surface normal there (surface_normal), in one call.  Single untransformed / translated spheres and boxes -- every surface of
+// the sphere, slab, skin and jacques scenes -- have both in closed form: the ray/sphere root and o/|o|; the face plane of a box and
+// its axis.  The closed forms are what the Newton polish and the h = 1e-6 four-tap gradient converge to (difference O(h^2/r^2)
+// resp. rounding), at ~1/6 of the FP64 work: Fresnel events run with ~2 of 32 lanes active, so their instruction count is what
+// a refractive scene pays for them.  Everything else (and a box hit closer to an edge than the probe reach) takes the generic path.
+// Returned in registers (<= 3 doubles each: a larger struct would come back through the caller's stack frame), hence two calls:
+// polish_hit() = the along-ray move, surface_normal() = the normal at the moved point; same signatures as the generic pair.
+__device__ __forceinline__ bool closed_form_prim(const KParams& P, const SceneView& sc, int t, const DevPrimD*& Q) {
+    const DevTop T = sc.tops[t];
+    if (T.mode != 0) return false;
+    Q = P.primsD + T.first;
+    return Q->xf != XF_AFFINE && (Q->kind == 1 || Q->kind == 2);
+}
+__device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
+                                          double uz, double tmax) {
+    const DevPrimD* Q;
+    if (closed_form_prim(P, sc, t, Q)) {
+        double ox = X, oy = Y, oz = Z;
+        if (Q->xf == XF_TRANSLATE) { ox += Q->m[3]; oy += Q->m[7]; oz += Q->m[11]; }
+        if (Q->kind == 1) {  // sphere: t^2 + 2 b t + c = 0, the root next to the packet
+            const double R = Q->p[0];
+            const double len2 = ox * ox + oy * oy + oz * oz, b = ox * ux + oy * uy + oz * uz;
+            const double disc = R * R - (len2 - b * b);
+            if (!(b * b > 1e-6 * len2 && disc > 0.0)) return 0.0;  // |df/dt| = |b|/|o| <= 1e-3: same grazing guard as polish_hit
+            const double s = sqrt(disc);
+            return fmin(fmax(b > 0.0 ? s - b : -b - s, -tmax), tmax);
+        }
+        // box: planar while the two other face distances stay negative over the probe reach and the normal's taps
+        const double dx = fabs(ox) - Q->p[0], dy = fabs(oy) - Q->p[1], dz = fabs(oz) - Q->p[2];
+        const double reach = -(tmax + 4e-6);
+        const bool fx = dx >= dy && dx >= dz, fy = !fx && dy >= dz;
+        const double da = fx ? dx : (fy ? dy : dz), db = fx ? dy : dx, dc = (fx || fy) ? dz : dy;
+        if (db < reach && dc < reach) {
+            const double oa = fx ? ox : (fy ? oy : oz), ua = fx ? ux : (fy ? uy : uz);
+            const double g = oa < 0.0 ? -ua : ua;
+            return fabs(g) > 1e-3 ? fmin(fmax(-da / g, -tmax), tmax) : 0.0;
+        }
+    }
+    return polish_hit_newton(P, sc, t, X, Y, Z, ux, uy, uz, tmax);
+}
+__device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
+    const DevPrimD* Q;
+    if (closed_form_prim(P, sc, t, Q)) {
+        double ox = X, oy = Y, oz = Z;
+        if (Q->xf == XF_TRANSLATE) { ox += Q->m[3]; oy += Q->m[7]; oz += Q->m[11]; }
+        if (Q->kind == 1) {
+            const double il = rsqrt(ox * ox + oy * oy + oz * oz);
+            return make_double3(ox * il, oy * il, oz * il);
+        }
+        const double dx = fabs(ox) - Q->p[0], dy = fabs(oy) - Q->p[1], dz = fabs(oz) - Q->p[2];
+        const bool fx = dx >= dy && dx >= dz, fy = !fx && dy >= dz;
+        const double db = fx ? dy : dx, dc = (fx || fy) ? dz : dy;
+        if (db < -4e-6 && dc < -4e-6) {  // every tap of the four-tap gradient sees the same face
+            const double sg = (fx ? ox : (fy ? oy : oz)) < 0.0 ? -1.0 : 1.0;
+            return make_double3(fx ? sg : 0.0, fy ? sg : 0.0, (fx || fy) ? 0.0 : sg);
+        }
+    }
+    return surface_normal_fd(P, sc, t, X, Y, Z);
+}
+
 // Evaluate ALL top-level SDFs at (x,y,z): min|d|, min d, argmax of the negatives (the reference's
 // maxloc(ds, mask=ds<0): innermost surface wins, ties -> lowest index, none -> 0), value there, and the value of
 // SDF `layer` (1-based).   src/inttau2.f90:63-68,80-84,135-139,179-183,216-221,229-234
@@ -171,6 +239,7 @@ struct Sweep {
     int L;
     bool bexact;
 };
+template <bool ANY_ORDER>
 __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, Sweep& s) {
     float d, b;
     bool ex;
@@ -184,7 +253,9 @@ __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, f
     s.amin = fminf(s.amin, fabsf(d));
     s.smin = fminf(s.smin, d);
     if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
-    if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
+    // innermost negative; ties -> lowest index (maxloc).  Culled lists are sorted by code path, not by index: explicit compare there
+    if (ANY_ORDER) { if (d < 0.f && (d > s.dL || (d == s.dL && i + 1 < s.L))) { s.dL = d; s.L = i + 1; } }
+    else if (d < 0.f && d > s.dL) { s.dL = d; s.L = i + 1; }
 }
 // Culled sweep: only the SDFs that can matter for a point of this coarse cell are evaluated.  The host builds, per cell, the
 // list of SDFs that can attain min|d| or be the innermost negative one somewhere in the cell (interval bounds from the value at
@@ -199,14 +270,14 @@ __device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc
         if (cx >= 0 && cx < P.cull_n[0] && cy >= 0 && cy < P.cull_n[1] && cz >= 0 && cz < P.cull_n[2]) {
             const int c = cx + P.cull_n[0] * (cy + P.cull_n[1] * cz);
             const int i0 = __ldg(P.cull_start + c), i1 = __ldg(P.cull_start + c + 1);
-            for (int k = i0; k < i1; ++k) sweep_one(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, s);
+            for (int k = i0; k < i1; ++k) sweep_one<true>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, s);
             const float far = __ldg(P.cull_far + c);
             if (far < s.bmin) { s.bmin = fmaxf(far, s.amin); s.bexact = false; }  // never step past an unlisted surface
             return s;
         }
     }
     const int n = sc.n_top;
-    for (int i = 0; i < n; ++i) sweep_one(sc, i, x, y, z, ux, uy, uz, s);
+    for (int i = 0; i < n; ++i) sweep_one<false>(sc, i, x, y, z, ux, uy, uz, s);
     return s;
 }
 
@@ -223,16 +294,18 @@ __device__ __noinline__ Refl reflect_refract(float ux, float uy, float uz, doubl
     const double dx = ux, dy = uy, dz = uz;
     const double idn = dx * N.x + dy * N.y + dz * N.z;
     const double costt = fmin(fabs(idn), 1.0);
-    const double sintt = sqrt(1.0 - costt * costt);
     const double eta = n1 / n2;
-    const double sint2 = eta * sintt;
-    double R;
-    if (sint2 > 1.0) R = 1.0;            // total internal reflection
+    // sin(theta_t)^2 = eta^2 (1 - cos^2): the TIR test and cos(theta_t) need no sin(theta_i) (one FP64 sqrt instead of three)
+    const double sin2t = eta * eta * (1.0 - costt * costt);
+    double R, cost2 = 0.0;
+    if (sin2t > 1.0) R = 1.0;            // total internal reflection
     else if (costt == 1.0) R = 0.0;      // exactly normal incidence: transmitted (reference quirk Q10)
     else {
-        const double cost2 = sqrt(1.0 - sint2 * sint2);
-        const double a = (n1 * costt - n2 * cost2) / (n1 * costt + n2 * cost2);
-        const double b = (n1 * cost2 - n2 * costt) / (n1 * cost2 + n2 * costt);
+        cost2 = sqrt(1.0 - sin2t);
+        const double an = n1 * costt - n2 * cost2, ad = n1 * costt + n2 * cost2;
+        const double bn = n1 * cost2 - n2 * costt, bd = n1 * cost2 + n2 * costt;
+        const double inv = 1.0 / (ad * bd);  // one division for both amplitude ratios
+        const double a = an * bd * inv, b = bn * ad * inv;
         R = 0.5 * (a * a + b * b);
     }
     Refl o;
@@ -246,7 +319,8 @@ __device__ __noinline__ Refl reflect_refract(float ux, float uy, float uz, doubl
         double c1 = idn, sg = 1.0;
         if (c1 < 0.0) c1 = -c1;
         else sg = -1.0;
-        const double c2 = sqrt(1.0 - eta * eta * (1.0 - c1 * c1));
+        // cos(theta_t): the value of the coefficient branch unless |I.N| was clamped or the incidence is exactly normal
+        const double c2 = (cost2 > 0.0 && c1 <= 1.0) ? cost2 : sqrt(1.0 - eta * eta * (1.0 - c1 * c1));
         const double k = (eta * c1 - c2) * sg;
         o.x = (float)(eta * dx + k * N.x); o.y = (float)(eta * dy + k * N.y); o.z = (float)(eta * dz + k * N.z);
     }
@@ -669,6 +743,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     sc.n_top = P.n_top;
     sc.n_det = P.n_det;
     const int lane = threadIdx.x & 31;
+    if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) P.tstamp[0] = globaltimer_ns();
 
     // ---- packet state (scalars only: nothing here may be address-taken, or it lands in local memory)
     // Position in FP64, mirrored to FP32 for everything evaluated per sweep: with an FP32 position a step smaller than
@@ -764,7 +839,12 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             if (lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(need));
             base = __shfl_sync(need, base, leader);
             const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-            if (k >= (unsigned long long)P.nphotons) state = ST_DONE;
+            if (k >= (unsigned long long)P.nphotons) {
+                state = ST_DONE;
+                // exactly one claim in the grid draws the first id past the end: the pool is empty from here on, what follows is the
+                // tail of the last histories
+                if (P.tstamp && k == (unsigned long long)P.nphotons) P.tstamp[1] = globaltimer_ns();
+            }
             else {
                 pid = P.id_offset + k;
                 have_pid = true;

@@ -188,7 +188,7 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
 // ONE interval [Tin, Tout] = [min in_i, max out_i] over the non-empty intervals of its three convex parts: the finite cylinder
 // around a-b and the two end spheres.  Roots use the cancellation-free forms of the sphere code (rejection-form discriminant,
 // {w, C/w} root pair).  The bound is shortened by a few ulp and NOT flagged exact: the next sweep confirms the landing.
-__device__ __noinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px, float py, float pz, float vx, float vy, float vz) {
+__device__ __forceinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px, float py, float pz, float vx, float vy, float vz) {
     const float* q = P.p;
     const float r = P.kind == 6 ? 0.1f : q[6];
     const float pax = px - q[0], pay = py - q[1], paz = pz - q[2];
@@ -258,7 +258,43 @@ __device__ __noinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px,
 // by min_i max(|d_i|, t_i) visits the same boundary points with the same optical depth (kappa is constant inside a
 // layer and deposits are linear along a straight ray), in one step instead of O(log(1/eps)/(1-cos)).
 // Kinds without a closed form keep b = |d| (plain sphere tracing).  *exact tells whether b is an exact hit distance.
-__device__ __noinline__ float eval_prim_generic(const PrimT<float>& P, float x, float y, float z) { return eval_prim<float>(P, x, y, z); }
+//
+// sphere (local point p, unit direction v): t^2 + 2 b t + c = 0 with c = |p|^2 - r^2 = d (|p| + r)  (no cancellation near the surface)
+__device__ __forceinline__ float sphere_ray(float px, float py, float pz, float vx, float vy, float vz, float r, float& bound) {
+    const float len = sqrtf(px * px + py * py + pz * pz);
+    const float d = len - r;
+    const float b = px * vx + py * vy + pz * vz;
+    const float c = d * (len + r);
+    // discriminant b^2 - c = r^2 - |p - b v|^2 (v unit): the rejection form does not subtract two O(|p|^2) numbers,
+    // which matters for grazing rays (disc -> 0)
+    const float rx = px - b * vx, ry = py - b * vy, rz = pz - b * vz;
+    const float disc = r * r - (rx * rx + ry * ry + rz * rz);
+    float t = SMCRT_BIG;
+    if (disc >= 0.f) {
+        const float w = -(b + copysignf(sqrtf(disc), b));  // numerically stable root pair {w, c/w}
+        const float t1 = w, t2 = (w != 0.f) ? c / w : SMCRT_BIG;
+        const float lo = fminf(t1, t2), hi = fmaxf(t1, t2);
+        t = lo > 0.f ? lo : (hi > 0.f ? hi : SMCRT_BIG);
+    }
+    bound = fmaxf(fabsf(d), t);
+    return d;
+}
+// box with half sizes (q0,q1,q2): slab method in the local frame
+__device__ __forceinline__ float box_ray(float px, float py, float pz, float vx, float vy, float vz, float q0, float q1, float q2, float& bound) {
+    const float dx = fabsf(px) - q0, dy = fabsf(py) - q1, dz = fabsf(pz) - q2;
+    const float ox = fmaxf(dx, 0.f), oy = fmaxf(dy, 0.f), oz = fmaxf(dz, 0.f);
+    const float d = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(dx, fmaxf(dy, dz)), 0.f);
+    const float ix = 1.0f / vx, iy = 1.0f / vy, iz = 1.0f / vz;  // +-inf for an axis-parallel ray: handled by min/max
+    const float sx = copysignf(q0, vx), sy = copysignf(q1, vy), sz = copysignf(q2, vz);
+    const float n1 = (-sx - px) * ix, f1 = (sx - px) * ix;
+    const float n2 = (-sy - py) * iy, f2 = (sy - py) * iy;
+    const float n3 = (-sz - pz) * iz, f3 = (sz - pz) * iz;
+    const float tn = fmaxf(n1, fmaxf(n2, n3)), tf = fminf(f1, fminf(f2, f3));  // fmaxf/fminf drop a NaN (0*inf) operand
+    float t = SMCRT_BIG;
+    if (tf >= 0.f && tn <= tf) t = tn > 0.f ? tn : tf;
+    bound = fmaxf(fabsf(d), t);
+    return d;
+}
 __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz,
                                                float& bound, bool& exact) {
     float px, py, pz, vx = ux, vy = uy, vz = uz;
@@ -275,59 +311,24 @@ __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, f
         vz = P.m[8] * ux + P.m[9] * uy + P.m[10] * uz;
     }
     const float* q = P.p;
-    if (P.kind == 1) {  // sphere: t^2 + 2 b t + c = 0 with c = |p|^2 - r^2 = d (|p| + r)  (no cancellation near the surface)
-        const float len = sqrtf(px * px + py * py + pz * pz);
-        const float d = len - q[0];
-        const float b = px * vx + py * vy + pz * vz;
-        const float c = d * (len + q[0]);
-        // discriminant b^2 - c = r^2 - |p - b v|^2 (v unit): the rejection form does not subtract two O(|p|^2) numbers,
-        // which matters for grazing rays (disc -> 0)
-        const float rx = px - b * vx, ry = py - b * vy, rz = pz - b * vz;
-        const float disc = q[0] * q[0] - (rx * rx + ry * ry + rz * rz);
-        float t = SMCRT_BIG;
-        if (disc >= 0.f) {
-            const float w = -(b + copysignf(sqrtf(disc), b));  // numerically stable root pair {w, c/w}
-            const float t1 = w, t2 = (w != 0.f) ? c / w : SMCRT_BIG;
-            const float lo = fminf(t1, t2), hi = fmaxf(t1, t2);
-            t = lo > 0.f ? lo : (hi > 0.f ? hi : SMCRT_BIG);
-        }
-        bound = fmaxf(fabsf(d), t);
-        exact = true;
-        return d;
-    }
-    if (P.kind == 2) {  // box: slab method in the local frame
-        const float dx = fabsf(px) - q[0], dy = fabsf(py) - q[1], dz = fabsf(pz) - q[2];
-        const float ox = fmaxf(dx, 0.f), oy = fmaxf(dy, 0.f), oz = fmaxf(dz, 0.f);
-        const float d = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(dx, fmaxf(dy, dz)), 0.f);
-        const float ix = 1.0f / vx, iy = 1.0f / vy, iz = 1.0f / vz;  // +-inf for an axis-parallel ray: handled by min/max
-        const float sx = copysignf(q[0], vx), sy = copysignf(q[1], vy), sz = copysignf(q[2], vz);
-        const float n1 = (-sx - px) * ix, f1 = (sx - px) * ix;
-        const float n2 = (-sy - py) * iy, f2 = (sy - py) * iy;
-        const float n3 = (-sz - pz) * iz, f3 = (sz - pz) * iz;
-        const float tn = fmaxf(n1, fmaxf(n2, n3)), tf = fminf(f1, fminf(f2, f3));  // fmaxf/fminf drop a NaN (0*inf) operand
-        float t = SMCRT_BIG;
-        if (tf >= 0.f && tn <= tf) t = tn > 0.f ? tn : tf;
-        bound = fmaxf(fabsf(d), t);
-        exact = true;
-        return d;
-    }
+    exact = true;
+    if (P.kind == 1) return sphere_ray(px, py, pz, vx, vy, vz, q[0], bound);
+    if (P.kind == 2) return box_ray(px, py, pz, vx, vy, vz, q[0], q[1], q[2], bound);
     if (P.kind == 10) {  // plane
         const float d = px * q[0] + py * q[1] + pz * q[2];
         const float dn = vx * q[0] + vy * q[1] + vz * q[2];
         const float t = -d / dn;
         bound = fmaxf(fabsf(d), (t > 0.f && t < SMCRT_BIG) ? t : SMCRT_BIG);
-        exact = true;
         return d;
     }
+    exact = false;
     if (P.kind == 7 || P.kind == 6) {
         const float2 r = eval_capsule_ray(P, px, py, pz, vx, vy, vz);
         bound = r.y;
-        exact = false;
         return r.x;
     }
-    const float d = eval_prim_generic(P, x, y, z);  // out of line: keeps the hot loop small (I-cache)
+    const float d = eval_prim<float>(P, x, y, z);
     bound = fabsf(d);
-    exact = false;
     return d;
 }
 
@@ -407,6 +408,30 @@ __device__ __noinline__ T eval_program(const PRIM* prims, const INSTR* prog, int
         }
     }
     return ds[0];
+}
+
+// The sweep's compact view of a top-level SDF: 2 x float4 = {code, a, b, c}, {p0, p1, p2, -}.
+//   HOT_SPHERE / HOT_BOX: a single sphere / box primitive with identity or translation transform, evaluated inline from these
+//                         32 bytes: (a,b,c) = translation (local point = world point + t), p = radius / half sizes
+//   HOT_PROGRAM:          compound `model`: a = first instruction, b = instruction count (int bits)
+//   HOT_GENERAL:          any other single primitive: a = primitive index (int bits) -> eval_prim_ray_general
+enum : int { HOT_GENERAL = 0, HOT_SPHERE = 1, HOT_BOX = 2, HOT_PROGRAM = 3 };
+struct DevHot {
+    int32_t code;
+    union { float t[3]; int32_t idx[3]; };
+    float p[3];
+    float pad_;
+};
+static_assert(sizeof(DevHot) == 32, "DevHot must be 32 bytes");
+
+// Every single primitive the inline sphere / box code of the sweep does not cover: planes, capsules, transformed primitives, kinds
+// without a closed-form ray bound.  Out of line: ONE copy, and the sweep loop stays small (I-cache).
+// -> (distance, step bound, exact flag)
+__device__ __noinline__ float3 eval_prim_ray_general(const DevPrim* prim, float x, float y, float z, float ux, float uy, float uz) {
+    float b;
+    bool ex;
+    const float d = eval_prim_ray(*prim, x, y, z, ux, uy, uz, b, ex);
+    return make_float3(d, b, ex ? 1.f : 0.f);
 }
 
 }  // namespace smcrt_dev

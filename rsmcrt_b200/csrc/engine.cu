@@ -144,7 +144,7 @@ struct smcrt_ctx {
     long long det_total = 0;
     std::vector<double> opt_mus, opt_mua, opt_hgg, opt_n;
     bool scene_dirty = true;
-    int off_tops = 0, off_prog = 0, off_dets = 0, blob_bytes = 0;
+    int off_tops = 0, off_prog = 0, off_dets = 0, off_hot = 0, blob_bytes = 0;
     // source
     int src_kind = SMCRT_SRC_POINT, src_sub = 0, src_alt = 0;
     float sp[24] = {0};
@@ -711,8 +711,30 @@ static int upload_scene(smcrt_ctx* c) {
     const int b_prog = align16((int)(c->prog.size() * sizeof(DevInstr)));
     const int b_dets = align16((int)(c->dets.size() * sizeof(DevDet)));
     c->off_tops = b_prims; c->off_prog = b_prims + b_tops; c->off_dets = c->off_prog + b_prog;
-    c->blob_bytes = c->off_dets + b_dets;
+    c->off_hot = c->off_dets + b_dets;
+    c->blob_bytes = c->off_hot + align16((int)(c->tops.size() * sizeof(DevHot)));
     std::vector<unsigned char> blob(c->blob_bytes, 0);
+    {  // the sweep's 32-byte view of every top-level SDF (device_scene.cuh: DevHot)
+        DevHot* hot = reinterpret_cast<DevHot*>(blob.data() + c->off_hot);
+        for (size_t j = 0; j < c->tops.size(); ++j) {
+            const DevTop& T = c->tops[j];
+            DevHot h;
+            std::memset(&h, 0, sizeof h);
+            h.code = HOT_GENERAL;
+            h.idx[0] = T.first;
+            if (T.mode != 0) { h.code = HOT_PROGRAM; h.idx[1] = T.count; }
+            else {
+                const DevPrim& Q = c->prims[T.first];
+                if (Q.xf != XF_AFFINE && (Q.kind == 1 || Q.kind == 2)) {
+                    h.code = Q.kind == 1 ? HOT_SPHERE : HOT_BOX;
+                    h.t[0] = h.t[1] = h.t[2] = 0.f;
+                    if (Q.xf == XF_TRANSLATE) { h.t[0] = Q.m[3]; h.t[1] = Q.m[7]; h.t[2] = Q.m[11]; }
+                    h.p[0] = Q.p[0]; h.p[1] = Q.p[1]; h.p[2] = Q.p[2];
+                }
+            }
+            hot[j] = h;
+        }
+    }
     std::memcpy(blob.data(), c->prims.data(), c->prims.size() * sizeof(DevPrim));
     std::memcpy(blob.data() + c->off_tops, c->tops.data(), c->tops.size() * sizeof(DevTop));
     if (!c->prog.empty()) std::memcpy(blob.data() + c->off_prog, c->prog.data(), c->prog.size() * sizeof(DevInstr));
@@ -739,7 +761,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.blob = D.blob; P.blob_bytes = c->blob_bytes;
     P.n_prims = (int)c->prims.size(); P.n_top = (int)c->tops.size(); P.n_instr = (int)c->prog.size(); P.n_det = (int)c->dets.size();
     for (const DevDet& d : c->dets) if (d.kind == SMCRT_DET_CAMERA) P.has_camera = 1;
-    P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets;
+    P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot;
     P.primsD = D.primsD; P.progD = D.progD;
     P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;
     const int nn[3] = {c->nxg, c->nyg, c->nzg};

@@ -21,7 +21,7 @@ struct KParams {
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
-    int off_tops, off_prog, off_dets;  // byte offsets inside the blob (prims at 0)
+    int off_tops, off_prog, off_dets, off_hot;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
     const DevInstrD* progD;
     // culling grid: per coarse cell the candidate list of top-level SDFs; null = evaluate all
@@ -122,8 +122,20 @@ struct SceneView {
     const DevTop* tops;
     const DevInstr* prog;
     const DevDet* dets;
+    const float4* hot;  // 2 x float4 per top-level SDF: the sweep's view of it (see DevHot in device_scene.cuh)
     int n_top, n_det;
 };
+__device__ __forceinline__ SceneView make_view(const unsigned char* base, const KParams& P) {
+    SceneView sc;
+    sc.prims = reinterpret_cast<const DevPrim*>(base);
+    sc.tops = reinterpret_cast<const DevTop*>(base + P.off_tops);
+    sc.prog = reinterpret_cast<const DevInstr*>(base + P.off_prog);
+    sc.dets = reinterpret_cast<const DevDet*>(base + P.off_dets);
+    sc.hot = reinterpret_cast<const float4*>(base + P.off_hot);
+    sc.n_top = P.n_top;
+    sc.n_det = P.n_det;
+    return sc;
+}
 
 __device__ __forceinline__ float eval_top_f(const SceneView& sc, int t, float x, float y, float z) {
     const DevTop T = sc.tops[t];
@@ -200,9 +212,9 @@ __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc,
         }
         // box: planar while the two other face distances stay negative over the probe reach and the normal's taps
         const double dx = fabs(ox) - Q->p[0], dy = fabs(oy) - Q->p[1], dz = fabs(oz) - Q->p[2];
-        const double reach = -(tmax + 4e-6);
         const bool fx = dx >= dy && dx >= dz, fy = !fx && dy >= dz;
         const double da = fx ? dx : (fy ? dy : dz), db = fx ? dy : dx, dc = (fx || fy) ? dz : dy;
+        const double reach = fmin(da, 0.0) - (tmax + 4e-6);
         if (db < reach && dc < reach) {
             const double oa = fx ? ox : (fy ? oy : oz), ua = fx ? ux : (fy ? uy : uz);
             const double g = oa < 0.0 ? -ua : ua;
@@ -217,13 +229,21 @@ __device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView
         double ox = X, oy = Y, oz = Z;
         if (Q->xf == XF_TRANSLATE) { ox += Q->m[3]; oy += Q->m[7]; oz += Q->m[11]; }
         if (Q->kind == 1) {
+            // The reference's stencil k_i = (+,-,-), (-,-,+), (-,+,-), (+,+,+) is not central: with f = |o| - r,
+            //   sum_i k_i f(o + h k_i) = 4h [ n - (h/|o|) (ny nz, nx nz, nx ny) ] + O(h^3),  n = o/|o|,
+            // i.e. calcNormal is tilted by ~h/r against the true normal (1e-3 for the smallest spheres of sphere.toml).  The tilt
+            // is part of the reference's deterministic output, so it is reproduced (residual O((h/|o|)^2)).
             const double il = rsqrt(ox * ox + oy * oy + oz * oz);
-            return make_double3(ox * il, oy * il, oz * il);
+            const double a = ox * il, b = oy * il, c = oz * il, e = 1e-6 * il;
+            const double nx = a - e * b * c, ny = b - e * a * c, nz = c - e * a * b;
+            const double in = rsqrt(nx * nx + ny * ny + nz * nz);
+            return make_double3(nx * in, ny * in, nz * in);
         }
         const double dx = fabs(ox) - Q->p[0], dy = fabs(oy) - Q->p[1], dz = fabs(oz) - Q->p[2];
         const bool fx = dx >= dy && dx >= dz, fy = !fx && dy >= dz;
         const double db = fx ? dy : dx, dc = (fx || fy) ? dz : dy;
-        if (db < -4e-6 && dc < -4e-6) {  // every tap of the four-tap gradient sees the same face
+        const double lim = fmin(fx ? dx : (fy ? dy : dz), 0.0) - 4e-6;
+        if (db < lim && dc < lim) {  // every tap of the four-tap gradient sees the same face (outside: no edge region; inside: same argmax)
             const double sg = (fx ? ox : (fy ? oy : oz)) < 0.0 ? -1.0 : 1.0;
             return make_double3(fx ? sg : 0.0, fy ? sg : 0.0, (fx || fy) ? 0.0 : sg);
         }
@@ -239,17 +259,33 @@ struct Sweep {
     int L;
     bool bexact;
 };
+// distance, directional step bound and exact flag of top-level SDF i
+__device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float& d, float& b,
+                                        bool& ex) {
+    // two 16-byte shared loads bring everything a translated sphere or box needs (no tops[] -> prims[] indirection, no
+    // transform-class / kind ladder); every other kind goes through the out-of-line general evaluator
+    const float4 h0 = sc.hot[2 * i], h1 = sc.hot[2 * i + 1];
+    const int code = __float_as_int(h0.x);
+    if (code == HOT_SPHERE) {
+        d = sphere_ray(x + h0.y, y + h0.z, z + h0.w, ux, uy, uz, h1.x, b);
+        ex = true;
+    } else if (code == HOT_BOX) {
+        d = box_ray(x + h0.y, y + h0.z, z + h0.w, ux, uy, uz, h1.x, h1.y, h1.z, b);
+        ex = true;
+    } else if (code == HOT_PROGRAM) {  // compound `model`: plain sphere tracing
+        d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, __float_as_int(h0.y), __float_as_int(h0.z), x, y, z);
+        b = fabsf(d);
+        ex = false;
+    } else {
+        const float3 r = eval_prim_ray_general(sc.prims + __float_as_int(h0.y), x, y, z, ux, uy, uz);
+        d = r.x; b = r.y; ex = r.z != 0.f;
+    }
+}
 template <bool ANY_ORDER>
 __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, Sweep& s) {
     float d, b;
     bool ex;
-    const int mode = sc.tops[i].mode, first = sc.tops[i].first;
-    if (mode == 0) d = eval_prim_ray(sc.prims[first], x, y, z, ux, uy, uz, b, ex);
-    else {
-        d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[i].count, x, y, z);
-        b = fabsf(d);
-        ex = false;
-    }
+    top_ray(sc, i, x, y, z, ux, uy, uz, d, b, ex);
     s.amin = fminf(s.amin, fabsf(d));
     s.smin = fminf(s.smin, d);
     if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
@@ -732,16 +768,12 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     uint32_t* xbuf = xtot + 16;
     if (COMPACT && threadIdx.x < 16) xtot[threadIdx.x] = 0u;
     uint32_t xiter = 0;
+    // COMPACT only: xiter == XTAIL = compaction switched off for the rest of the run (CTA-uniform; no register of its own)
+    constexpr uint32_t XTAIL = 0xffffffffu;
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
     __syncthreads();
-    SceneView sc;
-    sc.prims = reinterpret_cast<const DevPrim*>(smem);
-    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
-    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
-    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
-    sc.n_top = P.n_top;
-    sc.n_det = P.n_det;
+    const SceneView sc = make_view(smem, P);
     const int lane = threadIdx.x & 31;
     if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) P.tstamp[0] = globaltimer_ns();
 
@@ -975,7 +1007,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                 }
             }
         }
-        if (!COMPACT && __all_sync(__activemask(), state == ST_DONE)) break;
+        if ((!COMPACT || xiter == XTAIL) && __all_sync(__activemask(), state == ST_DONE)) break;
         // cold or done lanes sit the sweep out
 
         // ===================================== sweep =====================================
@@ -1061,7 +1093,15 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                     // clear of the boundary and the next tauint2 loop does not start with the on-boundary nudge (2 sweeps saved
                     // per oblique crossing).  The extra probe length is paid for in optical depth like the rest of the probe.
                     dstep += dlast;
+                    // ... and beyond that up to half the distance at which the ray meets the next surface (closed-form bounds of this
+                    // very sweep): a probe that stays short of every surface cannot skip one, and a packet skimming a flat wall
+                    // closer than eps (a uniform source whose edge lies on the box side) would otherwise creep the wall's whole
+                    // length in 256-eps steps: 16 000 sweeps, alone, after every other packet has finished
+#ifdef SMCRT_OLD_CREEP
                     dlast = fminf(2.0f * dlast, 256.0f * eps);
+#else
+                    dlast = fminf(2.0f * dlast, fmaxf(256.0f * eps, 0.5f * S.bmin));
+#endif
                     qs = dstep;
                 } else if (S.L == 0) {  // :237-241
                     tflag = true;
@@ -1118,7 +1158,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         if (HASDET && (P.has_camera ? det : post == POST_FINISH)) DETECT();
         if (post == POST_FINISH) FINISH();
 
-        if (COMPACT) {
+        if (COMPACT && xiter != XTAIL) {
             // ============================ event compaction ============================
             // Counting sort of the CTA's packets by state through shared memory: afterwards the lanes of a warp are (mostly)
             // in the same state, so the divergent cold blocks / transitions run with full warps.  Order inside a bucket is
@@ -1137,6 +1177,10 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 #pragma unroll
             for (int k = 0; k < ST_DONE; ++k) base += (k < state) ? tot[k] : 0u;
             const bool all_done = tot[ST_DONE] == (uint32_t)blockDim.x;
+            // The pool is empty and half of the CTA has nothing left to do: this is the last exchange.  The survivors end up packed
+            // in the first warps and finish without the two barriers per iteration, each warp leaving on its own; the run's tail
+            // -- the longest history, alone -- advances at one warp's latency instead of the CTA's.
+            const bool go_tail = 2u * tot[ST_DONE] >= (uint32_t)blockDim.x;
             uint32_t* w = xbuf + (base + woff + (uint32_t)rank);
             const int B = blockDim.x;
             // packet state: 18 words + 3 (segment start, detector scenes) + 1 (weight, survival biasing).  qs is implied by the
@@ -1172,7 +1216,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             if (HASDET) { sx = __uint_as_float(r[18 * B]); sy = __uint_as_float(r[19 * B]); sz = __uint_as_float(r[20 * B]); }
             if (P.survival) weight = __uint_as_float(r[21 * B]);
             qs = (state == ST_BND_PROBE || state == ST_CROSS) ? dstep : 0.f;
-            ++xiter;
+            xiter = go_tail ? XTAIL : xiter + 1u;
         }
     }
 
@@ -1204,12 +1248,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 // One thread per (cell, top-level SDF): FP64 distance at the cell centre.  The host turns the matrix into candidate lists.
 __global__ void cull_eval_kernel(const __grid_constant__ KParams P, long long n_pairs, double lox, double loy, double loz, double dx, double dy,
                                  double dz, int nx, int ny, float* out) {
-    SceneView sc;
-    sc.prims = reinterpret_cast<const DevPrim*>(P.blob);
-    sc.tops = reinterpret_cast<const DevTop*>(P.blob + P.off_tops);
-    sc.prog = reinterpret_cast<const DevInstr*>(P.blob + P.off_prog);
-    sc.dets = reinterpret_cast<const DevDet*>(P.blob + P.off_dets);
-    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    const SceneView sc = make_view(P.blob, P);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % P.n_top);
         const long long c = i / P.n_top;
@@ -1226,12 +1265,7 @@ __global__ void probe_sdf_kernel(const __grid_constant__ KParams P, int top_inde
     for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x)
         reinterpret_cast<int4*>(smem)[i] = reinterpret_cast<const int4*>(P.blob)[i];
     __syncthreads();
-    SceneView sc;
-    sc.prims = reinterpret_cast<const DevPrim*>(smem);
-    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
-    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
-    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
-    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    const SceneView sc = make_view(smem, P);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
         if (top_index > 0) {
@@ -1251,22 +1285,11 @@ __global__ void probe_ray_kernel(const __grid_constant__ KParams P, int top_inde
     for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x)
         reinterpret_cast<int4*>(smem)[i] = reinterpret_cast<const int4*>(P.blob)[i];
     __syncthreads();
-    SceneView sc;
-    sc.prims = reinterpret_cast<const DevPrim*>(smem);
-    sc.tops = reinterpret_cast<const DevTop*>(smem + P.off_tops);
-    sc.prog = reinterpret_cast<const DevInstr*>(smem + P.off_prog);
-    sc.dets = reinterpret_cast<const DevDet*>(smem + P.off_dets);
-    sc.n_top = P.n_top; sc.n_det = P.n_det;
+    const SceneView sc = make_view(smem, P);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int t = top_index - 1;
         float d, b;
         bool ex;
-        const int mode = sc.tops[t].mode, first = sc.tops[t].first;
-        if (mode == 0) d = eval_prim_ray(sc.prims[first], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], b, ex);
-        else {
-            d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, first, sc.tops[t].count, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
-            b = fabsf(d); ex = false;
-        }
+        top_ray(sc, top_index - 1, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], d, b, ex);
         dist[i] = d; bound[i] = b; exact[i] = ex ? 1 : 0;
     }
 }

@@ -12,7 +12,7 @@ LIB_DIR = ROOT / "lib"
 LIB_PATH = LIB_DIR / "libsmcrt_gpu.so"
 
 SOURCES = [CSRC / "engine.cu", CSRC / "host" / "host.cpp"]
-HEADERS = [CSRC / "kernels.cuh", CSRC / "device_scene.cuh", CSRC / "host_math.hpp", CSRC / "host" / "toml_lite.hpp",
+HEADERS = [CSRC / "kernels.cuh", CSRC / "step_body.inc", CSRC / "step_macros.inc", CSRC / "step_macros_undef.inc", CSRC / "device_scene.cuh", CSRC / "host_math.hpp", CSRC / "host" / "toml_lite.hpp",
            ROOT.parent / "include" / "smcrt.h", ROOT.parent / "include" / "smcrt_host.h"]
 
 NVCC_FLAGS = [

@@ -96,7 +96,7 @@ struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t tune_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
+    cudaEvent_t tune_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
     const float* src_table = nullptr;  // set for the duration of smcrt_run_sources
     unsigned long long* src_tot = nullptr;
     unsigned long long src_id0 = 0;
@@ -107,7 +107,7 @@ struct DeviceState {
     DevInstrD* progD = nullptr;
     float *jmean = nullptr, *absorb = nullptr, *emission = nullptr;
     unsigned long long* det_bins = nullptr;
-    unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last) + 2 x 6 time stamps of the variant trial
+    unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last) + 2 x 8 time stamps of the variant trial
     // sparse read-back scratch (smcrt_fetch): device pair list + cursor, pinned host mirror
     unsigned int* nz_idx = nullptr;
     float* nz_val = nullptr;
@@ -219,9 +219,10 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
             cudaEventCreate(&D.tune_ev[0]) != cudaSuccess || cudaEventCreate(&D.tune_ev[1]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
             cudaEventCreate(&D.tune_ev[4]) != cudaSuccess || cudaEventCreate(&D.tune_ev[5]) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[6]) != cudaSuccess ||
-            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 12)) != cudaSuccess ||
-            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 12)) != cudaSuccess) {
+            cudaEventCreate(&D.tune_ev[6]) != cudaSuccess || cudaEventCreate(&D.tune_ev[7]) != cudaSuccess ||
+            cudaEventCreate(&D.tune_ev[8]) != cudaSuccess ||
+            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess ||
+            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess) {
             delete c;
             return set_err("smcrt_create: resource allocation failed on device %d: %s", D.dev, cudaGetErrorString(cudaGetLastError()));
         }
@@ -794,9 +795,8 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     return 0;
 }
 
-template <bool PL, bool HD, bool CP, int MB>
-static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
-    auto kern = trace_persistent<PL, HD, CP, MB>;
+typedef void (*trace_kernel_t)(const KParams);
+static int launch_kernel(trace_kernel_t kern, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
@@ -810,24 +810,24 @@ static int launch_trace(const KParams& P, DeviceState& D, int smem_bytes, bool d
     CU(cudaGetLastError());
     return 0;
 }
+// Kernel variants: scheduling (one packet per thread / + compaction behind CTA barriers / slot queues) x register
+// budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers)
+enum : int { SCHED_PLAIN = 0, SCHED_COMPACT = 1, SCHED_QUEUED = 2 };
+struct Variant { int sched; int mb; };
+constexpr int NVAR = 8;
+static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 3}, {SCHED_COMPACT, 4}, {SCHED_COMPACT, 2},
+                                       {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
 template <bool PL, bool HD>
-static int launch_mb(bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
-    if (compact) {
-        switch (mb) {
-            case 2: return launch_trace<PL, HD, true, 2>(P, D, smem_bytes, dry);
-            case 4: return launch_trace<PL, HD, true, 4>(P, D, smem_bytes, dry);
-            default: return launch_trace<PL, HD, true, 3>(P, D, smem_bytes, dry);
-        }
-    }
-    switch (mb) {
-        case 2: return launch_trace<PL, HD, false, 2>(P, D, smem_bytes, dry);
-        case 4: return launch_trace<PL, HD, false, 4>(P, D, smem_bytes, dry);
-        default: return launch_trace<PL, HD, false, 3>(P, D, smem_bytes, dry);
-    }
+static trace_kernel_t pick_kernel(int sched, int mb) {
+    if (sched == SCHED_QUEUED) return mb == 2 ? trace_queued<PL, HD, 2> : trace_queued<PL, HD, 3>;
+    if (sched == SCHED_COMPACT) return mb == 2 ? trace_persistent<PL, HD, true, 2> : (mb == 4 ? trace_persistent<PL, HD, true, 4> : trace_persistent<PL, HD, true, 3>);
+    return mb == 2 ? trace_persistent<PL, HD, false, 2> : (mb == 4 ? trace_persistent<PL, HD, false, 4> : trace_persistent<PL, HD, false, 3>);
 }
-static int launch_variant(bool pl, bool hd, bool compact, int mb, const KParams& P, DeviceState& D, int smem_bytes, bool dry = false) {
-    if (pl) return hd ? launch_mb<true, true>(compact, mb, P, D, smem_bytes, dry) : launch_mb<true, false>(compact, mb, P, D, smem_bytes, dry);
-    return hd ? launch_mb<false, true>(compact, mb, P, D, smem_bytes, dry) : launch_mb<false, false>(compact, mb, P, D, smem_bytes, dry);
+static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
+    const Variant v = VARIANTS[var];
+    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb) : pick_kernel<true, false>(v.sched, v.mb))
+                          : (hd ? pick_kernel<false, true>(v.sched, v.mb) : pick_kernel<false, false>(v.sched, v.mb));
+    return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
 }
 
 static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
@@ -846,40 +846,36 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     const int smem_plain = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
     P.xchg_off = (smem_plain + 15) & ~15;
-    const int smem_compact = P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK;
+    const int smem_bytes[3] = {smem_plain, P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK, P.xchg_off + queued_smem_bytes(SMCRT_BLOCK)};
     CU(cudaEventRecord(D.ev0, D.stream));
     const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
-    // Kernel variant: register budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers) x event
-    // compaction on/off.  Which one wins depends on the scene, so the first large run of a scene spends equal slices of its
-    // own packets on the candidates, bracketed by events; smcrt_wait reads the times and later runs use the fastest.  No
-    // packet is traced twice: streams depend on (seed, id) only, so a run split into id ranges is the same run.
-    struct Variant { bool compact; int mb; };
-    constexpr int NVAR = 6;
-    static const Variant VARIANTS[NVAR] = {{false, 2}, {false, 3}, {false, 4}, {true, 3}, {true, 4}, {true, 2}};
+    // Which variant wins depends on the scene, so the first large run of a scene spends equal slices of its own packets on the
+    // candidates; smcrt_wait reads their device time stamps and later runs use the fastest.  No packet is traced twice: streams
+    // depend on (seed, id) only, so a run split into id ranges is the same run.
     static const char* force_mb = getenv("SMCRT_MINBLOCKS_FORCE");
     static const char* force_var = getenv("SMCRT_VARIANT_FORCE");
-    const bool compact_ok = c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;
+    const bool compact_ok = c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;  // layer indices share a word in the packet record
     int forced = -1;
     if (force_var) forced = std::min(std::max(atoi(force_var), 0), NVAR - 1);
     else if (c->compact_allowed) forced = 3;  // SMCRT_COMPACT=1
     else if (force_mb) forced = std::min(std::max(atoi(force_mb), 2), 4) - 2;
     int var = forced >= 0 ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] - 1 : 1);
-    if (VARIANTS[var].compact && !compact_ok) var = 1;
+    if (VARIANTS[var].sched != SCHED_PLAIN && !compact_ok) var = 1;
     int n_launch = 1;
     const long long TUNE_MIN = 8ll << 20;
     if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
-        const long long slice = std::min<long long>(std::max<long long>(nphotons / 48, 1ll << 20), 1ll << 23);  // long enough that the tail of one slow packet (~5 ms) does not decide
+        const long long slice = std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 23);
         for (int k = 0; k < NVAR; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
-            int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, P, D, VARIANTS[k].compact ? smem_compact : smem_plain, true);
+            int rc = launch_variant(pl, hd, k, P, D, smem_bytes, true);
             if (rc) return rc;
         }
-        CU(cudaMemsetAsync(D.counters + C_COUNT + 1, 0, sizeof(unsigned long long) * 12, D.stream));
+        CU(cudaMemsetAsync(D.counters + C_COUNT + 1, 0, sizeof(unsigned long long) * 16, D.stream));
         for (int k = 0; k < NVAR; ++k) {
             KParams Q = P;
             Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
             Q.tstamp = D.counters + C_COUNT + 1 + 2 * k;
             CU(cudaEventRecord(D.tune_ev[k], D.stream));
-            int rc = launch_variant(pl, hd, VARIANTS[k].compact, VARIANTS[k].mb, Q, D, VARIANTS[k].compact ? smem_compact : smem_plain);
+            int rc = launch_variant(pl, hd, k, Q, D, smem_bytes);
             if (rc) return rc;
             CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
         }
@@ -888,7 +884,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
         P.nphotons -= NVAR * slice; P.id_offset += (unsigned long long)(NVAR * slice);
         n_launch = NVAR + 1;
     }
-    int rc = launch_variant(pl, hd, VARIANTS[var].compact, VARIANTS[var].mb, P, D, VARIANTS[var].compact ? smem_compact : smem_plain);
+    int rc = launch_variant(pl, hd, var, P, D, smem_bytes);
     if (rc) return rc;
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
@@ -942,11 +938,11 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             // Ranked by the time from kernel start until the packet pool ran EMPTY (device time stamps): the events around a
             // slice also contain its tail -- the few longest histories finishing alone -- which is the same few milliseconds for
             // every variant and every run length, and would decide a trial of short slices by luck.
-            unsigned long long ts[12] = {0};
+            unsigned long long ts[2 * NVAR] = {0};
             CU(cudaMemcpy(ts, D.counters + C_COUNT + 1, sizeof ts, cudaMemcpyDeviceToHost));
             double best = 0;
             int arg = 1;
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < NVAR; ++k) {
                 float te = 0;
                 CU(cudaEventElapsedTime(&te, D.tune_ev[k], D.tune_ev[k + 1]));
                 const double t = ts[2 * k + 1] > ts[2 * k] ? 1e-6 * (double)(ts[2 * k + 1] - ts[2 * k]) : (double)te;

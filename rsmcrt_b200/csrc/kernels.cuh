@@ -791,372 +791,11 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     // per-thread event counters (< 2^32 each); the rare ones (bounces, emit retries, lost) go straight to the global counters
     unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
 
-#ifdef SMCRT_DBG_WALK  // engine diagnostics (-DSMCRT_DBG_WALK): print every update_grids call of packet SMCRT_DEBUG_PID
-#define DBG_WALK(FX, FY, FZ, LEN)                                                                                     \
-    if (P.dbg_log && (long long)pid == P.dbg_pid)                                                                     \
-        printf("walk st=%d ph=%d layer=%d from %.9g %.9g %.9g dir %.9g %.9g %.9g len %.9g taurun %.9g tau %.9g\n", state, phase, \
-               layer, (double)(FX), (double)(FY), (double)(FZ), (double)ux, (double)uy, (double)uz, (double)(LEN), (double)taurun, (double)tau)
-#else
-#define DBG_WALK(FX, FY, FZ, LEN)
-#endif
-#define ADVANCE(S, VX, VY, VZ)                                                          \
-    do {                                                                                \
-        pxd += (double)(S) * (double)(VX); pyd += (double)(S) * (double)(VY); pzd += (double)(S) * (double)(VZ); \
-        px = (float)pxd; py = (float)pyd; pz = (float)pzd;                              \
-    } while (0)
-    // update_grids (inttau2.f90:367-465) for the straight piece (FX,FY,FZ) + t*(ux,uy,uz), t in [0, LEN]
-#define WALK(FX, FY, FZ, LEN)                                                                                         \
-    do {                                                                                                              \
-        DBG_WALK(FX, FY, FZ, LEN);                                                                                    \
-        if (PATHLEN) { if (walk_dda(P, FX, FY, FZ, ux, uy, uz, LEN, weight)) tflag = true; }                          \
-        else if (!in_grid(P, (FX) + ux * (LEN), (FY) + uy * (LEN), (FZ) + uz * (LEN))) tflag = true;                  \
-    } while (0)
-    // record_hit on the straight segment start -> pos for every detector (inttau2.f90:126-131,196-201,298-303,330-335)
-#define DETECT()                                                                                                      \
-    do {                                                                                                              \
-        for (int i_ = 0; i_ < sc.n_det; ++i_) {                                                                       \
-            const DevDet* D_ = &sc.dets[i_];                                                                          \
-            {                                                                                                         \
-                const int b_ = detector_bin(D_, sx, sy, sz, ux, uy, uz, px, py, pz);                                  \
-                if (b_ > 0) {                                                                                         \
-                    const float w_ = D_->kind == 4 ? 1.0f : weight;                                                   \
-                    const unsigned long long q_ = (unsigned long long)__float2ll_rn(w_ * DET_FIX);                    \
-                    const int slot_ = D_->offset + b_ - 1;                                                            \
-                    if (P.src_tot)                                                                                    \
-                        atomicAdd(&P.src_tot[((pid - P.src_id0) / (unsigned long long)P.per_src) * sc.n_det + i_], q_);       \
-                    else if (P.det_in_smem) { /* two native 32-bit ATOMS.ADD with carry (a 64-bit shared add is a CAS spin loop) */ \
-                        unsigned int* w32_ = reinterpret_cast<unsigned int*>(&sbins[slot_]);                          \
-                        const unsigned int ql_ = (unsigned int)q_, qh_ = (unsigned int)(q_ >> 32);                    \
-                        const unsigned int old_ = atomicAdd(w32_, ql_);                                               \
-                        const unsigned int up_ = qh_ + ((old_ + ql_ < old_) ? 1u : 0u);                               \
-                        if (up_) atomicAdd(w32_ + 1, up_);                                                            \
-                    }                                                                                                 \
-                    else atomicAdd(&P.det_bins[slot_], q_);                                                           \
-                    ++c_dethits;                                                                                      \
-                }                                                                                                     \
-            }                                                                                                         \
-        }                                                                                                             \
-        sx = px; sy = py; sz = pz;                                                                                    \
-    } while (0)
-    // packet finished: publish the optional per-packet record and ask for a new packet
-#define RETIRE(FATE, WHY)                                                                                             \
-    do {                                                                                                              \
-        if (P.out_fate) record_packet(P, pid, (FATE), (WHY), ev, steps, px, py, pz);                                  \
-        if (bounces) atomicAdd(&P.counters[C_BOUNCES], (unsigned long long)bounces);                                  \
-        if ((FATE) == FATE_LOST) atomicAdd(&P.counters[C_LOST], 1ull);                                                \
-        state = ST_EMIT; have_pid = false;                                                                            \
-    } while (0)
-    // end of tauint2 (inttau2.f90:354-362) + loop test of kernelsMod.f90:1958
-#define FINISH()                                                                                                      \
-    do {                                                                                                              \
-        if (fabsf(px) > P.gmax[0] || fabsf(py) > P.gmax[1] || fabsf(pz) > P.gmax[2]) tflag = true;                    \
-        if (tflag) RETIRE(FATE_ESCAPED, 0);                                                                           \
-        else state = ST_INTERACT;                                                                                     \
-    } while (0)
-#define NEXT_LOOP() /* `do while (taurun <= tau)` head, inttau2.f90:61 */                                             \
-    do {                                                                                                              \
-        qs = 0.f;                                                                                                     \
-        if (tflag || !(taurun <= tau)) { post = POST_FINISH; state = ST_HOLD; }                                       \
-        else { state = ST_MARCH; phase = 0; }                                                                         \
-    } while (0)
-
+#include "step_macros.inc"
     for (;;) {
-        int post = POST_NONE;
-        bool det = false;  // camera scenes only: a straight piece ended and is a detector segment of its own (see DETECT site below)
-        // ===================================== cold phase =====================================
-        if (state == ST_EMIT && !have_pid) {  // claim a packet id: one atomic per warp for all lanes that need one
-            const unsigned need = __ballot_sync(__activemask(), true);
-            unsigned long long base = 0;
-            const int leader = __ffs(need) - 1;
-            if (lane == leader) base = atomicAdd(P.next, (unsigned long long)__popc(need));
-            base = __shfl_sync(need, base, leader);
-            const unsigned long long k = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-            if (k >= (unsigned long long)P.nphotons) {
-                state = ST_DONE;
-                // exactly one claim in the grid draws the first id past the end: the pool is empty from here on, what follows is the
-                // tail of the last histories
-                if (P.tstamp && k == (unsigned long long)P.nphotons) P.tstamp[1] = globaltimer_ns();
-            }
-            else {
-                pid = P.id_offset + k;
-                have_pid = true;
-                ev = 0; bounces = 0; steps = 0; weight = 1.0f; tflag = false;
-            }
-        }
-        if (state >= ST_FRESNEL && state <= ST_EMIT) {
-            uint32_t w[4];  // the ONE Philox site: one block per event
-            philox4x32_10(ev++, (uint32_t)pid, (uint32_t)(pid >> 32), 0u, P.seed_lo, P.seed_hi, w);
-            if (state == ST_FRESNEL) {
-                // inttau2.f90:248-317: which surface is being crossed, its normal, Fresnel reflect/refract
-                const float ds_pos_new = eval_top_f(sc, new_layer - 1, px, py, pz);  // ds(new_layer)
-                const float ds_pos_cur = eval_top_f(sc, layer - 1, px, py, pz);      // ds(old_layer)
-                const float bx = (float)(pxd + (double)dstep * (double)ux), by = (float)(pyd + (double)dstep * (double)uy),
-                            bz = (float)(pzd + (double)dstep * (double)uz);          // the crossing probe point (same bits as the sweep's)
-                const float dnew_L = eval_top_f(sc, new_layer - 1, bx, by, bz);      // dsNew(new_layer)
-                const float dnew_cur = eval_top_f(sc, layer - 1, bx, by, bz);        // dsNew(old_layer)
-                int surf;
-                if (dnew_L < 0.f && ds_pos_new >= 0.f) surf = new_layer;
-                else if (dnew_cur >= 0.f && ds_pos_cur < 0.f) surf = layer;
-                else if (dnew_L < 0.f && dnew_cur < 0.f) surf = new_layer;
-                else if (ds_pos_cur >= 0.f && dnew_cur >= 0.f) surf = layer;
-                else surf = -1;  // reference: error stop (:276)
-                if (surf < 0) RETIRE(FATE_LOST, LOST_NO_SURFACE);
-                else {
-                    {
-                        const float e_ = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
-                        // reach: the FP32 ray/primitive root of a grazing ray is only good to ~1e-5 along the ray
-                        const double tp = polish_hit(P, sc, surf - 1, pxd, pyd, pzd, ux, uy, uz, 256.0 * (double)e_);
-                        pxd += tp * (double)ux; pyd += tp * (double)uy; pzd += tp * (double)uz;
-                        px = (float)pxd; py = (float)pyd; pz = (float)pzd;
-                    }
-                    const double3 N = surface_normal(P, sc, surf - 1, pxd, pyd, pzd);
-                    // FP32 guard: the SDF gradient points out of `surf`.  Leaving `layer` through its own surface
-                    // needs I.N > 0, entering `new_layer` through its surface needs I.N < 0.  The opposite sign means the packet
-                    // sits in the rounding skin of a surface it is moving AWAY from (impossible at the reference's FP64/1e-8
-                    // scales), i.e. its layer label lags behind where it is; a Fresnel event there would flip it back and forth
-                    // for ever.  It is moved on like an equal-index crossing: the probe's layer is adopted, direction unchanged.
-                    const double idn = (double)ux * N.x + (double)uy * N.y + (double)uz * N.z;
-                    const bool spurious = (surf == layer) ? (idn < 0.0) : (idn > 0.0);
-                    if (P.dbg_log && (long long)pid == P.dbg_pid && (int)ev <= P.dbg_cap) {
-                        float* g = P.dbg_log + 16 * (ev - 1);
-                        g[0] = (float)steps; g[1] = (float)layer; g[2] = (float)new_layer; g[3] = (float)surf; g[4] = (float)idn;
-                        g[5] = spurious ? 1.f : 0.f; g[6] = dstep; g[7] = px; g[8] = py; g[9] = pz; g[10] = ux; g[11] = uy; g[12] = uz;
-                        g[13] = dnew_L; g[14] = ds_pos_new; g[15] = ds_pos_cur;
-                    }
-                    // the straight segment that arrived here ends: detectors see it before the direction changes
-                    if (HASDET && !P.has_camera) DETECT();
-                    Refl R;
-                    if (spurious) { R.x = ux; R.y = uy; R.z = uz; R.R = 0.f; R.reflected = false; --ev; }
-                    else R = reflect_refract(ux, uy, uz, N, sc.tops[layer - 1].n, sc.tops[new_layer - 1].n, u01(w[0]));
-                    ux = R.x; uy = R.y; uz = R.z;
-                    if (!R.reflected) {  // transmitted :284-303
-                        layer = new_layer;
-                        WALK(px, py, pz, dstep);
-                        taurun += dstep * sc.tops[layer - 1].kappa;
-                        // The reference continues from the probe point, which was computed with the PRE-refraction direction
-                        // (quirk Q4: a 2e-8 lateral offset there).  With FP32-sized probes the same offset is 1e-6..1e-4 and
-                        // measurably changes the impact parameter inside curved bodies (packets refracted at grazing incidence
-                        // end up beyond the critical angle and are trapped); the packet continues along the refracted ray here.
-                        ADVANCE(dstep, ux, uy, uz);
-                        det = true;
-                        NEXT_LOOP();
-                    } else {  // reflected :304-317
-                        sx = px; sy = py; sz = pz;
-                        ++bounces;
-                        if (bounces > 1000) {
-                            if (P.out_dbg) {
-                                float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
-                                g[0] = -3.f; g[1] = (float)layer; g[2] = (float)new_layer; g[3] = (float)idn; g[4] = dstep; g[5] = ux;
-                                g[6] = uy; g[7] = uz; g[8] = R.R; g[9] = 1.f; g[10] = (float)surf; g[11] = (float)steps;
-                            }
-                            RETIRE(FATE_LOST, LOST_BOUNCES);
-                        }
-                        else NEXT_LOOP();
-                    }
-                }
-            } else if (state == ST_INTERACT) {  // kernelsMod.f90:1958-1974 (analog) / :2032-2066 (survival bias)
-                const float ran = u01(w[0]);
-                const float albedo = sc.tops[layer - 1].albedo;
-                bool alive = true;
-                if (!P.survival) {
-                    if (!(ran < albedo)) {
-                        // plain RED: absorption sites rarely coincide inside a warp, the match/shuffle aggregation costs more than it saves
-                        if (P.tally_mode & TALLY_ABSORB) atomicAdd(P.absorb + voxel_of(P, px, py, pz), 1.0f);
-                        RETIRE(FATE_ABSORBED, 0);
-                        alive = false;
-                    }
-                } else {
-                    const float wabs = weight * (1.0f - albedo);
-                    weight -= wabs;
-                    if (P.tally_mode & TALLY_ABSORB) atomicAdd(P.absorb + voxel_of(P, px, py, pz), wabs);
-                    if (weight < P.threshold) {
-                        if (ran < P.chance) weight = weight / P.chance;
-                        else {
-                            RETIRE(FATE_ROULETTE, 0);
-                            alive = false;
-                        }
-                    }
-                }
-                if (alive) {
-                    hg_scatter(ux, uy, uz, sc.tops[layer - 1].hgg, u01(w[1]), u01(w[2]));
-                    ++c_nscatt;
-                    if (P.out_nscatt) ++P.out_nscatt[pid - P.id_offset];  // smcrt_trace_packets only (zeroed by the host)
-                    tau = -SMCRT_LOG(u01_open0(w[3]));
-                    taurun = 0.f; qs = 0.f;
-                    sx = px; sy = py; sz = pz;
-                    state = ST_MARCH; phase = 0;
-                }
-            } else {  // ST_EMIT with a packet id: one emission attempt per iteration (rejections retry next iteration)
-                const Emitted em = emit_packet(P, u01(w[0]), u01(w[1]), u01(w[2]));
-                px = em.x; py = em.y; pz = em.z; ux = em.dx; uy = em.dy; uz = em.dz;
-                if (P.src_table) {
-                    const float* sp_ = P.src_table + 3ull * ((pid - P.src_id0) / (unsigned long long)P.per_src);
-                    px = sp_[0]; py = sp_[1]; pz = sp_[2];
-                }
-                if (em.ok && in_grid(P, px, py, pz)) {
-                    pxd = px; pyd = py; pzd = pz;
-                    if (P.tally_mode & TALLY_EMISSION) deposit(P.emission, voxel_of(P, px, py, pz), 1.0f);
-                    tau = -SMCRT_LOG(u01_open0(w[3]));
-                    taurun = 0.f; qs = 0.f;
-                    sx = px; sy = py; sz = pz;
-                    launch = true; layer = 0;
-                    state = ST_MARCH; phase = 0;
-                } else {  // emitter rejection / start voxel outside the grid (kernelsMod.f90:1939-1943, quirk Q6)
-                    atomicAdd(&P.counters[C_RETRIES], 1ull);
-                    if (ev > 100000u) RETIRE(FATE_LOST, LOST_EMIT);
-                }
-            }
-        }
-        if ((!COMPACT || xiter == XTAIL) && __all_sync(__activemask(), state == ST_DONE)) break;
-        // cold or done lanes sit the sweep out
-
-        // ===================================== sweep =====================================
-        if (state <= ST_CROSS) {
-            const float qx = (float)(pxd + (double)qs * (double)ux), qy = (float)(pyd + (double)qs * (double)uy),
-                        qz = (float)(pzd + (double)qs * (double)uz);
-            const Sweep S = sweep_all(P, sc, qx, qy, qz, ux, uy, uz);
-            ++c_sweeps;
-            const float eps = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
-            // ---------------- transition, part A (divergent, cheap): decide how far to move and what happens next
-            float adv = 0.f;     // signed distance to move along the direction
-            float wlen = -1.f;   // >= 0: update_grids over this length, from the position BEFORE the move, along +dir
-            float dtau = 0.f;    // optical depth spent by the move
-            float dl = 0.f;      // AFTER_TRACE: distance to the nearest surface at the segment end
-            if (++steps > P.max_steps) {
-                if (P.out_dbg) {
-                    float* g = P.out_dbg + 12 * (long long)(pid - P.id_offset);
-                    g[0] = (float)state; g[1] = (float)phase; g[2] = S.amin; g[3] = S.bmin; g[4] = dstep; g[5] = qs; g[6] = (float)layer;
-                    g[7] = (float)S.L; g[8] = taurun; g[9] = tau; g[10] = S.smin; g[11] = (float)bounces;
-                }
-                RETIRE(FATE_LOST, LOST_STEPS);
-            } else if (state == ST_MARCH) {
-                if (launch) {  // kernelsMod.f90:1949-1952 fused with the first sweep of tauint2 (same point)
-                    launch = false;
-                    layer = S.L;
-                }
-                if (layer == 0) {  // outside every SDF at launch: the reference would index array(0); engine guard
-                    RETIRE(FATE_LOST, LOST_NO_LAYER);
-                } else {
-                    if (phase != 0 && S.smin > 0.f) tflag = true;  // left all SDFs (:143-145, :188-191)
-                    if (phase == 0 && S.amin < eps) {               // sitting on a boundary (:73-84)
-                        dstep = S.amin + 2.0f * eps;
-                        qs = dstep;
-                        state = ST_BND_PROBE;
-                    } else if (taurun >= tau || tflag) {
-                        det = (phase == 2);  // end of the sphere-trace loop (:196-201); not at the loop top / after a nudge (:149)
-                        post = POST_FINISH;
-                    } else if (S.amin >= eps) {  // sphere-trace step (:155-176) with the directional bound
-                        phase = 2;
-                        const float kap = sc.tops[layer - 1].kappa;
-                        // exact hit distances are shortened by a rounding margin so that the packet lands just INSIDE its layer
-                        // (|d| < eps), like the reference's approach from inside; never below the plain sphere-trace step
-                        const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
-                        if (taurun + s * kap < tau) {
-                            adv = s; wlen = s; dtau = s * kap;
-                            if (S.bexact) post = POST_AFTER_TRACE;  // landed ON the nearest surface: no confirmation sweep needed
-                        } else {
-                            const float dd = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                            adv = dd; wlen = dd; dtau = tau - taurun;
-                            det = true;
-                            post = POST_FINISH;
-                        }
-                    } else {
-                        dl = S.amin;
-                        post = POST_AFTER_TRACE;
-                    }
-                }
-            } else if (state == ST_BND_PROBE && S.L == layer) {  // forward nudge :86-102
-                const float kap = sc.tops[layer - 1].kappa;
-                const float t = dstep * kap;
-                if (taurun + t < tau) {
-                    adv = dstep; wlen = dstep; dtau = t;
-                } else {  // Q1 of the reference: optical depth exhausted inside the nudge, position not advanced
-                    wlen = kap > 0.f ? (tau - taurun) / kap : 0.f;
-                    dtau = t;
-                }
-                det = true;
-                qs = 0.f;
-                state = ST_MARCH; phase = 1;  // re-evaluation at the nudged position (:134-146)
-            } else {  // ST_CROSS :220-337
-                // ... or a boundary probe that found another layer ahead.  The reference then steps BACK by the probe length
-                // (:104-121, charging optical depth and path for it: quirks Q2/Q3), re-approaches the surface and probes across
-                // it again: 3 more sweeps to learn what this sweep already says.  The probe is taken as the crossing probe it is;
-                // position and optical depth differ from the reference's sequence by O(eps).
-                if (state == ST_BND_PROBE) { state = ST_CROSS; dlast = eps; }
-                if (S.L != 0 && S.amin < eps) {
-                    // creep (:225-235).  The reference lengthens the probe by eps per iteration; a ray skimming a curved surface
-                    // stays within eps of it over ~sqrt(8 r eps), i.e. thousands of sweeps per grazing bounce.  The increment
-                    // doubles here (eps, 2 eps, ... capped at 256 eps): same exit condition, O(log) sweeps.
-                    // The reference creeps only while the probe is still in the old layer.  Here it creeps until the probe is at
-                    // least eps away from EVERY surface: (i) FP32 signs closer than ~2 ulp to a surface are rounding noise, so the
-                    // probe's layer classification is only trusted at a clear distance; (ii) the packet then lands
-                    // clear of the boundary and the next tauint2 loop does not start with the on-boundary nudge (2 sweeps saved
-                    // per oblique crossing).  The extra probe length is paid for in optical depth like the rest of the probe.
-                    dstep += dlast;
-                    // ... and beyond that up to half the distance at which the ray meets the next surface (closed-form bounds of this
-                    // very sweep): a probe that stays short of every surface cannot skip one, and a packet skimming a flat wall
-                    // closer than eps (a uniform source whose edge lies on the box side) would otherwise creep the wall's whole
-                    // length in 256-eps steps: 16 000 sweeps, alone, after every other packet has finished
-#ifdef SMCRT_OLD_CREEP
-                    dlast = fminf(2.0f * dlast, 256.0f * eps);
-#else
-                    dlast = fminf(2.0f * dlast, fmaxf(256.0f * eps, 0.5f * S.bmin));
-#endif
-                    qs = dstep;
-                } else if (S.L == 0) {  // :237-241
-                    tflag = true;
-                    post = POST_FINISH;
-                } else if (sc.tops[layer - 1].n != sc.tops[S.L - 1].n) {
-                    new_layer = S.L;
-                    state = ST_FRESNEL;
-                } else {  // :318-337
-                    layer = S.L;
-                    const float kap = sc.tops[layer - 1].kappa;
-                    const float tc = taurun + dstep * kap;  // optical depth after the crossing piece
-                    det = true;
-                    if (!(tc <= tau) || !(S.amin >= eps) || P.has_camera) {
-                        adv = dstep; wlen = dstep; dtau = dstep * kap;
-                        post = POST_NEXT_LOOP;
-                    } else {
-                        // The accepted probe IS the packet's next position (same bits) and the direction is kept, so this sweep
-                        // is also the one the reference takes at the top of its next loop (:63-68).  The crossing piece and the
-                        // first sphere-trace step of the new layer are taken as ONE straight move: one update_grids walk, one
-                        // detector segment, one sweep saved per equal-index crossing.
-                        qs = 0.f;
-                        state = ST_MARCH; phase = 2;
-                        const float s = S.bmin < SMCRT_BIG ? fmaxf(S.amin, S.bmin - (0.25f * eps + 2.4e-7f * S.bmin)) : S.amin;
-                        if (tc + s * kap < tau) {
-                            adv = dstep + s; wlen = adv; dtau = adv * kap;
-                            if (S.bexact) post = POST_AFTER_TRACE;
-                            else det = false;  // mid-trace: the detector segment stays open
-                        } else {
-                            const float dd = kap > 0.f ? (tau - tc) / kap : 0.f;
-                            adv = dstep + dd; wlen = adv; dtau = tau - taurun;
-                            post = POST_FINISH;
-                        }
-                    }
-                }
-            }
-            // ---------------- part B (common): update_grids, move, spend optical depth
-            if (wlen >= 0.f) WALK(px, py, pz, wlen);
-            if (adv != 0.f) ADVANCE(adv, ux, uy, uz);
-            taurun += dtau;
-            // ---------------- part C: what the move led to
-            if (post == POST_AFTER_TRACE) {  // straight piece ended on a surface: detectors, then probe across it (:196-221)
-                det = true;
-                if (taurun >= tau || tflag) post = POST_FINISH;
-                else { dstep = dl + 2.0f * eps; dlast = eps; qs = dstep; state = ST_CROSS; }
-            } else if (post == POST_NEXT_LOOP) {
-                NEXT_LOOP();
-            }
-        }
-        // record_hit (inttau2.f90:126-131,196-201,298-303,330-335).  The reference tests the detectors after every straight
-        // piece; pieces that share a direction form ONE straight segment and a plane crossing is found on the union exactly
-        // when it is found on one of the pieces (watertight end-point test), so the segment is kept open until the direction
-        // changes (Fresnel block) or tauint2 returns.  A camera counts segments (detector_base.f90:222-229): with one in the
-        // scene every piece is tested on its own, as in the reference.
-        if (HASDET && (P.has_camera ? det : post == POST_FINISH)) DETECT();
-        if (post == POST_FINISH) FINISH();
+#define STEP_EXIT_CHECK if ((!COMPACT || xiter == XTAIL) && __all_sync(__activemask(), state == ST_DONE)) break;
+#include "step_body.inc"
+#undef STEP_EXIT_CHECK
 
         if (COMPACT && xiter != XTAIL) {
             // ============================ event compaction ============================
@@ -1220,12 +859,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         }
     }
 
-#undef ADVANCE
-#undef WALK
-#undef DETECT
-#undef RETIRE
-#undef FINISH
-#undef NEXT_LOOP
+#include "step_macros_undef.inc"
 
     // ---- epilogue: flush CTA-private detector bins and per-thread counters
     __syncthreads();
@@ -1233,6 +867,213 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
     // every id below nphotons was claimed exactly once
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[C_LAUNCHED], (unsigned long long)P.nphotons);
+    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits};
+#pragma unroll
+    for (int c = 0; c < C_COUNT; ++c) {
+        unsigned long long v = cs[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&P.counters[c], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the queued kernel
+// Same per-packet state machine (step_body.inc), different scheduling.  trace_persistent keeps one packet per THREAD and, in its
+// COMPACT variants, re-sorts the CTA's packets by state every iteration behind two CTA-wide barriers: every warp then waits for
+// the slowest one (a warp of FP64 Fresnel events takes ~4x a warp of sweeps; ncu: 44 % of the samples of the 41-sphere scene sit
+// at that barrier).  Here packets live in SLOTS in shared memory (QSLOTS_PER_THREAD per thread) and four lock-free ring queues
+// hold the slot numbers by what the packet needs next:
+//     Q_SWEEP (march / boundary probe / crossing probe)   Q_FRESNEL   Q_INTERACT   Q_EMIT (free slot: claim the next packet id)
+// A WARP takes up to 32 slots from the fullest queue, loads them (6 x 16 bytes per lane), runs ONE step -- its lanes all start in
+// the same state, so the cold event code runs with full warps, FP64 Fresnel included -- stores them and appends each to the queue of
+// its new state.  No barrier anywhere in the loop; a warp never waits for another warp's step.  Results are those of the other
+// kernels bit for bit where the tallies are integers (streams depend on (seed, packet id, event index) only).
+enum : int { Q_SWEEP = 0, Q_FRESNEL, Q_INTERACT, Q_EMIT, Q_COUNT };
+constexpr int QSLOTS_PER_THREAD = 2;
+constexpr int QSLOT_WORDS = 24;  // 96 bytes: the 22 words of the compaction exchange, padded to 6 x 16 bytes
+struct QueueCtl {
+    unsigned int head[Q_COUNT];      // next entry to take
+    unsigned int reserved[Q_COUNT];  // producers: entries handed out for writing
+    unsigned int published[Q_COUNT]; // producers: entries written (published in reservation order)
+    unsigned int retired;            // slots whose EMIT step found the packet pool empty
+    unsigned int pad_[3];
+};
+__host__ __device__ constexpr int queued_smem_bytes(int threads) {
+    return (int)sizeof(QueueCtl) + Q_COUNT * threads * QSLOTS_PER_THREAD * 2 + threads * QSLOTS_PER_THREAD * QSLOT_WORDS * 4;
+}
+
+template <bool PATHLEN, bool HASDET, int MINBLOCKS>
+__global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) trace_queued(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    {  // stage the scene in shared memory (16-byte vector copies)
+        const int4* src = reinterpret_cast<const int4*>(P.blob);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    unsigned long long* sbins = reinterpret_cast<unsigned long long*>(smem + P.blob_bytes);
+    static_assert((SMCRT_BLOCK & (SMCRT_BLOCK - 1)) == 0 && SMCRT_BLOCK * QSLOTS_PER_THREAD <= 65536, "ring indices are masked 16-bit slot numbers");
+    const int M = blockDim.x * QSLOTS_PER_THREAD;  // packets in flight per CTA (power of two: the rings wrap with a mask)
+    QueueCtl* qc = reinterpret_cast<QueueCtl*>(smem + P.xchg_off);
+    unsigned short* ring = reinterpret_cast<unsigned short*>(qc + 1);                  // [Q_COUNT][M]
+    uint4* slots = reinterpret_cast<uint4*>(ring + Q_COUNT * M);                         // [M][6]
+    volatile QueueCtl* vq = qc;
+    if (threadIdx.x < Q_COUNT) {
+        const unsigned int n0 = threadIdx.x == Q_EMIT ? (unsigned int)M : 0u;          // every slot starts free
+        qc->head[threadIdx.x] = 0u; qc->reserved[threadIdx.x] = n0; qc->published[threadIdx.x] = n0;
+    }
+    if (threadIdx.x == 0) qc->retired = 0u;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        ring[Q_EMIT * M + i] = (unsigned short)i;
+        slots[6 * i + 3] = make_uint4(0u, 0u, (uint32_t)ST_EMIT, 0u);                    // w[14]: state EMIT, no packet id yet
+    }
+    if (HASDET && P.det_in_smem)
+        for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
+    __syncthreads();
+    const SceneView sc = make_view(smem, P);
+    const int lane = threadIdx.x & 31;
+    if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) P.tstamp[0] = globaltimer_ns();
+    const unsigned full = 0xffffffffu;
+    const unsigned int mask = (unsigned int)M - 1u;
+    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
+
+#include "step_macros.inc"
+    // The warp keeps the packets that stay in its current class in registers from one iteration to the next and only moves the
+    // others: packets that changed class are stored and queued, the lanes they leave (and the lanes of finished packets) are
+    // refilled from the queue of the class the warp works on.  A packet is loaded / stored once per class change, not once per
+    // step, and a class that only a few lanes of this warp are in (Fresnel events, typically) is never run on those few lanes:
+    // they are queued until a whole warp's worth has gathered somewhere in the CTA.
+    constexpr int KEEP_MIN = 12;  // fewer held packets than this in every class: queue them all and take a batch of the fullest class
+    double pxd = 0, pyd = 0, pzd = 0;
+    float px = 0, py = 0, pz = 0, ux = 0, uy = 0, uz = 1, sx = 0, sy = 0, sz = 0;
+    float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
+    int layer = 0, new_layer = 0, state = ST_DONE, bounces = 0, steps = 0;
+    bool tflag = false, launch = false, have_pid = false;
+    int phase = 0;
+    unsigned long long pid = 0;
+    uint32_t ev = 0;
+    unsigned int slot = 0;
+    bool has = false;  // this lane holds a packet (slot `slot`) in registers
+    for (;;) {
+        // ---- which class does the warp work on next
+        const int cls = !has ? -1 : (state <= ST_CROSS ? Q_SWEEP : (state == ST_FRESNEL ? Q_FRESNEL : (state == ST_INTERACT ? Q_INTERACT : Q_EMIT)));
+        int c = -1;
+        unsigned keep = 0u;
+        {
+            int bestn = 0;
+#pragma unroll
+            for (int q = 0; q < Q_COUNT; ++q) {
+                const unsigned m = __ballot_sync(full, cls == q);
+                const int k = __popc(m);
+                if (k > bestn) { bestn = k; c = q; keep = m; }
+            }
+            if (bestn < KEEP_MIN) { c = -1; keep = 0u; }
+        }
+        // ---- store and queue the packets that leave (all of them when no class is kept)
+        const bool push = has && cls != c;
+        const unsigned pm = __ballot_sync(full, push);
+        if (push) {
+            uint4* w = slots + 6 * slot;
+            w[0] = make_uint4((uint32_t)__double2loint(pxd), (uint32_t)__double2hiint(pxd), (uint32_t)__double2loint(pyd), (uint32_t)__double2hiint(pyd));
+            w[1] = make_uint4((uint32_t)__double2loint(pzd), (uint32_t)__double2hiint(pzd), __float_as_uint(ux), __float_as_uint(uy));
+            w[2] = make_uint4(__float_as_uint(uz), __float_as_uint(tau), __float_as_uint(taurun), __float_as_uint(dstep));
+            w[3] = make_uint4(__float_as_uint(dlast), (uint32_t)layer | ((uint32_t)new_layer << 16),
+                              (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u) | (ev << 11),
+                              (uint32_t)steps | ((uint32_t)bounces << 21));
+            w[4] = make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), __float_as_uint(sx), __float_as_uint(sy));
+            w[5] = make_uint4(__float_as_uint(sz), __float_as_uint(weight), 0u, 0u);
+            const unsigned grp = __match_any_sync(pm, cls);
+            const int cnt = __popc(grp), lead = __ffs(grp) - 1;
+            unsigned int start = 0;
+            if (lane == lead) start = atomicAdd(&qc->reserved[cls], (unsigned int)cnt);
+            start = __shfl_sync(grp, start, lead);
+            ring[cls * M + ((start + (unsigned int)__popc(grp & ((1u << lane) - 1u))) & mask)] = (unsigned short)slot;
+            __syncwarp(grp);
+            if (lane == lead) {
+                __threadfence_block();  // slot contents and ring entries before the publication
+                while (atomicCAS(&qc->published[cls], start, start + (unsigned int)cnt) != start) { }  // publish in reservation order
+            }
+            has = false;
+            state = ST_DONE;
+        }
+        __syncwarp(full);
+        // ---- (re)fill the free lanes from the queue of the kept class, or take a batch of the fullest queue
+        const unsigned freem = ~keep;
+        const int want = 32 - __popc(keep);
+        if (c < 0 || want >= 8) {  // a nearly full warp does not bother
+            unsigned int h0 = 0, n = 0;
+            int q = c;
+            if (lane == 0) {
+                if (q < 0) {  // fullest queue (head first: the difference can only over-estimate)
+                    unsigned int bestn = 0;
+#pragma unroll
+                    for (int k = 0; k < Q_COUNT; ++k) {
+                        const unsigned int h = vq->head[k];
+                        const unsigned int a = vq->published[k] - h;
+                        if (a > bestn) { bestn = a; q = k; }
+                    }
+                }
+                if (q >= 0) {
+                    h0 = vq->head[q];
+                    n = min(vq->published[q] - h0, (unsigned int)want);
+                    if (n && atomicCAS(&qc->head[q], h0, h0 + n) != h0) n = 0;  // another warp was faster: next iteration looks again
+                }
+            }
+            n = __shfl_sync(full, n, 0);
+            if (n) {
+                h0 = __shfl_sync(full, h0, 0);
+                q = __shfl_sync(full, q, 0);
+                c = q;
+                // The entries [h0, h0 + n) cannot be overwritten before they are read here: a ring holds M entries and at most
+                // M - n slots can be queued anywhere while this warp holds n of them.
+                const unsigned int rank = (unsigned int)__popc(freem & ((1u << lane) - 1u));
+                if (((freem >> lane) & 1u) && rank < n) {
+                    slot = ring[q * M + ((h0 + rank) & mask)];
+                    const uint4* r = slots + 6 * slot;
+                    const uint4 a = r[0], b = r[1], cc = r[2], d = r[3], e = r[4], f = r[5];
+                    pxd = __hiloint2double((int)a.y, (int)a.x); pyd = __hiloint2double((int)a.w, (int)a.z); pzd = __hiloint2double((int)b.y, (int)b.x);
+                    px = (float)pxd; py = (float)pyd; pz = (float)pzd;
+                    ux = __uint_as_float(b.z); uy = __uint_as_float(b.w); uz = __uint_as_float(cc.x);
+                    tau = __uint_as_float(cc.y); taurun = __uint_as_float(cc.z); dstep = __uint_as_float(cc.w);
+                    dlast = __uint_as_float(d.x);
+                    layer = (int)(d.y & 0xffffu); new_layer = (int)(d.y >> 16);
+                    const uint32_t fl = d.z;
+                    state = (int)(fl & 15u); phase = (int)((fl >> 4) & 15u); tflag = (fl & 256u) != 0; launch = (fl & 512u) != 0; have_pid = (fl & 1024u) != 0;
+                    ev = fl >> 11;
+                    steps = (int)(d.w & 0x1fffffu); bounces = (int)(d.w >> 21);
+                    pid = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+                    sx = __uint_as_float(e.z); sy = __uint_as_float(e.w); sz = __uint_as_float(f.x);
+                    weight = __uint_as_float(f.y);
+                    qs = (state == ST_BND_PROBE || state == ST_CROSS) ? dstep : 0.f;
+                    has = true;
+                }
+            }
+        }
+        if (!__any_sync(full, has)) {  // nothing held, nothing to take
+            if (vq->retired == (unsigned int)M) break;  // every slot has found the pool empty: the CTA is done
+            __nanosleep(40);
+            continue;
+        }
+
+        // ---- one step (lanes without a packet are in ST_DONE and sit it out)
+#define STEP_EXIT_CHECK
+#include "step_body.inc"
+#undef STEP_EXIT_CHECK
+
+        // ---- slots whose EMIT step found the pool empty are retired
+        const unsigned gone = __ballot_sync(full, has && state == ST_DONE);
+        if (gone) {
+            if (lane == 0) atomicAdd(&qc->retired, (unsigned int)__popc(gone));
+            if (state == ST_DONE) has = false;
+        }
+    }
+#include "step_macros_undef.inc"
+
+    // ---- epilogue: flush CTA-private detector bins and per-thread counters
+    __syncthreads();
+    if (HASDET && P.det_in_smem)
+        for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
+            if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[C_LAUNCHED], (unsigned long long)P.nphotons);
     unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits};
 #pragma unroll

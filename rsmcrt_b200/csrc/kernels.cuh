@@ -890,7 +890,16 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 // its new state.  No barrier anywhere in the loop; a warp never waits for another warp's step.  Results are those of the other
 // kernels bit for bit where the tallies are integers (streams depend on (seed, packet id, event index) only).
 enum : int { Q_SWEEP = 0, Q_FRESNEL, Q_INTERACT, Q_EMIT, Q_COUNT };
-constexpr int QSLOTS_PER_THREAD = 2;
+#ifndef SMCRT_Q_SLOTS
+#define SMCRT_Q_SLOTS 2
+#endif
+#ifndef SMCRT_Q_KEEP_MIN
+#define SMCRT_Q_KEEP_MIN 20
+#endif
+#ifndef SMCRT_Q_REFILL_MIN
+#define SMCRT_Q_REFILL_MIN 1
+#endif
+constexpr int QSLOTS_PER_THREAD = SMCRT_Q_SLOTS;  // packets in flight per thread
 constexpr int QSLOT_WORDS = 24;  // 96 bytes: the 22 words of the compaction exchange, padded to 6 x 16 bytes
 struct QueueCtl {
     unsigned int head[Q_COUNT];      // next entry to take
@@ -943,7 +952,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     // refilled from the queue of the class the warp works on.  A packet is loaded / stored once per class change, not once per
     // step, and a class that only a few lanes of this warp are in (Fresnel events, typically) is never run on those few lanes:
     // they are queued until a whole warp's worth has gathered somewhere in the CTA.
-    constexpr int KEEP_MIN = 12;  // fewer held packets than this in every class: queue them all and take a batch of the fullest class
+    constexpr int KEEP_MIN = SMCRT_Q_KEEP_MIN;  // fewer held packets than this in every class: queue them all and take a batch of the fullest class
     double pxd = 0, pyd = 0, pzd = 0;
     float px = 0, py = 0, pz = 0, ux = 0, uy = 0, uz = 1, sx = 0, sy = 0, sz = 0;
     float tau = 0.f, taurun = 0.f, dstep = 0.f, qs = 0.f, dlast = 0.f, weight = 1.f;
@@ -1000,7 +1009,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         // ---- (re)fill the free lanes from the queue of the kept class, or take a batch of the fullest queue
         const unsigned freem = ~keep;
         const int want = 32 - __popc(keep);
-        if (c < 0 || want >= 8) {  // a nearly full warp does not bother
+        if (c < 0 || want >= SMCRT_Q_REFILL_MIN) {  // a nearly full warp does not bother
             unsigned int h0 = 0, n = 0;
             int q = c;
             if (lane == 0) {

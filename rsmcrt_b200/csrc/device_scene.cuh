@@ -188,7 +188,7 @@ __device__ __forceinline__ T eval_prim(const PrimT<T>& P, T x, T y, T z) {
 // ONE interval [Tin, Tout] = [min in_i, max out_i] over the non-empty intervals of its three convex parts: the finite cylinder
 // around a-b and the two end spheres.  Roots use the cancellation-free forms of the sphere code (rejection-form discriminant,
 // {w, C/w} root pair).  The bound is shortened by a few ulp and NOT flagged exact: the next sweep confirms the landing.
-__device__ __forceinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px, float py, float pz, float vx, float vy, float vz) {
+__device__ __forceinline__ float2 eval_capsule_ray(const PrimT<float>& P, float px, float py, float pz, float vx, float vy, float vz, float need) {
     const float* q = P.p;
     const float r = P.kind == 6 ? 0.1f : q[6];
     const float pax = px - q[0], pay = py - q[1], paz = pz - q[2];
@@ -200,6 +200,7 @@ __device__ __forceinline__ float2 eval_capsule_ray(const PrimT<float>& P, float 
     const float h = fminf(fmaxf(baoa * inv, 0.f), 1.f);
     const float ex = pax - bax * h, ey = pay - bay * h, ez = paz - baz * h;
     const float d = sqrtf(ex * ex + ey * ey + ez * ez) - r;
+    if (fabsf(d) >= need) return make_float2(d, fabsf(d));  // farther than the packet will travel: the plain distance is bound enough
     float tin = SMCRT_BIG, tout = -SMCRT_BIG;
     // end spheres
 #pragma unroll
@@ -258,6 +259,10 @@ __device__ __forceinline__ float2 eval_capsule_ray(const PrimT<float>& P, float 
 // by min_i max(|d_i|, t_i) visits the same boundary points with the same optical depth (kappa is constant inside a
 // layer and deposits are linear along a straight ray), in one step instead of O(log(1/eps)/(1-cos)).
 // Kinds without a closed form keep b = |d| (plain sphere tracing).  *exact tells whether b is an exact hit distance.
+// `need` = how far the packet can travel before its optical depth runs out (+ margin; SMCRT_BIG when unknown).  A capsule whose
+// plain distance |d| is already beyond that cannot limit this move, so its (expensive) ray interval is not computed (bound = |d|):
+// in a scattering medium most sweeps end in an interaction long before any wall.  Spheres and boxes are cheap enough that the
+// test costs more than it saves (measured: -3..-7 % on every scene without capsules), so they ignore `need`.
 //
 // sphere (local point p, unit direction v): t^2 + 2 b t + c = 0 with c = |p|^2 - r^2 = d (|p| + r)  (no cancellation near the surface)
 __device__ __forceinline__ float sphere_ray(float px, float py, float pz, float vx, float vy, float vz, float r, float& bound) {
@@ -295,7 +300,7 @@ __device__ __forceinline__ float box_ray(float px, float py, float pz, float vx,
     bound = fmaxf(fabsf(d), t);
     return d;
 }
-__device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz,
+__device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, float y, float z, float ux, float uy, float uz, float need,
                                                float& bound, bool& exact) {
     float px, py, pz, vx = ux, vy = uy, vz = uz;
     if (P.xf == XF_IDENTITY) {
@@ -323,7 +328,7 @@ __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, f
     }
     exact = false;
     if (P.kind == 7 || P.kind == 6) {
-        const float2 r = eval_capsule_ray(P, px, py, pz, vx, vy, vz);
+        const float2 r = eval_capsule_ray(P, px, py, pz, vx, vy, vz, need);
         bound = r.y;
         return r.x;
     }
@@ -427,10 +432,10 @@ static_assert(sizeof(DevHot) == 32, "DevHot must be 32 bytes");
 // Every single primitive the inline sphere / box code of the sweep does not cover: planes, capsules, transformed primitives, kinds
 // without a closed-form ray bound.  Out of line: ONE copy, and the sweep loop stays small (I-cache).
 // -> (distance, step bound, exact flag)
-__device__ __noinline__ float3 eval_prim_ray_general(const DevPrim* prim, float x, float y, float z, float ux, float uy, float uz) {
+__device__ __noinline__ float3 eval_prim_ray_general(const DevPrim* prim, float x, float y, float z, float ux, float uy, float uz, float need) {
     float b;
     bool ex;
-    const float d = eval_prim_ray(*prim, x, y, z, ux, uy, uz, b, ex);
+    const float d = eval_prim_ray(*prim, x, y, z, ux, uy, uz, need, b, ex);
     return make_float3(d, b, ex ? 1.f : 0.f);
 }
 

@@ -762,6 +762,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.blob = D.blob; P.blob_bytes = c->blob_bytes;
     P.n_prims = (int)c->prims.size(); P.n_top = (int)c->tops.size(); P.n_instr = (int)c->prog.size(); P.n_det = (int)c->dets.size();
     for (const DevDet& d : c->dets) if (d.kind == SMCRT_DET_CAMERA) P.has_camera = 1;
+    for (const DevTop& T : c->tops) if (T.mode == 0 && (c->prims[T.first].kind == 6 || c->prims[T.first].kind == 7)) P.has_capsule = 1;
     P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot;
     P.primsD = D.primsD; P.progD = D.progD;
     P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;

@@ -20,6 +20,7 @@ struct KParams {
     const unsigned char* blob;
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
+    int has_capsule;  // some top-level SDF is a bare capsule / segment: the sweep is told how far the packet can travel (`need`)
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
     int off_tops, off_prog, off_dets, off_hot;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
@@ -260,8 +261,8 @@ struct Sweep {
     bool bexact;
 };
 // distance, directional step bound and exact flag of top-level SDF i
-__device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float& d, float& b,
-                                        bool& ex) {
+__device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float need, float& d,
+                                        float& b, bool& ex) {
     // two 16-byte shared loads bring everything a translated sphere or box needs (no tops[] -> prims[] indirection, no
     // transform-class / kind ladder); every other kind goes through the out-of-line general evaluator
     const float4 h0 = sc.hot[2 * i], h1 = sc.hot[2 * i + 1];
@@ -277,15 +278,15 @@ __device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, flo
         b = fabsf(d);
         ex = false;
     } else {
-        const float3 r = eval_prim_ray_general(sc.prims + __float_as_int(h0.y), x, y, z, ux, uy, uz);
+        const float3 r = eval_prim_ray_general(sc.prims + __float_as_int(h0.y), x, y, z, ux, uy, uz, need);
         d = r.x; b = r.y; ex = r.z != 0.f;
     }
 }
 template <bool ANY_ORDER>
-__device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, Sweep& s) {
+__device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float need, Sweep& s) {
     float d, b;
     bool ex;
-    top_ray(sc, i, x, y, z, ux, uy, uz, d, b, ex);
+    top_ray(sc, i, x, y, z, ux, uy, uz, need, d, b, ex);
     s.amin = fminf(s.amin, fabsf(d));
     s.smin = fminf(s.smin, d);
     if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
@@ -297,7 +298,7 @@ __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, f
 // list of SDFs that can attain min|d| or be the innermost negative one somewhere in the cell (interval bounds from the value at
 // the cell centre and 1-Lipschitz continuity), plus `far`: a lower bound of |d| of all the others.  The min / argmax over the
 // list equals the min / argmax over all SDFs for every point of the cell, and a step is additionally capped by `far`.
-__device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc, float x, float y, float z, float ux, float uy, float uz) {
+__device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc, float x, float y, float z, float ux, float uy, float uz, float need) {
     Sweep s;
     s.amin = SMCRT_BIG; s.smin = SMCRT_BIG; s.dL = -SMCRT_BIG; s.L = 0; s.bmin = SMCRT_BIG; s.bexact = false;
     if (P.cull_start) {
@@ -306,14 +307,14 @@ __device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc
         if (cx >= 0 && cx < P.cull_n[0] && cy >= 0 && cy < P.cull_n[1] && cz >= 0 && cz < P.cull_n[2]) {
             const int c = cx + P.cull_n[0] * (cy + P.cull_n[1] * cz);
             const int i0 = __ldg(P.cull_start + c), i1 = __ldg(P.cull_start + c + 1);
-            for (int k = i0; k < i1; ++k) sweep_one<true>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, s);
+            for (int k = i0; k < i1; ++k) sweep_one<true>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, need, s);
             const float far = __ldg(P.cull_far + c);
             if (far < s.bmin) { s.bmin = fmaxf(far, s.amin); s.bexact = false; }  // never step past an unlisted surface
             return s;
         }
     }
     const int n = sc.n_top;
-    for (int i = 0; i < n; ++i) sweep_one<false>(sc, i, x, y, z, ux, uy, uz, s);
+    for (int i = 0; i < n; ++i) sweep_one<false>(sc, i, x, y, z, ux, uy, uz, need, s);
     return s;
 }
 
@@ -1139,7 +1140,7 @@ __global__ void probe_ray_kernel(const __grid_constant__ KParams P, int top_inde
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float d, b;
         bool ex;
-        top_ray(sc, top_index - 1, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], d, b, ex);
+        top_ray(sc, top_index - 1, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], SMCRT_BIG, d, b, ex);
         dist[i] = d; bound[i] = b; exact[i] = ex ? 1 : 0;
     }
 }

@@ -69,7 +69,16 @@ int smcrt_write_detectors(const smcrt_config* cfg, const double* det_bins, const
 /* metadata text written into NRRD headers (the `dict` toml dump, kernelsMod.f90:2378-2382) */
 const char* smcrt_config_metadata(const smcrt_config* cfg);
 
-/* default_MCRT (src/kernelsMod.f90:29-83): setup -> run_MCRT -> finalise.  Writes out_dir/{jmean,absorb,emission,
+/* checkpoint (src/writer.f90:426-457): "tomlfile=<name>\nphotons_run=<n>\n" followed by the raw float32 jmean grid (x fastest).
+   smcrt_checkpoint_read is the reader of default_MCRT's load_checkpoint branch (src/kernelsMod.f90:52-72): toml_out receives the
+   input-deck name (NUL-terminated, truncated to toml_cap), jmean (may be NULL) the n_voxels floats. */
+int smcrt_checkpoint_write(const char* path, const char* toml_filename, int64_t nphotons_run, const float* jmean, int64_t n_voxels);
+int smcrt_checkpoint_read(const char* path, char* toml_out, int toml_cap, int64_t* nphotons_run, float* jmean, int64_t n_voxels);
+
+/* default_MCRT (src/kernelsMod.f90:29-83): setup -> run_MCRT -> finalise.
+   Checkpoints ([simulation] load_checkpoint / checkpoint_file / checkpoint_every_n): the run is cut at multiples of
+   checkpoint_every_n and the file rewritten there, but not more often than every ~2 s (one packet takes ~0.3 ns here, not ~10 us);
+   a resumed run continues the SAME job (same seed, packet ids from photons_run on -- the reference re-seeds with iseed*101).  Writes out_dir/{jmean,absorb,emission,
    detectors}/... with the reference's names.  tally_mode<0: default build semantics (absorb [+emission when
    render_source]); nphotons<=0: the toml's.  photons_per_s (may be NULL) receives what the reference prints
    (kernelsMod.f90:1897). */

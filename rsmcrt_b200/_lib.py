@@ -94,6 +94,8 @@ PROTOTYPES = {
     "smcrt_normalise_fluence": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64]),
     "smcrt_write_nrrd_f32": (C.c_int, [C.c_char_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     "smcrt_write_detectors": (C.c_int, [C.c_void_p, c_double_p, C.c_char_p]),
+    "smcrt_checkpoint_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, c_float_p, C.c_int64]),
+    "smcrt_checkpoint_read": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), c_float_p, C.c_int64]),
     "smcrt_config_metadata": (C.c_char_p, [C.c_void_p]),
     "smcrt_default_mcrt": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, c_double_p,
                                      C.POINTER(Counters)]),

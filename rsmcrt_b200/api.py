@@ -407,6 +407,22 @@ def write_nrrd(path, array, meta=""):
                                            meta.encode() if meta else None))
 
 
+def checkpoint_write(path, toml_filename, nphotons_run, jmean):
+    """writer.f90:426-457: two header lines + the raw float32 jmean grid (x fastest)."""
+    flat = np.ascontiguousarray(np.asarray(jmean, np.float32).reshape(-1, order="F"))
+    check(_lib.load().smcrt_checkpoint_write(str(path).encode(), str(toml_filename).encode(), int(nphotons_run), _p(flat, C.c_float), flat.size))
+
+
+def checkpoint_read(path, n_voxels=0):
+    """-> (toml_filename, nphotons_run, jmean flat float32 or None)   (the load_checkpoint branch, kernelsMod.f90:52-72)"""
+    name = C.create_string_buffer(1024)
+    run = C.c_int64()
+    jm = np.zeros(int(n_voxels), np.float32) if n_voxels else None
+    check(_lib.load().smcrt_checkpoint_read(str(path).encode(), name, 1024, C.byref(run), None if jm is None else _p(jm, C.c_float),
+                                            int(n_voxels)))
+    return name.value.decode(), int(run.value), jm
+
+
 def default_MCRT(input_file, res_dir=None, out_dir="data", n_gpus=1, tally_mode=-1, survival_bias=False, nphotons=-1):
     """`program mcpolar` -> default_MCRT (app/main.f90:24, src/kernelsMod.f90:29-83). Returns (photons/s, counters)."""
     pps = C.c_double()

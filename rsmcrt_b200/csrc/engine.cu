@@ -144,7 +144,7 @@ struct smcrt_ctx {
     long long det_total = 0;
     std::vector<double> opt_mus, opt_mua, opt_hgg, opt_n;
     bool scene_dirty = true;
-    int off_tops = 0, off_prog = 0, off_dets = 0, off_hot = 0, blob_bytes = 0;
+    int off_tops = 0, off_prog = 0, off_dets = 0, off_hot = 0, off_detp = 0, blob_bytes = 0;
     // source
     int src_kind = SMCRT_SRC_POINT, src_sub = 0, src_alt = 0;
     float sp[24] = {0};
@@ -713,8 +713,14 @@ static int upload_scene(smcrt_ctx* c) {
     const int b_dets = align16((int)(c->dets.size() * sizeof(DevDet)));
     c->off_tops = b_prims; c->off_prog = b_prims + b_tops; c->off_dets = c->off_prog + b_prog;
     c->off_hot = c->off_dets + b_dets;
-    c->blob_bytes = c->off_hot + align16((int)(c->tops.size() * sizeof(DevHot)));
+    c->off_detp = c->off_hot + align16((int)(c->tops.size() * sizeof(DevHot)));
+    c->blob_bytes = c->off_detp + (int)(c->dets.size() * 16);
     std::vector<unsigned char> blob(c->blob_bytes, 0);
+    for (size_t j = 0; j < c->dets.size(); ++j) {  // detector planes (n, n.p0): the crossing pre-test of the DETECT site
+        const DevDet& D = c->dets[j];
+        const float pl[4] = {D.dir[0], D.dir[1], D.dir[2], D.q[13]};
+        std::memcpy(blob.data() + c->off_detp + 16 * j, pl, 16);
+    }
     {  // the sweep's 32-byte view of every top-level SDF (device_scene.cuh: DevHot)
         DevHot* hot = reinterpret_cast<DevHot*>(blob.data() + c->off_hot);
         for (size_t j = 0; j < c->tops.size(); ++j) {
@@ -763,7 +769,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.n_prims = (int)c->prims.size(); P.n_top = (int)c->tops.size(); P.n_instr = (int)c->prog.size(); P.n_det = (int)c->dets.size();
     for (const DevDet& d : c->dets) if (d.kind == SMCRT_DET_CAMERA) P.has_camera = 1;
     for (const DevTop& T : c->tops) if (T.mode == 0 && (c->prims[T.first].kind == 6 || c->prims[T.first].kind == 7)) P.has_capsule = 1;
-    P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot;
+    P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot; P.off_detp = c->off_detp;
     P.primsD = D.primsD; P.progD = D.progD;
     P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;
     const int nn[3] = {c->nxg, c->nyg, c->nzg};

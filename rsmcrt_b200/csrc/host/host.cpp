@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -228,7 +229,7 @@ struct Config {
     // [simulation] (parse.f90:170-184)
     int64_t iseed = 123456789;
     bool tev = false, absorb = false, loadckpt = false;
-    std::string ckptfile = "check.ckpt";
+    std::string ckptfile = "check.ckpt", ckpt_deck;  // ckpt_deck: the input deck's name as written into checkpoints
     int64_t ckptfreq = 1000000;
     // derived
     std::string res_dir;
@@ -979,12 +980,63 @@ int smcrt_write_detectors(const smcrt_config* cfg, const double* det_bins, const
     return 0;
 }
 
+// checkpoint, src/writer.f90:426-457 (two formatted lines, then the stream-appended jmean)
+int smcrt_checkpoint_write(const char* path, const char* toml_filename, int64_t nphotons_run, const float* jmean, int64_t n_voxels) {
+    if (!path || !toml_filename || !jmean || n_voxels < 0) return host_fail("smcrt_checkpoint_write: invalid arguments");
+    const std::string tmp = std::string(path) + ".tmp";  // written aside and renamed: a kill mid-write leaves the previous checkpoint
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return host_fail(std::string("cannot write checkpoint ") + path);
+    std::fprintf(f, "tomlfile=%s\nphotons_run=%lld\n", toml_filename, (long long)nphotons_run);
+    const size_t w = std::fwrite(jmean, sizeof(float), (size_t)n_voxels, f);
+    const bool ok = w == (size_t)n_voxels && std::fclose(f) == 0;
+    if (!ok || std::rename(tmp.c_str(), path) != 0) return host_fail(std::string("cannot write checkpoint ") + path);
+    return 0;
+}
+int smcrt_checkpoint_read(const char* path, char* toml_out, int toml_cap, int64_t* nphotons_run, float* jmean, int64_t n_voxels) {
+    if (!path) return host_fail("smcrt_checkpoint_read: invalid arguments");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return host_fail(std::string("cannot open checkpoint ") + path);
+    auto line = [&](std::string& out) {
+        out.clear();
+        int ch;
+        while ((ch = std::fgetc(f)) != EOF && ch != '\n') out.push_back((char)ch);
+        return ch != EOF;
+    };
+    std::string l1, l2;
+    if (!line(l1) || !line(l2) || l1.find('=') == std::string::npos || l2.find('=') == std::string::npos) {
+        std::fclose(f);
+        return host_fail(std::string("malformed checkpoint header in ") + path);
+    }
+    const std::string name = l1.substr(l1.find('=') + 1);  // kernelsMod.f90:55-57: everything after the first '='
+    if (toml_out && toml_cap > 0) std::snprintf(toml_out, (size_t)toml_cap, "%s", name.c_str());
+    if (nphotons_run) *nphotons_run = std::atoll(l2.substr(l2.find('=') + 1).c_str());
+    int rc = 0;
+    if (jmean && std::fread(jmean, sizeof(float), (size_t)n_voxels, f) != (size_t)n_voxels)
+        rc = host_fail(std::string("checkpoint ") + path + " holds fewer voxels than the grid of its input deck");
+    std::fclose(f);
+    return rc;
+}
+
 // default_MCRT, src/kernelsMod.f90:29-83
 int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* out_dir, int n_gpus, int tally_mode,
                        int survival_bias, int64_t nphotons, double* photons_per_s, smcrt_counters* counters) {
     smcrt_config* cfg = nullptr;
     int rc = smcrt_config_load(toml_path, res_dir, &cfg);
     if (rc) return rc;
+    // load_checkpoint (kernelsMod.f90:52-72): the checkpoint names the input deck it belongs to; that deck is the one that runs
+    int64_t photons_done = 0;
+    std::string ckpt_in;
+    if (cfg->c.loadckpt) {
+        ckpt_in = cfg->c.ckptfile;
+        char name[1024];
+        if ((rc = smcrt_checkpoint_read(ckpt_in.c_str(), name, (int)sizeof name, &photons_done, nullptr, 0))) { smcrt_config_free(cfg); return rc; }
+        smcrt_config_free(cfg);
+        cfg = nullptr;
+        if ((rc = smcrt_config_load(name, res_dir, &cfg))) return rc;
+        toml_path = nullptr;  // (the deck's own name is used for later checkpoints)
+        cfg->c.ckpt_deck = name;
+    } else
+        cfg->c.ckpt_deck = toml_path;
     Config& c = cfg->c;
     if (nphotons > 0) c.nphotons = nphotons;
     smcrt_ctx* ctx = nullptr;
@@ -997,16 +1049,44 @@ int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* o
     };
     if ((rc = smcrt_config_apply(cfg, ctx))) return cleanup(rc);
     if (tally_mode < 0) tally_mode = SMCRT_TALLY_ABSORB | (c.render_source ? SMCRT_TALLY_EMISSION : 0);
-    auto t0 = std::chrono::steady_clock::now();
-    if ((rc = smcrt_run(ctx, c.nphotons, (uint64_t)c.iseed, 0, tally_mode, survival_bias, -1.0, -1.0))) return cleanup(rc);
-    auto t1 = std::chrono::steady_clock::now();
-    const double secs = std::chrono::duration<double>(t1 - t0).count();
-    if (photons_per_s) *photons_per_s = (double)c.nphotons / secs;  // print*,"Photons/s: ", kernelsMod.f90:1897
     const size_t nv = (size_t)c.nxg * c.nyg * c.nzg;
     std::vector<float> jmean(nv, 0.f), absorb(nv, 0.f), emission(nv, 0.f);
+    if (!ckpt_in.empty()) {  // resume: jmean of the packets already run (the only tally the reference checkpoints)
+        if ((rc = smcrt_checkpoint_read(ckpt_in.c_str(), nullptr, 0, nullptr, jmean.data(), (int64_t)nv))) return cleanup(rc);
+        if (photons_done < 0 || photons_done > c.nphotons) return cleanup(host_fail("checkpoint has run more packets than the deck asks for"));
+    }
+    // run_MCRT's loop (kernelsMod.f90:1861-1888) with its `mod(j, ckptfreq) == 0 -> checkpoint` cut points.  Packet streams depend
+    // on (seed, packet id) only, so the pieces -- and a resumed run, which starts at id photons_done -- are ONE job.
+    const bool ckpt_on = (tally_mode & SMCRT_TALLY_PATHLENGTH) && c.ckptfreq > 0 && c.ckptfreq < c.nphotons;
+    auto t0 = std::chrono::steady_clock::now();
+    auto last_write = t0;
+    int64_t done = photons_done;
+    std::vector<float> snap;
+    while (done < c.nphotons) {
+        int64_t piece = c.nphotons - done;
+        if (ckpt_on) {  // up to the next multiple of ckptfreq that is >= 64 Mi packets away (a piece shorter than that is all overhead)
+            static const char* mp = std::getenv("SMCRT_CKPT_MIN_PIECE");  // tests
+            const int64_t min_piece = mp ? std::max<int64_t>(1, std::atoll(mp)) : (64ll << 20);
+            const int64_t k = std::max<int64_t>(1, (min_piece + c.ckptfreq - 1) / c.ckptfreq);
+            piece = std::min<int64_t>(piece, (done / c.ckptfreq + k) * c.ckptfreq - done);
+        }
+        if ((rc = smcrt_run(ctx, piece, (uint64_t)c.iseed, done, tally_mode, survival_bias, -1.0, -1.0))) return cleanup(rc);
+        done += piece;
+        const auto now = std::chrono::steady_clock::now();
+        static const char* ms = std::getenv("SMCRT_CKPT_MIN_SECONDS");  // tests
+        if (ckpt_on && done < c.nphotons && std::chrono::duration<double>(now - last_write).count() >= (ms ? std::atof(ms) : 2.0)) {
+            snap = jmean;  // what the checkpoint held + what the device has accumulated since
+            if ((rc = smcrt_fetch(ctx, snap.data(), nullptr, nullptr, nullptr, nullptr, 1))) return cleanup(rc);
+            if ((rc = smcrt_checkpoint_write(c.ckptfile.c_str(), c.ckpt_deck.c_str(), done, snap.data(), (int64_t)nv))) return cleanup(rc);
+            last_write = std::chrono::steady_clock::now();
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    const double secs = std::chrono::duration<double>(t1 - t0).count();
+    if (photons_per_s) *photons_per_s = (double)(c.nphotons - photons_done) / secs;  // print*,"Photons/s: ", kernelsMod.f90:1897
     std::vector<double> bins((size_t)std::max<int64_t>(1, smcrt_det_bins_total(ctx)), 0.0);
     smcrt_counters cn{};
-    if ((rc = smcrt_fetch(ctx, jmean.data(), absorb.data(), emission.data(), bins.data(), &cn, 0))) return cleanup(rc);
+    if ((rc = smcrt_fetch(ctx, jmean.data(), absorb.data(), emission.data(), bins.data(), &cn, 1))) return cleanup(rc);
     if (counters) *counters = cn;
     std::printf(" Average # of scatters per photon: %.10g\n", cn.nscatt / (double)c.nphotons);
     // finalise: metadata then files (kernelsMod.f90:2376-2392)

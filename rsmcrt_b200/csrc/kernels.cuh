@@ -22,7 +22,7 @@ struct KParams {
     int n_prims, n_top, n_instr, n_det;
     int has_capsule;  // some top-level SDF is a bare capsule / segment: the sweep is told how far the packet can travel (`need`)
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
-    int off_tops, off_prog, off_dets, off_hot;  // byte offsets inside the blob (prims at 0)
+    int off_tops, off_prog, off_dets, off_hot, off_detp;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
     const DevInstrD* progD;
     // culling grid: per coarse cell the candidate list of top-level SDFs; null = evaluate all
@@ -124,6 +124,7 @@ struct SceneView {
     const DevInstr* prog;
     const DevDet* dets;
     const float4* hot;  // 2 x float4 per top-level SDF: the sweep's view of it (see DevHot in device_scene.cuh)
+    const float4* detp; // one float4 per detector: its plane (n, n.p0), all the crossing pre-test needs
     int n_top, n_det;
 };
 __device__ __forceinline__ SceneView make_view(const unsigned char* base, const KParams& P) {
@@ -133,6 +134,7 @@ __device__ __forceinline__ SceneView make_view(const unsigned char* base, const 
     sc.prog = reinterpret_cast<const DevInstr*>(base + P.off_prog);
     sc.dets = reinterpret_cast<const DevDet*>(base + P.off_dets);
     sc.hot = reinterpret_cast<const float4*>(base + P.off_hot);
+    sc.detp = reinterpret_cast<const float4*>(base + P.off_detp);
     sc.n_top = P.n_top;
     sc.n_det = P.n_det;
     return sc;
@@ -513,13 +515,19 @@ __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, floa
 // crossing is seen exactly once ("watertight"), which is what the reference's FP64 arithmetic achieves implicitly.
 __device__ __forceinline__ int nint_pos(float v) { return (int)floorf(v + 0.5f); }  // Fortran nint for v >= 0
 // Plane detectors (circle, annulus, fibre): crossing test + radial distance of the hit point from the detector centre.
+// The side function is evaluated in plane form g(x) = n.p0 - n.x from ONE 16-byte record (pl = (n, n.p0)): a segment that does
+// not cross -- nearly all of them -- costs one shared load, six FMAs and two compares per detector.  Any fixed g keeps the test
+// watertight: consecutive segments share their end point bit for bit, so g(end of k) IS g(start of k+1).
 // `denom` = n.l is returned for the fibre's acceptance chain.
-__device__ __forceinline__ bool det_plane_hit(const DevDet& D, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
-                                              float e1, float e2, float& r, float& denom) {
-    denom = D.dir[0] * d0 + D.dir[1] * d1 + D.dir[2] * d2;
-    const float gs = (D.pos[0] - s0) * D.dir[0] + (D.pos[1] - s1) * D.dir[1] + (D.pos[2] - s2) * D.dir[2];
-    const float ge = (D.pos[0] - e0) * D.dir[0] + (D.pos[1] - e1) * D.dir[1] + (D.pos[2] - e2) * D.dir[2];
-    if (!(denom > 1e-6f) || !(gs >= 0.f) || !(ge < 0.f)) return false;  // intersectPlane: src/geometryMod.f90:234
+__device__ __forceinline__ bool det_plane_cross(const float4 pl, float s0, float s1, float s2, float e0, float e1, float e2, float& gs) {
+    gs = pl.w - (pl.x * s0 + pl.y * s1 + pl.z * s2);
+    const float ge = pl.w - (pl.x * e0 + pl.y * e1 + pl.z * e2);
+    return gs >= 0.f && ge < 0.f;
+}
+__device__ __forceinline__ bool det_plane_hit(const DevDet& D, const float4 pl, float gs, float s0, float s1, float s2, float d0, float d1, float d2,
+                                              float& r, float& denom) {
+    denom = pl.x * d0 + pl.y * d1 + pl.z * d2;
+    if (!(denom > 1e-6f)) return false;  // intersectPlane: src/geometryMod.f90:234
     const float t = gs / denom;
     const float vx = s0 + d0 * t - D.pos[0], vy = s1 + d1 * t - D.pos[1], vz = s2 + d2 * t - D.pos[2];
     r = sqrtf(vx * vx + vy * vy + vz * vz);
@@ -568,11 +576,12 @@ __device__ __noinline__ int det_bin_camera(const DevDet* Dp, float s0, float s1,
     return ix + (iy - 1) * D.nbins;
 }
 // One straight segment against one detector -> 1-based flat bin, 0 on miss (the kernel's DETECT site and the probe kernel)
-__device__ __forceinline__ int detector_bin(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
+__device__ __forceinline__ int detector_bin(const DevDet* Dp, const float4 pl, float s0, float s1, float s2, float d0, float d1, float d2, float e0,
                                             float e1, float e2) {
     if (Dp->kind == 4) return det_bin_camera(Dp, s0, s1, s2, d0, d1, d2);
-    float r, denom;
-    if (!det_plane_hit(*Dp, s0, s1, s2, d0, d1, d2, e0, e1, e2, r, denom)) return 0;
+    float r, denom, gs;
+    if (!det_plane_cross(pl, s0, s1, s2, e0, e1, e2, gs)) return 0;
+    if (!det_plane_hit(*Dp, pl, gs, s0, s1, s2, d0, d1, d2, r, denom)) return 0;
     return Dp->kind == 1 ? det_bin_circle(*Dp, r) : det_bin_annulus_fibre(Dp, r, denom);
 }
 
@@ -964,12 +973,16 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     uint32_t ev = 0;
     unsigned int slot = 0;
     bool has = false;  // this lane holds a packet (slot `slot`) in registers
+    int wc = -1;       // class of the warp's previous iteration (warp-uniform)
     for (;;) {
         // ---- which class does the warp work on next
         const int cls = !has ? -1 : (state <= ST_CROSS ? Q_SWEEP : (state == ST_FRESNEL ? Q_FRESNEL : (state == ST_INTERACT ? Q_INTERACT : Q_EMIT)));
         int c = -1;
         unsigned keep = 0u;
-        {
+        // usual case: enough lanes are still in the class the warp worked on last time (one ballot instead of four)
+        const unsigned stay = wc >= 0 ? __ballot_sync(full, cls == wc) : 0u;
+        if (__popc(stay) >= KEEP_MIN) { c = wc; keep = stay; }
+        else {
             int bestn = 0;
 #pragma unroll
             for (int q = 0; q < Q_COUNT; ++q) {
@@ -1059,6 +1072,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                 }
             }
         }
+        wc = c;
         if (!__any_sync(full, has)) {  // nothing held, nothing to take
             if (vq->retired == (unsigned int)M) break;  // every slot has found the pool empty: the CTA is done
             __nanosleep(40);
@@ -1182,7 +1196,7 @@ __global__ void probe_detector_kernel(const __grid_constant__ KParams P, int det
         const float s[3] = {start[3 * i], start[3 * i + 1], start[3 * i + 2]};
         const float d[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
         const float e[3] = {s[0] + d[0] * len[i], s[1] + d[1] * len[i], s[2] + d[2] * len[i]};
-        const int b = detector_bin(D, s[0], s[1], s[2], d[0], d[1], d[2], e[0], e[1], e[2]);
+        const int b = detector_bin(D, reinterpret_cast<const float4*>(P.blob + P.off_detp)[det_index - 1], s[0], s[1], s[2], d[0], d[1], d[2], e[0], e[1], e[2]);
         hit[i] = b > 0;
         bin[i] = b;
     }

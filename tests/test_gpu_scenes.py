@@ -98,3 +98,38 @@ def test_egg_revolution(engine, oracle, smcrt):
     o = osc.run(n, 3, per_packet=True, grids=False)
     assert (g["fate"] == A.FATE_LOST).sum() <= 2
     ensemble_close(g, o, n)
+
+
+def test_checkpoint_and_resume_is_the_same_job(smcrt, tmp_path, monkeypatch):
+    """[simulation] checkpoint_every_n / load_checkpoint (kernelsMod.f90:52-72,1863; writer.f90:426-457): the run is cut at multiples
+    of checkpoint_every_n and the checkpoint rewritten; resuming from it traces the packets that were still to come -- same seed,
+    ids from photons_run on -- so the path-length grid equals that of the uninterrupted run."""
+    from rsmcrt_b200 import api as A
+    monkeypatch.setenv("SMCRT_CKPT_MIN_PIECE", "1")
+    monkeypatch.setenv("SMCRT_CKPT_MIN_SECONDS", "0")
+    ck = tmp_path / "run.ckpt"
+    deck = (RES / "scat_test.toml").read_text()   # ships load_checkpoint=false, checkpoint_file="check.ckpt", checkpoint_every_n=10000
+    assert 'checkpoint_file="check.ckpt"' in deck and "checkpoint_every_n=10000" in deck and "load_checkpoint=false" in deck
+    deck = deck.replace('checkpoint_file="check.ckpt"', f'checkpoint_file="{ck}"').replace("checkpoint_every_n=10000", "checkpoint_every_n=50000")
+    base = tmp_path / "deck.toml"
+    base.write_text(deck)
+    n = 200_000
+    mode = A.TALLY_ABSORB | A.TALLY_PATHLENGTH
+    smcrt.default_MCRT(base, out_dir=tmp_path / "full", tally_mode=mode, nphotons=n)
+    name, run, jm = smcrt.checkpoint_read(ck, 0)
+    assert name == str(base) and run == 150_000                    # the last cut before the end
+    cfg = smcrt.Config.load(base)
+    nv = int(np.prod(cfg.grid[0]))
+    _, _, jm = smcrt.checkpoint_read(ck, nv)
+    assert jm.sum() > 0
+    resume = tmp_path / "resume.toml"
+    resume.write_text(deck.replace("load_checkpoint=false", "load_checkpoint=true"))
+    smcrt.default_MCRT(resume, out_dir=tmp_path / "resumed", tally_mode=mode, nphotons=n)
+
+    def grid(d):
+        raw = (tmp_path / d / "jmean" / "fluence.nrrd").read_bytes()
+        return np.frombuffer(raw[-4 * nv:], np.float32).astype(np.float64)
+    a, b = grid("full"), grid("resumed")
+    assert a.sum() > 0
+    assert abs(a.sum() - b.sum()) <= 1e-5 * a.sum()                 # float atomics: same deposits, different order
+    assert np.abs(a - b).max() <= 1e-4 * a.max()

@@ -247,3 +247,22 @@ def test_escape_cell_centre(smcrt):
     assert lib.smcrt_escape_cell_centre(1, 2, 4, 4, 4, 4, 1.0, 2.0, 4.0, M.ctypes.data_as(P), None, None, out.ctypes.data_as(P)) == 0
     v = np.array([-0.75, -0.5, 3.0, 1.0]) @ rz
     assert np.allclose(out, v[:3])
+
+
+def test_checkpoint_file_format_round_trip(smcrt, tmp_path):
+    """writer.f90:426-457: `tomlfile=<name>` / `photons_run=<n>` as two formatted lines, then the raw float32 jmean appended as a
+    stream; kernelsMod.f90:52-66 reads it back by scanning for '=' and taking the stream position after line 2."""
+    rng = np.random.default_rng(5)
+    jm = rng.random((4, 3, 5), dtype=np.float32)
+    p = tmp_path / "check.ckpt"
+    smcrt.checkpoint_write(p, "res/validation1.toml", 1234567, jm)
+    raw = p.read_bytes()
+    head = b"tomlfile=res/validation1.toml\nphotons_run=1234567\n"
+    assert raw.startswith(head) and len(raw) == len(head) + 4 * jm.size
+    assert np.array_equal(np.frombuffer(raw[len(head):], np.float32), jm.reshape(-1, order="F"))   # x fastest
+    name, run, back = smcrt.checkpoint_read(p, jm.size)
+    assert name == "res/validation1.toml" and run == 1234567 and np.array_equal(back, jm.reshape(-1, order="F"))
+    with pytest.raises(smcrt.SmcrtError):
+        smcrt.checkpoint_read(p, jm.size + 1)                      # grid larger than the file
+    with pytest.raises(smcrt.SmcrtError):
+        smcrt.checkpoint_read(tmp_path / "missing.ckpt")

@@ -118,6 +118,7 @@ struct DeviceState {
     int* cull_start = nullptr;
     int* cull_items = nullptr;
     float* cull_far = nullptr;
+    float* cull_clear = nullptr;
     nccl::ncclComm_t comm = nullptr;
     int sm_count = 148;
     bool ran = false;
@@ -245,7 +246,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
         cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters);
-        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far);
+        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
         if (D.ev0) cudaEventDestroy(D.ev0);
         if (D.ev1) cudaEventDestroy(D.ev1);
@@ -623,8 +624,8 @@ static int build_cull(smcrt_ctx* c) {
     const int nt = (int)c->tops.size();
     for (DeviceState& D : c->devs) {
         cudaSetDevice(D.dev);
-        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far);
-        D.cull_start = D.cull_items = nullptr; D.cull_far = nullptr;
+        cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
+        D.cull_start = D.cull_items = nullptr; D.cull_far = nullptr; D.cull_clear = nullptr;
     }
     if (!c->cull_allowed || !c->scene_lipschitz || nt < CULL_MIN_TOPS || c->nxg == 0) return 0;
     int G = (int)std::lround(std::cbrt((double)nt) * 6.0);
@@ -657,7 +658,7 @@ static int build_cull(smcrt_ctx* c) {
     if (ke != cudaSuccess) return set_err("culling grid: %s", cudaGetErrorString(ke));
     c->launches += 1;
     std::vector<int> start((size_t)ncell + 1, 0), items;
-    std::vector<float> far((size_t)ncell);
+    std::vector<float> far((size_t)ncell), clear((size_t)ncell);
     items.reserve((size_t)ncell * 4);
     // Evaluation order inside a cell: by code path (primitive kind / transform class), rarest class first, so that the lanes of a
     // warp -- each walking the list of its own cell -- meet the same kind of primitive at the same loop index (a scene of one
@@ -689,6 +690,11 @@ static int build_cull(smcrt_ctx* c) {
         std::sort(items.begin() + start[cell], items.end(), by_class);
         start[cell + 1] = (int)items.size();
         far[cell] = (float)f;
+        bool inside_some = false;
+        for (int j = 0; j < nt; ++j) inside_some = inside_some || d[j] < 0;
+        // min_j |dc_j| - h: no surface within that of any point of the cell; cells outside every SDF keep the full sweep (it is what
+        // notices that a packet has left the scene, inttau2.f90:143-145)
+        clear[cell] = inside_some ? (float)std::max(0.0, (U - 2.0 * h) * (1.0 - 1e-6)) : 0.f;
     }
     c->cull_mean_list = (double)items.size() / (double)ncell;
     if (c->cull_mean_list > 0.6 * nt) return 0;  // nothing to gain on this scene
@@ -700,6 +706,8 @@ static int build_cull(smcrt_ctx* c) {
         CU(cudaMemcpy(D.cull_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(D.cull_items, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(D.cull_far, far.data(), sizeof(float) * far.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&D.cull_clear, sizeof(float) * clear.size()));
+        CU(cudaMemcpy(D.cull_clear, clear.data(), sizeof(float) * clear.size(), cudaMemcpyHostToDevice));
     }
     c->cull_on = true;
     return 0;
@@ -789,7 +797,10 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.det_in_smem = (c->det_total > 0 && c->det_total <= SMEM_BIN_CAP) ? 1 : 0;
     P.counters = D.counters; P.next = D.counters + C_COUNT;
     if (c->cull_on) {
-        P.cull_start = D.cull_start; P.cull_items = D.cull_items; P.cull_far = D.cull_far;
+        P.cull_start = D.cull_start; P.cull_items = D.cull_items; P.cull_far = D.cull_far; P.cull_clear = D.cull_clear;
+        // clear cells pay off where packets interact between the bodies: some medium with a mean free path shorter than the grid
+        double ext = std::max(c->gmax[0], std::max(c->gmax[1], c->gmax[2]));
+        for (const DevTop& T : c->tops) if ((double)T.kappa * ext > 1.0) P.has_capsule = 1;
         for (int a = 0; a < 3; ++a) {
             P.cull_n[a] = c->cull_n[a];
             P.cull_lo[a] = (float)c->cull_lo[a];

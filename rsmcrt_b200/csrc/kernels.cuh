@@ -20,7 +20,7 @@ struct KParams {
     const unsigned char* blob;
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
-    int has_capsule;  // some top-level SDF is a bare capsule / segment: the sweep is told how far the packet can travel (`need`)
+    int has_capsule;  // the sweep is told how far the packet can travel (`need`): a bare capsule / segment in the scene, or clear cells in use
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
     int off_tops, off_prog, off_dets, off_hot, off_detp;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
@@ -29,6 +29,7 @@ struct KParams {
     const int* cull_start;     // [ncell + 1]
     const int* cull_items;     // top-level SDF indices (0-based), ascending inside a cell
     const float* cull_far;     // [ncell] lower bound of |d| of every SDF NOT in the cell's list, for any point of the cell
+    const float* cull_clear;   // [ncell] lower bound of min_i |d_i| over the cell (0 when a surface may cross it); null = not used
     int cull_n[3];
     float cull_lo[3], cull_inv[3];  // cell = floor((x - lo) * inv)
     // voxel grid (src/grid.f90:14-25)
@@ -308,6 +309,14 @@ __device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc
                   cz = (int)floorf((z - P.cull_lo[2]) * P.cull_inv[2]);
         if (cx >= 0 && cx < P.cull_n[0] && cy >= 0 && cy < P.cull_n[1] && cz >= 0 && cz < P.cull_n[2]) {
             const int c = cx + P.cull_n[0] * (cy + P.cull_n[1] * cz);
+            if (need < SMCRT_BIG) {
+                // Clear cell: no surface comes closer than `cl` to any point of it.  A packet whose optical depth runs out within
+                // `need` < cl interacts before it can reach one: no SDF is evaluated at all (a scattering medium between sparse
+                // bodies -- the dermis around the vessels -- spends most of its sweeps here).  The step decision sees a surface
+                // at distance cl and takes the interaction branch, exactly as it would with the true distances.
+                const float cl = __ldg(P.cull_clear + c);
+                if (need < cl) { s.amin = cl; s.smin = -cl; s.bmin = cl; return s; }
+            }
             const int i0 = __ldg(P.cull_start + c), i1 = __ldg(P.cull_start + c + 1);
             for (int k = i0; k < i1; ++k) sweep_one<true>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, need, s);
             const float far = __ldg(P.cull_far + c);

@@ -233,9 +233,9 @@ int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_off
                         int survival_bias, int32_t* fate, int32_t* nscatt, double* final_pos,
                         int32_t* n_events, int32_t* n_sweeps);
 /* Which kernel variant the engine settled on for this scene and tally mode after timing the candidates on slices of the first
- * large run (>= 8 Mi packets): 0..2 = one packet per thread at 2/3/4 resident CTAs per SM (128/80/64 registers), 3..5 = the same
- * with CTA-level event compaction at 3/4/2 CTAs, 6..7 = queue-scheduled (packets in shared-memory slots, warps pull batches of one
- * state) at 2/3 CTAs; -1 = not timed yet (variant 1 is used).  Environment override: SMCRT_VARIANT_FORCE=0..7. */
+ * large run (>= 8 Mi packets): 0..2 = one packet per thread at 2/3/4 resident CTAs per SM (128/80/64 registers), 3 = the same
+ * with CTA-level event compaction (2 CTAs), 4..5 = queue-scheduled (packets in shared-memory slots, warps pull batches of one
+ * state) at 2/3 CTAs; -1 = not timed yet (variant 1 is used).  Environment override: SMCRT_VARIANT_FORCE=0..5. */
 int smcrt_kernel_variant(const smcrt_ctx* ctx, int tally_mode);
 /* Batched point sources in ONE launch: the body of the escape-function drivers cart_calc_escape_sym / cyl_calc_escape_sym
  * (src/kernelsMod.f90:533-642, 959-1071), which call run_MCRT once per symmetry-grid cell with set_photon(cell centre).

@@ -370,7 +370,7 @@ class Engine:
         return int(self._L.smcrt_last_fetch_bytes(self._h))
 
     def kernel_variant(self, tally_mode=TALLY_ABSORB):
-        """-1 until the first large run has timed the candidates; then 0..7 (smcrt_kernel_variant)."""
+        """-1 until the first large run has timed the candidates; then 0..5 (smcrt_kernel_variant)."""
         return int(self._L.smcrt_kernel_variant(self._h, int(tally_mode)))
 
     def bench_red(self, pattern, span=333, n_ops=1 << 30):

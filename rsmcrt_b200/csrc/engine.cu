@@ -92,11 +92,16 @@ static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
     return h;
 }
 
+constexpr int NVAR_MAX = 8;  // kernel variants a trial can cover (events / time stamps are sized for it)
+static bool create_events(cudaEvent_t* ev, int n) {
+    for (int i = 0; i < n; ++i) if (cudaEventCreate(&ev[i]) != cudaSuccess) return false;
+    return true;
+}
 struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t tune_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // brackets of the kernel-variant trial launches
+    cudaEvent_t tune_ev[NVAR_MAX + 1] = {};  // brackets of the kernel-variant trial launches
     const float* src_table = nullptr;  // set for the duration of smcrt_run_sources
     unsigned long long* src_tot = nullptr;
     unsigned long long src_id0 = 0;
@@ -217,11 +222,7 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
         D.sm_count = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&D.ev0) != cudaSuccess || cudaEventCreate(&D.ev1) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[0]) != cudaSuccess || cudaEventCreate(&D.tune_ev[1]) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[2]) != cudaSuccess || cudaEventCreate(&D.tune_ev[3]) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[4]) != cudaSuccess || cudaEventCreate(&D.tune_ev[5]) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[6]) != cudaSuccess || cudaEventCreate(&D.tune_ev[7]) != cudaSuccess ||
-            cudaEventCreate(&D.tune_ev[8]) != cudaSuccess ||
+            !create_events(D.tune_ev, NVAR_MAX + 1) ||
             cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess ||
             cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess) {
             delete c;
@@ -628,8 +629,11 @@ static int build_cull(smcrt_ctx* c) {
         D.cull_start = D.cull_items = nullptr; D.cull_far = nullptr; D.cull_clear = nullptr;
     }
     if (!c->cull_allowed || !c->scene_lipschitz || nt < CULL_MIN_TOPS || c->nxg == 0) return 0;
-    int G = (int)std::lround(std::cbrt((double)nt) * 6.0);
-    G = std::min(std::max(G, 8), 40);
+    // G^3 cells, G = 10 cbrt(N) (measured: 6 -> 10 cbrt(N) is worth 12 % on the 241-capsule tree, 3 % on the 41 spheres; the lists
+    // get shorter and more cells are clear), bounded by 64 and by 64 Mi (cell, SDF) pairs of set-up work
+    int G = (int)std::lround(std::cbrt((double)nt) * 10.0);
+    G = std::min(G, (int)std::floor(std::cbrt(64.0 * 1048576.0 / (double)nt)));
+    G = std::min(std::max(G, 8), 64);
     double ext = 0;
     for (int a = 0; a < 3; ++a) {
         const double pad = 0.005 * c->gmax[a] + 1e-9;
@@ -832,19 +836,20 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P, DeviceState& D, 
 // budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers)
 enum : int { SCHED_PLAIN = 0, SCHED_COMPACT = 1, SCHED_QUEUED = 2 };
 struct Variant { int sched; int mb; };
-constexpr int NVAR = 8;
-static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 3}, {SCHED_COMPACT, 4}, {SCHED_COMPACT, 2},
-                                       {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
+constexpr int NVAR = 6;
+static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
 template <bool PL, bool HD>
-static trace_kernel_t pick_kernel(int sched, int mb) {
+static trace_kernel_t pick_kernel(int sched, int mb, bool need) {
     if (sched == SCHED_QUEUED) return mb == 2 ? trace_queued<PL, HD, 2> : trace_queued<PL, HD, 3>;
-    if (sched == SCHED_COMPACT) return mb == 2 ? trace_persistent<PL, HD, true, 2> : (mb == 4 ? trace_persistent<PL, HD, true, 4> : trace_persistent<PL, HD, true, 3>);
-    return mb == 2 ? trace_persistent<PL, HD, false, 2> : (mb == 4 ? trace_persistent<PL, HD, false, 4> : trace_persistent<PL, HD, false, 3>);
+    if (sched == SCHED_COMPACT) return trace_persistent<PL, HD, true, 2, false>;
+    if (need) return mb == 2 ? trace_persistent<PL, HD, false, 2, true> : (mb == 4 ? trace_persistent<PL, HD, false, 4, true> : trace_persistent<PL, HD, false, 3, true>);
+    return mb == 2 ? trace_persistent<PL, HD, false, 2, false> : (mb == 4 ? trace_persistent<PL, HD, false, 4, false> : trace_persistent<PL, HD, false, 3, false>);
 }
 static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
     const Variant v = VARIANTS[var];
-    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb) : pick_kernel<true, false>(v.sched, v.mb))
-                          : (hd ? pick_kernel<false, true>(v.sched, v.mb) : pick_kernel<false, false>(v.sched, v.mb));
+    const bool need = P.has_capsule != 0;
+    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need) : pick_kernel<true, false>(v.sched, v.mb, need))
+                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need) : pick_kernel<false, false>(v.sched, v.mb, need));
     return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
 }
 
@@ -875,7 +880,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     const bool compact_ok = c->tops.size() <= 65535 && nphotons >= 4 * SMCRT_BLOCK;  // layer indices share a word in the packet record
     int forced = -1;
     if (force_var) forced = std::min(std::max(atoi(force_var), 0), NVAR - 1);
-    else if (c->compact_allowed) forced = 3;  // SMCRT_COMPACT=1
+    else if (c->compact_allowed) forced = 3;  // SMCRT_COMPACT=1 (the compacted kernel)
     else if (force_mb) forced = std::min(std::max(atoi(force_mb), 2), 4) - 2;
     int var = forced >= 0 ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] - 1 : 1);
     if (VARIANTS[var].sched != SCHED_PLAIN && !compact_ok) var = 1;

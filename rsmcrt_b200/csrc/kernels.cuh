@@ -20,7 +20,7 @@ struct KParams {
     const unsigned char* blob;
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
-    int has_capsule;  // the sweep is told how far the packet can travel (`need`): a bare capsule / segment in the scene, or clear cells in use
+    int has_capsule;  // host side: pick the NEED kernels (a bare capsule / segment in the scene, or clear cells in use)
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
     int off_tops, off_prog, off_dets, off_hot, off_detp;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
@@ -773,7 +773,9 @@ constexpr int XCHG_WORDS = 22;  // 32-bit words of packet state exchanged by the
 // MINBLOCKS = resident CTAs per SM the register allocation is made for (2: 128 registers, no spills; 3: 80; 4: 64).  Which one
 // wins depends on the scene (slab with detectors: 4, +8 %; long histories inside one body: 2, +17 %), so the engine times
 // the three on the first large run of a scene and keeps the fastest (engine.cu: run_on_device).
-template <bool PATHLEN, bool HASDET, bool COMPACT, int MINBLOCKS>
+// NEED: the sweep is told how far the packet can still travel (capsule scenes, clear cells of the culling grid): compiled in only
+// for the scenes that use it -- carrying the value through the sweep costs 4 % on the ones that do not.
+template <bool PATHLEN, bool HASDET, bool COMPACT, int MINBLOCKS, bool NEED>
 __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) trace_persistent(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
@@ -962,6 +964,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     const int lane = threadIdx.x & 31;
     if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) P.tstamp[0] = globaltimer_ns();
     const unsigned full = 0xffffffffu;
+    constexpr bool NEED = false;  // (the plain kernels win on the scenes that use it)
     const unsigned int mask = (unsigned int)M - 1u;
     unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
 

@@ -489,24 +489,28 @@ __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, floa
     const float dtx = dt3[0], dty = dt3[1], dtz = dt3[2];
     float t = 0.f;
     bool out = false;
+    // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
+    const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
+    const long long svx = sx, svy = sy > 0 ? vy : -vy, svz = sz > 0 ? vz : -vz;
+    float* cell = P.jmean + ((long long)i + vy * (long long)j + vz * (long long)k);
 #ifdef SMCRT_DBG_WALK
     if (P.dbg_log) printf("  dda x %.9g %.9g %.9g ijk %d %d %d t0 %.9g %.9g %.9g dt %.9g %.9g %.9g len %.9g\n", (double)fx, (double)fy, (double)fz, i, j, k,
                           (double)tx, (double)ty, (double)tz, (double)dtx, (double)dty, (double)dtz, (double)len);
 #endif
     for (;;) {
         const float tn = fminf(tx, fminf(ty, tz));
-        const long long v = (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
         if (tn >= len) {
-            if (P.dda_plain) atomicAdd(P.jmean + v, fmaxf(len - t, 0.f) * weight);
-            else deposit(P.jmean, v, fmaxf(len - t, 0.f) * weight);
+            if (P.dda_plain) atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
+            else deposit(cell, 0, fmaxf(len - t, 0.f) * weight);
             break;
         }
-        if (P.dda_plain) atomicAdd(P.jmean + v, fmaxf(tn - t, 0.f) * weight);
-        else deposit(P.jmean, v, fmaxf(tn - t, 0.f) * weight);
+        if (P.dda_plain) atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
+        else deposit(cell, 0, fmaxf(tn - t, 0.f) * weight);
         t = tn;
-        if (tx <= ty && tx <= tz) { i += sx; tx += dtx; out = (i < 0 || i >= P.nxg); }
-        else if (ty <= tz)        { j += sy; ty += dty; out = (j < 0 || j >= P.nyg); }
-        else                      { k += sz; tz += dtz; out = (k < 0 || k >= P.nzg); }
+        // (unsigned)index >= n  <=>  index < 0 or index >= n
+        if (tx <= ty && tx <= tz) { i += sx; cell += svx; tx += dtx; out = (unsigned)i >= (unsigned)P.nxg; }
+        else if (ty <= tz)        { j += sy; cell += svy; ty += dty; out = (unsigned)j >= (unsigned)P.nyg; }
+        else                      { k += sz; cell += svz; tz += dtz; out = (unsigned)k >= (unsigned)P.nzg; }
         if (out) break;  // :437-440
     }
     return out;

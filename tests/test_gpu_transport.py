@@ -325,3 +325,25 @@ def test_sparse_fetch_equals_dense_fetch(engine, oracle, smcrt, monkeypatch):
         e2.close()
     assert np.array_equal(a["absorb"], b["absorb"])
     assert np.allclose(a["jmean"], b["jmean"], rtol=1e-4, atol=1e-9)   # float RED order differs between runs
+
+
+def test_kernel_variants_trace_identical_histories_with_fresnel_events(engine, oracle, smcrt):
+    """Five refractive layers (res/skin_b200.toml): the variant trial runs slices of ONE job through the plain, compacted and
+    queue-scheduled kernels (FP64 closed-form Fresnel geometry included); a second run with the chosen kernel alone must give
+    the same unit-deposit absorb grid voxel for voxel, the same scatter and reflection counts, and lose no packet."""
+    import os
+    if any(os.environ.get(k) for k in ("SMCRT_VARIANT_FORCE", "SMCRT_MINBLOCKS_FORCE", "SMCRT_COMPACT")):
+        pytest.skip("kernel variant forced by the environment")
+    cfg, _ = _setup(smcrt, oracle, engine, "skin_b200.toml")
+    n = 9_000_000
+    l0 = engine.launch_count
+    engine.run(n, 11)
+    assert engine.launch_count - l0 == 7
+    a = engine.fetch()
+    engine.reset_tallies()
+    engine.run(n, 11)
+    b = engine.fetch()
+    for k in ("launched", "nscatt", "bounces", "lost"):
+        assert a["counters"][k] == b["counters"][k], k
+    assert a["counters"]["lost"] == 0 and a["counters"]["bounces"] > n // 2
+    assert np.array_equal(a["absorb"], b["absorb"])

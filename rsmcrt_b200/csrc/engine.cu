@@ -957,6 +957,15 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
             ms = std::max(ms, (double)t);
         }
+        if (D.ran) {  // trace_queued's watchdog (kernels.cuh): a run that tripped it is incomplete
+            unsigned long long wd = 0;
+            CU(cudaMemcpy(&wd, D.counters + C_SPARE, sizeof wd, cudaMemcpyDeviceToHost));
+            if (wd) {
+                CU(cudaMemset(D.counters + C_SPARE, 0, sizeof wd));
+                c->pending = false;
+                return set_err("queue-scheduled kernel: watchdog fired on device %d (a warp found no work for ~10 s); this run's tallies are incomplete", D.dev);
+            }
+        }
         if (D.tuning >= 0) {  // the trial slices of run_on_device: keep the fastest kernel variant
             // Ranked by the time from kernel start until the packet pool ran EMPTY (device time stamps): the events around a
             // slice also contain its tail -- the few longest histories finishing alone -- which is the same few milliseconds for

@@ -80,7 +80,7 @@ struct KParams {
     int dbg_cap;
 };
 
-enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE, C_DETHITS, C_COUNT };
+enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE /* trace_queued watchdog */, C_DETHITS, C_COUNT };
 enum : int { TALLY_ABSORB = 1, TALLY_PATHLENGTH = 2, TALLY_EMISSION = 4 };
 constexpr float TWOPI_F = 6.283185307179586f;
 constexpr float DET_FIX = 16777216.0f;  // 2^24: detector bins are Q40.24 fixed point
@@ -990,6 +990,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     unsigned int slot = 0;
     bool has = false;  // this lane holds a packet (slot `slot`) in registers
     int wc = -1;       // class of the warp's previous iteration (warp-uniform)
+    unsigned int idle = 0u;  // consecutive iterations without work (watchdog)
     for (;;) {
         // ---- which class does the warp work on next
         const int cls = !has ? -1 : (state <= ST_CROSS ? Q_SWEEP : (state == ST_FRESNEL ? Q_FRESNEL : (state == ST_INTERACT ? Q_INTERACT : Q_EMIT)));
@@ -1030,7 +1031,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             __syncwarp(grp);
             if (lane == lead) {
                 __threadfence_block();  // slot contents and ring entries before the publication
-                while (atomicCAS(&qc->published[cls], start, start + (unsigned int)cnt) != start) { }  // publish in reservation order
+                unsigned int spins = 0u;  // publish in reservation order (bounded: see the watchdog below)
+                while (atomicCAS(&qc->published[cls], start, start + (unsigned int)cnt) != start)
+                    if (++spins > (1u << 28)) { atomicAdd(&P.counters[C_SPARE], 1ull); break; }
             }
             has = false;
             state = ST_DONE;
@@ -1091,9 +1094,16 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         wc = c;
         if (!__any_sync(full, has)) {  // nothing held, nothing to take
             if (vq->retired == (unsigned int)M) break;  // every slot has found the pool empty: the CTA is done
+            // watchdog: waiting is normal only while other warps finish the last histories (milliseconds).  ~10 s of it means the
+            // queues have lost a slot; leave with an error flag (smcrt_wait reports it) rather than hang the device.
+            if (++idle > (1u << 26)) {
+                if (lane == 0) atomicAdd(&P.counters[C_SPARE], 1ull);
+                break;
+            }
             __nanosleep(40);
             continue;
         }
+        idle = 0u;
 
         // ---- one step (lanes without a packet are in ST_DONE and sit it out)
 #define STEP_EXIT_CHECK

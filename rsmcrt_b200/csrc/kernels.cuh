@@ -990,7 +990,6 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     unsigned int slot = 0;
     bool has = false;  // this lane holds a packet (slot `slot`) in registers
     int wc = -1;       // class of the warp's previous iteration (warp-uniform)
-    unsigned int idle = 0u;  // consecutive iterations without work (watchdog)
     for (;;) {
         // ---- which class does the warp work on next
         const int cls = !has ? -1 : (state <= ST_CROSS ? Q_SWEEP : (state == ST_FRESNEL ? Q_FRESNEL : (state == ST_INTERACT ? Q_INTERACT : Q_EMIT)));
@@ -1096,14 +1095,24 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             if (vq->retired == (unsigned int)M) break;  // every slot has found the pool empty: the CTA is done
             // watchdog: waiting is normal only while other warps finish the last histories (milliseconds).  ~10 s of it means the
             // queues have lost a slot; leave with an error flag (smcrt_wait reports it) rather than hang the device.
-            if (++idle > (1u << 26)) {
+            // (the wait has its own loop: its counter is not live state of the hot loop)
+            bool stalled = false;
+            for (unsigned int spins = 0u;; ++spins) {
+                unsigned int a = 0u;
+                if (lane < Q_COUNT) {
+                    const unsigned int h = vq->head[lane];
+                    a = vq->published[lane] - h;
+                }
+                if (__any_sync(full, a != 0u) || vq->retired == (unsigned int)M) break;
+                if (spins > (1u << 26)) { stalled = true; break; }
+                __nanosleep(40);
+            }
+            if (stalled) {
                 if (lane == 0) atomicAdd(&P.counters[C_SPARE], 1ull);
                 break;
             }
-            __nanosleep(40);
             continue;
         }
-        idle = 0u;
 
         // ---- one step (lanes without a packet are in ST_DONE and sit it out)
 #define STEP_EXIT_CHECK

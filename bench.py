@@ -35,6 +35,12 @@ UNIT = "packets/s"
 F_AFFINE = 18
 F_PRIM = {1: 25, 2: 37, 3: 28, 4: 70, 5: 23, 6: 47, 7: 47, 8: 80, 9: 45, 10: 23}
 F_FRESNEL, F_HG, F_DET_CIRCLE, F_VOXEL, F_EMIT = 45, 60, 30, 9, 20
+WORKLOADS = {
+    "validation1.toml": "BASELINE configs[1]: slab validation, pencil beam, 500^3 grid, 2 circle detectors",
+    "sphere.toml": "BASELINE configs[0]: 40 spheres n=1.37 in a box, uniform source, 200^3 grid, default build (absorb tallies)",
+    "skin_b200.toml": "BASELINE configs[2]: five refractive tissue layers, uniform source, 200^3 grid",
+    "lens.toml": "BASELINE configs[3]: refractive lens (model of two spheres), uniform source, 200^3 grid",
+}
 # flops/packet of the reference algorithm (oracle counters x the table above), as printed by N=1 runs of this file
 ALGORITHMIC_FLOPS = {"validation1.toml": 7399.0}
 # DRAM bytes (read + write) of ONE launch of the dominant kernel at the default packets/step, from the ncu --set full capture of
@@ -160,7 +166,7 @@ def run_reference(args, rank: int, world: int):
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"res/{args.scene} (BASELINE configs[1] slab validation)", "packets_per_step": per_step,
+        "config": {"workload": f"res/{args.scene} ({WORKLOADS.get(args.scene, 'shipped input deck')})", "packets_per_step": per_step,
                    "note": "CPU restatement of the reference path (oracle/oracle.cpp, OpenMP); the gfortran/fpm binary cannot be built here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step} packets/step x {args.steps} steps of res/{args.scene}, xoshiro256** per thread"},
@@ -370,9 +376,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"res/{args.scene} (BASELINE configs[1]: slab validation, pencil beam, 500^3 grid, 2 circle detectors)",
+        "config": {"workload": f"res/{args.scene} ({WORKLOADS.get(args.scene, 'shipped input deck')})",
                    "packets_per_step_per_gpu": n_step, "tally_mode": mode, "parallelism": f"packets sharded over {world} GPU(s), NCCL reduce at end",
-                   "l2_note": "no HBM-resident input stream: scene (<1 KB) lives in shared memory; tally grid 500 MB > L2",
+                   "l2_note": f"no HBM-resident input stream: the scene lives in shared memory; tally grid {nv * 4 / 1e6:.0f} MB "
+                              + ("> L2" if nv * 4 > 126e6 else "(L2 resident)"),
                    "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms, "kernel_variant": eng.kernel_variant(mode)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_actual // args.steps),

@@ -790,6 +790,9 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.n_prims = (int)c->prims.size(); P.n_top = (int)c->tops.size(); P.n_instr = (int)c->prog.size(); P.n_det = (int)c->dets.size();
     for (const DevDet& d : c->dets) if (d.kind == SMCRT_DET_CAMERA) P.has_camera = 1;
     for (const DevTop& T : c->tops) if (T.mode == 0 && (c->prims[T.first].kind == 6 || c->prims[T.first].kind == 7)) P.has_capsule = 1;
+    P.simple_scene = 1;  // every top-level SDF is a sphere or box the sweep evaluates inline (same test as the DevHot records)
+    for (const DevTop& T : c->tops)
+        if (T.mode != 0 || c->prims[T.first].xf == XF_AFFINE || (c->prims[T.first].kind != 1 && c->prims[T.first].kind != 2)) P.simple_scene = 0;
     P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot; P.off_detp = c->off_detp;
     P.primsD = D.primsD; P.progD = D.progD;
     P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;
@@ -848,17 +851,20 @@ struct Variant { int sched; int mb; };
 constexpr int NVAR = 6;
 static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
 template <bool PL, bool HD>
-static trace_kernel_t pick_kernel(int sched, int mb, bool need) {
-    if (sched == SCHED_QUEUED) return mb == 2 ? trace_queued<PL, HD, 2> : trace_queued<PL, HD, 3>;
+static trace_kernel_t pick_kernel(int sched, int mb, bool need, bool simple) {
+    if (sched == SCHED_QUEUED) {
+        if (simple) return mb == 2 ? trace_queued<PL, HD, 2, true> : trace_queued<PL, HD, 3, true>;
+        return mb == 2 ? trace_queued<PL, HD, 2, false> : trace_queued<PL, HD, 3, false>;
+    }
     if (sched == SCHED_COMPACT) return trace_persistent<PL, HD, true, 2, false>;
     if (need) return mb == 2 ? trace_persistent<PL, HD, false, 2, true> : (mb == 4 ? trace_persistent<PL, HD, false, 4, true> : trace_persistent<PL, HD, false, 3, true>);
     return mb == 2 ? trace_persistent<PL, HD, false, 2, false> : (mb == 4 ? trace_persistent<PL, HD, false, 4, false> : trace_persistent<PL, HD, false, 3, false>);
 }
 static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
     const Variant v = VARIANTS[var];
-    const bool need = P.has_capsule != 0;
-    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need) : pick_kernel<true, false>(v.sched, v.mb, need))
-                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need) : pick_kernel<false, false>(v.sched, v.mb, need));
+    const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
+    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need, simple) : pick_kernel<true, false>(v.sched, v.mb, need, simple))
+                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need, simple) : pick_kernel<false, false>(v.sched, v.mb, need, simple));
     return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
 }
 

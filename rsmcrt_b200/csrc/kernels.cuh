@@ -21,6 +21,7 @@ struct KParams {
     int blob_bytes;
     int n_prims, n_top, n_instr, n_det;
     int has_capsule;  // host side: pick the NEED kernels (a bare capsule / segment in the scene, or clear cells in use)
+    int simple_scene;  // host side: pick the SIMPLE kernels (translated spheres / boxes only)
     int has_camera;  // a camera detector counts SEGMENTS (detector_base.f90:222-229): segments are then never merged
     int off_tops, off_prog, off_dets, off_hot, off_detp;  // byte offsets inside the blob (prims at 0)
     const DevPrimD* primsD;            // FP64 copies for the surface normal
@@ -263,7 +264,9 @@ struct Sweep {
     int L;
     bool bexact;
 };
-// distance, directional step bound and exact flag of top-level SDF i
+// distance, directional step bound and exact flag of top-level SDF i.  SIMPLE: the scene holds translated spheres and boxes only (the
+// host checked): the general evaluators are not even compiled into the loop (4 % on the slab: the hot loop is I-cache sensitive).
+template <bool SIMPLE>
 __device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float need, float& d,
                                         float& b, bool& ex) {
     // two 16-byte shared loads bring everything a translated sphere or box needs (no tops[] -> prims[] indirection, no
@@ -276,6 +279,8 @@ __device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, flo
     } else if (code == HOT_BOX) {
         d = box_ray(x + h0.y, y + h0.z, z + h0.w, ux, uy, uz, h1.x, h1.y, h1.z, b);
         ex = true;
+    } else if (SIMPLE) {
+        d = b = SMCRT_BIG; ex = false;  // not reached
     } else if (code == HOT_PROGRAM) {  // compound `model`: plain sphere tracing
         d = eval_program<float, DevPrim, DevInstr>(sc.prims, sc.prog, __float_as_int(h0.y), __float_as_int(h0.z), x, y, z);
         b = fabsf(d);
@@ -285,11 +290,11 @@ __device__ __forceinline__ void top_ray(const SceneView& sc, int i, float x, flo
         d = r.x; b = r.y; ex = r.z != 0.f;
     }
 }
-template <bool ANY_ORDER>
+template <bool ANY_ORDER, bool SIMPLE>
 __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, float y, float z, float ux, float uy, float uz, float need, Sweep& s) {
     float d, b;
     bool ex;
-    top_ray(sc, i, x, y, z, ux, uy, uz, need, d, b, ex);
+    top_ray<SIMPLE>(sc, i, x, y, z, ux, uy, uz, need, d, b, ex);
     s.amin = fminf(s.amin, fabsf(d));
     s.smin = fminf(s.smin, d);
     if (b < s.bmin) { s.bmin = b; s.bexact = ex; }
@@ -301,6 +306,7 @@ __device__ __forceinline__ void sweep_one(const SceneView& sc, int i, float x, f
 // list of SDFs that can attain min|d| or be the innermost negative one somewhere in the cell (interval bounds from the value at
 // the cell centre and 1-Lipschitz continuity), plus `far`: a lower bound of |d| of all the others.  The min / argmax over the
 // list equals the min / argmax over all SDFs for every point of the cell, and a step is additionally capped by `far`.
+template <bool SIMPLE>
 __device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc, float x, float y, float z, float ux, float uy, float uz, float need) {
     Sweep s;
     s.amin = SMCRT_BIG; s.smin = SMCRT_BIG; s.dL = -SMCRT_BIG; s.L = 0; s.bmin = SMCRT_BIG; s.bexact = false;
@@ -318,14 +324,14 @@ __device__ __forceinline__ Sweep sweep_all(const KParams& P, const SceneView& sc
                 if (need < cl) { s.amin = cl; s.smin = -cl; s.bmin = cl; return s; }
             }
             const int i0 = __ldg(P.cull_start + c), i1 = __ldg(P.cull_start + c + 1);
-            for (int k = i0; k < i1; ++k) sweep_one<true>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, need, s);
+            for (int k = i0; k < i1; ++k) sweep_one<true, SIMPLE>(sc, __ldg(P.cull_items + k), x, y, z, ux, uy, uz, need, s);
             const float far = __ldg(P.cull_far + c);
             if (far < s.bmin) { s.bmin = fmaxf(far, s.amin); s.bexact = false; }  // never step past an unlisted surface
             return s;
         }
     }
     const int n = sc.n_top;
-    for (int i = 0; i < n; ++i) sweep_one<false>(sc, i, x, y, z, ux, uy, uz, need, s);
+    for (int i = 0; i < n; ++i) sweep_one<false, SIMPLE>(sc, i, x, y, z, ux, uy, uz, need, s);
     return s;
 }
 
@@ -793,6 +799,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     uint32_t* xbuf = xtot + 16;
     if (COMPACT && threadIdx.x < 16) xtot[threadIdx.x] = 0u;
     uint32_t xiter = 0;
+    constexpr bool SIMPLE = false;  // (sphere/box-only specialisation: queued kernels only)
     // COMPACT only: xiter == XTAIL = compaction switched off for the rest of the run (CTA-uniform; no register of its own)
     constexpr uint32_t XTAIL = 0xffffffffu;
     if (HASDET && P.det_in_smem)
@@ -937,7 +944,7 @@ __host__ __device__ constexpr int queued_smem_bytes(int threads) {
     return (int)sizeof(QueueCtl) + Q_COUNT * threads * QSLOTS_PER_THREAD * 2 + threads * QSLOTS_PER_THREAD * QSLOT_WORDS * 4;
 }
 
-template <bool PATHLEN, bool HASDET, int MINBLOCKS>
+template <bool PATHLEN, bool HASDET, int MINBLOCKS, bool SIMPLE>
 __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) trace_queued(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)
@@ -1189,7 +1196,7 @@ __global__ void probe_ray_kernel(const __grid_constant__ KParams P, int top_inde
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float d, b;
         bool ex;
-        top_ray(sc, top_index - 1, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], SMCRT_BIG, d, b, ex);
+        top_ray<false>(sc, top_index - 1, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], SMCRT_BIG, d, b, ex);
         dist[i] = d; bound[i] = b; exact[i] = ex ? 1 : 0;
     }
 }

@@ -851,10 +851,11 @@ struct Variant { int sched; int mb; };
 constexpr int NVAR = 6;
 static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
 template <bool PL, bool HD>
-static trace_kernel_t pick_kernel(int sched, int mb, bool need, bool simple) {
+static trace_kernel_t pick_kernel(int sched, int mb, bool need, bool simple, bool lean) {
     if (sched == SCHED_QUEUED) {
-        if (simple) return mb == 2 ? trace_queued<PL, HD, 2, true> : trace_queued<PL, HD, 3, true>;
-        return mb == 2 ? trace_queued<PL, HD, 2, false> : trace_queued<PL, HD, 3, false>;
+        if (simple && lean) return mb == 2 ? trace_queued<PL, HD, 2, true, true> : trace_queued<PL, HD, 3, true, true>;
+        if (simple) return mb == 2 ? trace_queued<PL, HD, 2, true, false> : trace_queued<PL, HD, 3, true, false>;
+        return mb == 2 ? trace_queued<PL, HD, 2, false, false> : trace_queued<PL, HD, 3, false, false>;
     }
     if (sched == SCHED_COMPACT) return trace_persistent<PL, HD, true, 2, false>;
     if (need) return mb == 2 ? trace_persistent<PL, HD, false, 2, true> : (mb == 4 ? trace_persistent<PL, HD, false, 4, true> : trace_persistent<PL, HD, false, 3, true>);
@@ -863,8 +864,10 @@ static trace_kernel_t pick_kernel(int sched, int mb, bool need, bool simple) {
 static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
     const Variant v = VARIANTS[var];
     const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
-    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need, simple) : pick_kernel<true, false>(v.sched, v.mb, need, simple))
-                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need, simple) : pick_kernel<false, false>(v.sched, v.mb, need, simple));
+    // LEAN: nothing optional asked of this run (no per-packet records, diagnostics, batched sources, survival biasing)
+    const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival;
+    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need, simple, lean) : pick_kernel<true, false>(v.sched, v.mb, need, simple, lean))
+                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need, simple, lean) : pick_kernel<false, false>(v.sched, v.mb, need, simple, lean));
     return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
 }
 

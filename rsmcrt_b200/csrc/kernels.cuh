@@ -762,6 +762,9 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #else
 #define SMCRT_LOG __logf
 #endif
+// optional features of a run (per-packet records, diagnostics, batched sources, survival biasing): tested through SMCRT_OPT so
+// that the LEAN kernels -- what a plain smcrt_run of a sphere/box scene uses -- do not carry their branches (5 % on the slab)
+#define SMCRT_OPT(X) (!LEAN && (X))
 #ifndef SMCRT_BLOCK
 #define SMCRT_BLOCK 256      // threads per CTA
 #endif
@@ -800,6 +803,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     if (COMPACT && threadIdx.x < 16) xtot[threadIdx.x] = 0u;
     uint32_t xiter = 0;
     constexpr bool SIMPLE = false;  // (sphere/box-only specialisation: queued kernels only)
+    constexpr bool LEAN = false;
     // COMPACT only: xiter == XTAIL = compaction switched off for the rest of the run (CTA-uniform; no register of its own)
     constexpr uint32_t XTAIL = 0xffffffffu;
     if (HASDET && P.det_in_smem)
@@ -944,7 +948,7 @@ __host__ __device__ constexpr int queued_smem_bytes(int threads) {
     return (int)sizeof(QueueCtl) + Q_COUNT * threads * QSLOTS_PER_THREAD * 2 + threads * QSLOTS_PER_THREAD * QSLOT_WORDS * 4;
 }
 
-template <bool PATHLEN, bool HASDET, int MINBLOCKS, bool SIMPLE>
+template <bool PATHLEN, bool HASDET, int MINBLOCKS, bool SIMPLE, bool LEAN>
 __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) trace_queued(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     {  // stage the scene in shared memory (16-byte vector copies)

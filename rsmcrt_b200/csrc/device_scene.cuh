@@ -353,7 +353,7 @@ __device__ __forceinline__ T csg_op(int kind, T d1, T d2, T k) {  // src/sdfs/sd
 // program interpreter for `model` / modifier trees (sdf_base.f90:146-161, sdfModifiers.f90:286-426).
 // Stacks are tiny (depth checked at compile time on the host: <= 4 distances, <= 3 saved points).
 template <typename T, typename PRIM, typename INSTR>
-__device__ __noinline__ T eval_program(const PRIM* prims, const INSTR* prog, int first, int count, T x, T y, T z) {
+static __device__ __noinline__ T eval_program(const PRIM* prims, const INSTR* prog, int first, int count, T x, T y, T z) {
     T ds[4];
     T ps[3][3];
     int nd = 0, np = 0;
@@ -432,7 +432,7 @@ static_assert(sizeof(DevHot) == 32, "DevHot must be 32 bytes");
 // Every single primitive the inline sphere / box code of the sweep does not cover: planes, capsules, transformed primitives, kinds
 // without a closed-form ray bound.  Out of line: ONE copy, and the sweep loop stays small (I-cache).
 // -> (distance, step bound, exact flag)
-__device__ __noinline__ float3 eval_prim_ray_general(const DevPrim* prim, float x, float y, float z, float ux, float uy, float uz, float need) {
+static __device__ __noinline__ float3 eval_prim_ray_general(const DevPrim* prim, float x, float y, float z, float ux, float uy, float uz, float need) {
     float b;
     bool ex;
     const float d = eval_prim_ray(*prim, x, y, z, ux, uy, uz, need, b, ex);

@@ -111,6 +111,12 @@ struct DeviceState {
     DevPrimD* primsD = nullptr;
     DevInstrD* progD = nullptr;
     float *jmean = nullptr, *absorb = nullptr, *emission = nullptr;
+    // path-length mode: fixed-point difference grids per axis (allocated by the first path-length run), their
+    // "touched" flags, whether deposits are waiting in them, and how many packets have gone in since the last scan
+    long long* jdiff[3] = {nullptr, nullptr, nullptr};
+    unsigned int* jdiff_used = nullptr;
+    bool jdiff_dirty = false;
+    long long jdiff_packets = 0;
     unsigned long long* det_bins = nullptr;
     unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last) + 2 x 8 time stamps of the variant trial
     // sparse read-back scratch (smcrt_fetch): device pair list + cursor, pinned host mirror
@@ -168,6 +174,7 @@ struct smcrt_ctx {
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
     bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
+    bool dda_legacy = false;  // SMCRT_DDA_LEGACY at smcrt_create: path-length deposits one red per voxel crossed (A/B switch, tests)
     // kernel-variant choice per tally configuration [pathlength][detectors]: 0 = not timed yet, else 1 + index into VARIANTS
     int tuned_mb[2][2] = {{0, 0}, {0, 0}};
     uint64_t last_fetch_bytes = 0;  // device -> host bytes moved by the last smcrt_fetch
@@ -204,6 +211,7 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
     c->cull_allowed = getenv("SMCRT_NO_CULL") == nullptr;  // A/B switch for the culling grid (tests, profiling)
     // Event compaction is OPT-IN: measured slower than the plain persistent loop on every shipped scene
     c->compact_allowed = getenv("SMCRT_COMPACT") != nullptr;
+    c->dda_legacy = getenv("SMCRT_DDA_LEGACY") != nullptr;
     c->devs.resize(n_gpus);
     for (int g = 0; g < n_gpus; ++g) {
         DeviceState& D = c->devs[g];
@@ -239,6 +247,8 @@ static void free_grids(DeviceState& D) {
     cudaSetDevice(D.dev);
     cudaFree(D.jmean); cudaFree(D.absorb); cudaFree(D.emission);
     D.jmean = D.absorb = D.emission = nullptr;
+    for (int a = 0; a < 3; ++a) { cudaFree(D.jdiff[a]); D.jdiff[a] = nullptr; }
+    D.jdiff_dirty = false; D.jdiff_packets = 0;
 }
 
 extern "C" void smcrt_destroy(smcrt_ctx* c) {
@@ -248,7 +258,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.stream) cudaStreamSynchronize(D.stream);
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
-        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters);
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used);
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
         if (D.ev0) cudaEventDestroy(D.ev0);
@@ -823,13 +833,17 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
             P.cull_inv[a] = (float)(1.0 / c->cull_cell[a]);
         }
     }
-    P.dda_plain = getenv("SMCRT_DDA_AGG") ? 0 : 1;
+    P.dda_legacy = c->dda_legacy ? 1 : 0;
+    for (int a = 0; a < 3; ++a) {
+        P.jdiff[a] = D.jdiff[a];
+        P.jfix[a] = (float)(268435456.0 /* 2^28 */ * nn[a] / (2.0 * c->gmax[a]));
+    }
+    P.jdiff_used = D.jdiff_used;
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     P.max_steps = (int)std::min<long long>(c->max_steps, 1900000ll);  // the compaction step packs sweep count and event index (<= sweeps + 100000 emit retries) into 21 bits each
     return 0;
 }
 
-typedef void (*trace_kernel_t)(const KParams);
 static int launch_kernel(trace_kernel_t kern, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
@@ -844,31 +858,34 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P, DeviceState& D, 
     CU(cudaGetLastError());
     return 0;
 }
-// Kernel variants: scheduling (one packet per thread / + compaction behind CTA barriers / slot queues) x register
-// budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers)
-enum : int { SCHED_PLAIN = 0, SCHED_COMPACT = 1, SCHED_QUEUED = 2 };
 struct Variant { int sched; int mb; };
 constexpr int NVAR = 6;
 static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
-template <bool PL, bool HD>
-static trace_kernel_t pick_kernel(int sched, int mb, bool need, bool simple, bool lean) {
-    if (sched == SCHED_QUEUED) {
-        if (simple && lean) return mb == 2 ? trace_queued<PL, HD, 2, true, true> : trace_queued<PL, HD, 3, true, true>;
-        if (simple) return mb == 2 ? trace_queued<PL, HD, 2, true, false> : trace_queued<PL, HD, 3, true, false>;
-        return mb == 2 ? trace_queued<PL, HD, 2, false, false> : trace_queued<PL, HD, 3, false, false>;
-    }
-    if (sched == SCHED_COMPACT) return trace_persistent<PL, HD, true, 2, false>;
-    if (need) return mb == 2 ? trace_persistent<PL, HD, false, 2, true> : (mb == 4 ? trace_persistent<PL, HD, false, 4, true> : trace_persistent<PL, HD, false, 3, true>);
-    return mb == 2 ? trace_persistent<PL, HD, false, 2, false> : (mb == 4 ? trace_persistent<PL, HD, false, 4, false> : trace_persistent<PL, HD, false, 3, false>);
-}
 static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
     const Variant v = VARIANTS[var];
     const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
     // LEAN: nothing optional asked of this run (no per-packet records, diagnostics, batched sources, survival biasing)
     const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival;
-    trace_kernel_t k = pl ? (hd ? pick_kernel<true, true>(v.sched, v.mb, need, simple, lean) : pick_kernel<true, false>(v.sched, v.mb, need, simple, lean))
-                          : (hd ? pick_kernel<false, true>(v.sched, v.mb, need, simple, lean) : pick_kernel<false, false>(v.sched, v.mb, need, simple, lean));
+    trace_kernel_t k = pl ? (hd ? pick_kernel_pl1_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl1_hd0(v.sched, v.mb, need, simple, lean))
+                          : (hd ? pick_kernel_pl0_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl0_hd0(v.sched, v.mb, need, simple, lean));
     return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
+}
+
+// Path-length deposits waiting in the difference grids -> jmean (prefix sums along each touched axis; the grids come back zero).
+// Called before anything reads jmean: fetch, the NCCL reduce, and before the fixed-point entries could overflow.
+static int scan_pathlength(smcrt_ctx* c, DeviceState& D) {
+    if (!D.jdiff_dirty || !D.jdiff[0]) return 0;
+    CU(cudaSetDevice(D.dev));
+    const int blocks = D.sm_count * 8;
+    jdiff_scan_kernel<0><<<blocks, 256, 0, D.stream>>>(D.jdiff[0], D.jmean, D.jdiff_used, c->nxg, c->nyg, c->nzg, 2.0 * c->gmax[0] / c->nxg / 268435456.0);
+    jdiff_scan_kernel<1><<<blocks, 256, 0, D.stream>>>(D.jdiff[1], D.jmean, D.jdiff_used, c->nxg, c->nyg, c->nzg, 2.0 * c->gmax[1] / c->nyg / 268435456.0);
+    jdiff_scan_kernel<2><<<blocks, 256, 0, D.stream>>>(D.jdiff[2], D.jmean, D.jdiff_used, c->nxg, c->nyg, c->nzg, 2.0 * c->gmax[2] / c->nzg / 268435456.0);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream));
+    c->launches += 3;
+    D.jdiff_dirty = false;
+    D.jdiff_packets = 0;
+    return 0;
 }
 
 static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint64_t seed, long long id_offset, int tally_mode,
@@ -884,6 +901,23 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps; P.out_dbg = out_dbg;
     P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
     CU(cudaSetDevice(D.dev));
+    if ((tally_mode & SMCRT_TALLY_PATHLENGTH) && !P.dda_legacy) {
+        if (!D.jdiff[0]) {  // first path-length run on this grid
+            size_t nv;
+            n_voxels(c, &nv);
+            if (!D.jdiff_used) { CU(cudaMalloc(&D.jdiff_used, 16)); CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream)); }
+            for (int a = 0; a < 3; ++a) {
+                CU(cudaMalloc(&D.jdiff[a], nv * sizeof(long long)));
+                CU(cudaMemsetAsync(D.jdiff[a], 0, nv * sizeof(long long), D.stream));
+                P.jdiff[a] = D.jdiff[a];
+            }
+            P.jdiff_used = D.jdiff_used;
+        }
+        // an entry of a difference grid holds < 2^63 for 2^32 full-chord deposits (2^28 units each, weights <= 1/chance)
+        if (D.jdiff_packets + nphotons > (1ll << 32)) { int rc = scan_pathlength(c, D); if (rc) return rc; }
+        D.jdiff_dirty = true;
+        D.jdiff_packets += nphotons;
+    }
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     const int smem_plain = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
     P.xchg_off = (smem_plain + 15) & ~15;
@@ -1025,6 +1059,7 @@ static int reduce_buffers(smcrt_ctx* c, int root_rank_or_dev) {
     // one grouped ncclReduce per tally buffer; root receives in place
     size_t nv;
     n_voxels(c, &nv);
+    for (DeviceState& D : c->devs) { int rc = scan_pathlength(c, D); if (rc) return rc; }
     NC(nccl::GroupStart());
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceState& D = c->devs[g];
@@ -1064,6 +1099,11 @@ static int zero_device_tallies(smcrt_ctx* c, DeviceState& D) {
     size_t nv;
     n_voxels(c, &nv);
     CU(cudaSetDevice(D.dev));
+    if (D.jdiff_dirty) {  // deposits waiting in the difference grids are dropped with the rest
+        for (int a = 0; a < 3; ++a) CU(cudaMemsetAsync(D.jdiff[a], 0, nv * sizeof(long long), D.stream));
+        CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream));
+        D.jdiff_dirty = false; D.jdiff_packets = 0;
+    }
     CU(cudaMemsetAsync(D.jmean, 0, nv * 4, D.stream));
     CU(cudaMemsetAsync(D.absorb, 0, nv * 4, D.stream));
     CU(cudaMemsetAsync(D.emission, 0, nv * 4, D.stream));
@@ -1125,6 +1165,7 @@ extern "C" int smcrt_fetch(smcrt_ctx* c, float* jmean, float* absorb, float* emi
     }
     DeviceState& D = c->devs[0];
     CU(cudaSetDevice(D.dev));
+    if ((rc = scan_pathlength(c, D))) return rc;
     size_t nv;
     n_voxels(c, &nv);
     std::vector<float> tmp;

@@ -68,7 +68,11 @@ struct KParams {
     float eps0, eps_rel;
     int max_steps;
     int xchg_off;   // byte offset of the compaction scratch in dynamic shared memory (16-byte aligned)
-    int dda_plain;  // 1: path-length deposits use plain red.global (no warp aggregation)
+    int dda_legacy;  // 1: path-length deposits one red.global.add.f32 per voxel crossed (SMCRT_DDA_LEGACY; cross-check of the run walker)
+    // run walker (walk_dda_runs): fixed-point difference grids per axis, their scale (2^28 / voxel edge) and "touched" flags
+    long long* jdiff[3];
+    float jfix[3];
+    unsigned int* jdiff_used;
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
     int* out_nscatt;
@@ -201,7 +205,7 @@ __device__ __forceinline__ bool closed_form_prim(const KParams& P, const SceneVi
     Q = P.primsD + T.first;
     return Q->xf != XF_AFFINE && (Q->kind == 1 || Q->kind == 2);
 }
-__device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
+static __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
                                           double uz, double tmax) {
     const DevPrimD* Q;
     if (closed_form_prim(P, sc, t, Q)) {
@@ -228,7 +232,7 @@ __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc,
     }
     return polish_hit_newton(P, sc, t, X, Y, Z, ux, uy, uz, tmax);
 }
-__device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
+static __device__ __noinline__ double3 surface_normal(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z) {
     const DevPrimD* Q;
     if (closed_form_prim(P, sc, t, Q)) {
         double ox = X, oy = Y, oz = Z;
@@ -343,7 +347,7 @@ struct Refl {
     float x, y, z, R;
     bool reflected;
 };
-__device__ __noinline__ Refl reflect_refract(float ux, float uy, float uz, double3 N, float n1f, float n2f, float xi) {
+static __device__ __noinline__ Refl reflect_refract(float ux, float uy, float uz, double3 N, float n1f, float n2f, float xi) {
     const double n1 = n1f, n2 = n2f;
     const double dx = ux, dy = uy, dz = uz;
     const double idn = dx * N.x + dy * N.y + dz * N.z;
@@ -429,9 +433,12 @@ __device__ __forceinline__ void hg_scatter(float& dx_, float& dy_, float& dz_, f
 // ------------------------------------------------------------------------------------------------ voxels
 __device__ __forceinline__ bool in_grid(const KParams& P, float x, float y, float z) {
     // update_voxels (src/inttau2.f90:587-614): cell = floor(n (x + max) / (2 max)) + 1 is valid  <=>  -max <= x < max.
-    // Compared on the coordinate itself: the scaled form rounds up to n in FP32 for x within ~n ulp of the upper face, which
-    // would kill every packet that reaches a medium surface coinciding with the grid face before it can reflect.
-    return x >= -P.gmax[0] && x < P.gmax[0] && y >= -P.gmax[1] && y < P.gmax[1] && z >= -P.gmax[2] && z < P.gmax[2];
+    // Compared on the coordinate itself: the scaled form rounds up to n in FP32 for x within ~n ulp of the upper face.
+    // CLOSED at the upper face too: a medium surface that coincides with the grid face (the side walls of the skin stack, the slab
+    // scenes) puts a packet that reflects there ON the face -- x == max in FP32, a set of measure zero at the reference's FP64 --
+    // and the half-open test killed it on the +x, +y, +z faces only (2 % of the packets of skin_b200.toml, none on the minus
+    // faces).  voxel_of / dda_start clamp the index of such a point to the last cell.
+    return fabsf(x) <= P.gmax[0] && fabsf(y) <= P.gmax[1] && fabsf(z) <= P.gmax[2];
 }
 __device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y, float z) {
     int i = (int)floorf((x + P.gmax[0]) * P.inv_vox[0]);
@@ -462,21 +469,24 @@ __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
     if (lane == leader) atomicAdd(grid + vox, sum);  // result unused -> RED.E.ADD.F32
 }
 
-// update_grids in -Dpathlength mode (src/inttau2.f90:408-445): 3-D DDA depositing (segment length * weight) into every
-// voxel the straight piece crosses.  Returns true when the walk starts or ends outside the grid (packet dies).
+// update_grids in -Dpathlength mode (src/inttau2.f90:408-445): deposits (segment length * weight) into every voxel the straight
+// piece crosses.  Returns true when the walk starts or ends outside the grid (packet dies).
 // (Default build: only the end-of-step voxel matters, see the WALK macro of the kernel.)  Arguments by value: a pointer
 // argument would force the caller's state into local memory.
-__device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
-    if (!in_grid(P, fx, fy, fz)) return true;  // :411-415
-    // Cell faces are taken centre-origin, face(i) = (2i - n) * (max / n), so their rounding error scales with the face's own
-    // coordinate and not with max: with the corner-origin form (x + max) a packet on the beam axis of a wide grid
-    // (|x| << max) sees face - x wrong by ulp(max), and dividing that by a small direction cosine gives an arbitrarily
-    // large NEGATIVE first crossing distance, which the loop below would deposit as path that was never travelled.
+//
+// Cell faces are taken centre-origin, face(i) = (2i - n) * (max / n), so their rounding error scales with the face's own
+// coordinate and not with max: with the corner-origin form (x + max) a packet on the beam axis of a wide grid
+// (|x| << max) sees face - x wrong by ulp(max), and dividing that by a small direction cosine gives an arbitrarily
+// large NEGATIVE first crossing distance, which the loop below would deposit as path that was never travelled.
+struct DdaStart {
+    int c[3];
+    float t[3], dt[3];
+};
+__device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz) {
     const float f3[3] = {fx, fy, fz}, d3[3] = {dx, dy, dz};
     const int n3[3] = {P.nxg, P.nyg, P.nzg};
-    int c3[3];
-    float t3[3], dt3[3];
     const float BIG = 3.0e38f;
+    DdaStart s;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float hv = P.hvox[a];
@@ -484,42 +494,178 @@ __device__ __noinline__ bool walk_dda(const KParams& P, float fx, float fy, floa
         c = min(max(c, 0), n3[a] - 1);
         if (c > 0 && f3[a] < (float)(2 * c - n3[a]) * hv) --c;                       // make the cell agree with its own faces
         else if (c < n3[a] - 1 && f3[a] >= (float)(2 * c + 2 - n3[a]) * hv) ++c;
-        c3[a] = c;
+        s.c[a] = c;
         const float face = (float)(2 * (c + (d3[a] > 0.f)) - n3[a]) * hv;
-        t3[a] = d3[a] != 0.f ? fmaxf((face - f3[a]) / d3[a], 0.f) : BIG;
-        dt3[a] = d3[a] != 0.f ? P.vox[a] / fabsf(d3[a]) : BIG;
+        s.t[a] = d3[a] != 0.f ? fmaxf((face - f3[a]) / d3[a], 0.f) : BIG;
+        s.dt[a] = d3[a] != 0.f ? P.vox[a] / fabsf(d3[a]) : BIG;
     }
-    int i = c3[0], j = c3[1], k = c3[2];
-    const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
-    float tx = t3[0], ty = t3[1], tz = t3[2];
-    const float dtx = dt3[0], dty = dt3[1], dtz = dt3[2];
-    float t = 0.f;
-    bool out = false;
-    // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
+    return s;
+}
+// The deposits of one straight segment (start f, unit direction d, length len), one call per SEGMENT (SEGMENT_END of the kernel),
+// not per piece: a packet of sphere.toml moves in 15 pieces but changes direction three times.
+//
+// Voxel walk (the reference's loop, :417-441): an Amanatides-Woo DDA with one red.global.add.f32 per voxel crossed.
+//
+// Run walk.  One red per voxel crossed cannot go faster than the L2 atomic units (~2e11 red/s when the lines stay
+// in L2, 6e10 into one column), and a packet of the slab scene crosses ~600 voxels.  But a straight segment is a sequence of RUNS:
+// maximal stretches inside one voxel column along the ray's dominant axis `a` (the axis whose faces come fastest).  A run that
+// enters voxel k_in, crosses m faces and ends in voxel k_out deposits
+//        p_in, c, c, ..., c, p_out            c = vox_a / |u_a| (the full chord), p_in / p_out the partial end pieces
+// -- a range update.  It is issued as FOUR integer atomics into a fixed-point DIFFERENCE grid of axis a,
+//        D[lo] += p_lo;  D[lo+1] += c - p_lo;  D[hi] += p_hi - c;  D[hi+1] -= p_hi,
+// whose prefix sum along a (jdiff_scan_kernel, run once before the grid is read) is exactly that deposit sequence: integer adds
+// are associative, so the telescoping is exact whatever the order of the atomics.  The loop iterates over COLUMN CHANGES, not
+// voxels: a segment of the slab's pencil beam (166 voxels) costs 4 atomics.  Runs of fewer than 4 voxels are deposited directly
+// (f32 red into jmean), and a segment whose runs are expected to be that short -- oblique to the grid, or only a few voxels long:
+// the short free paths of a turbid medium -- takes the plain voxel walk, which has less set-up.  Same voxels, same lengths as the
+// voxel walk up to the rounding of a face time (ta + j dta by one fma instead of j additions).
+// Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
+// full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
+__device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+static __device__ __noinline__ void walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+    if (!in_grid(P, fx, fy, fz)) return;  // :411-415
+    const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
-    const long long svx = sx, svy = sy > 0 ? vy : -vy, svz = sz > 0 ? vz : -vz;
-    float* cell = P.jmean + ((long long)i + vy * (long long)j + vz * (long long)k);
-#ifdef SMCRT_DBG_WALK
-    if (P.dbg_log) printf("  dda x %.9g %.9g %.9g ijk %d %d %d t0 %.9g %.9g %.9g dt %.9g %.9g %.9g len %.9g\n", (double)fx, (double)fy, (double)fz, i, j, k,
-                          (double)tx, (double)ty, (double)tz, (double)dtx, (double)dty, (double)dtz, (double)len);
-#endif
-    for (;;) {
-        const float tn = fminf(tx, fminf(ty, tz));
-        if (tn >= len) {
-            if (P.dda_plain) atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
-            else deposit(cell, 0, fmaxf(len - t, 0.f) * weight);
-            break;
+    long long off = (long long)S.c[0] + vy * (long long)S.c[1] + vz * (long long)S.c[2];
+    // dominant axis a; the two others b, c in index order
+    const int a = S.dt[0] <= S.dt[1] ? (S.dt[0] <= S.dt[2] ? 0 : 2) : (S.dt[1] <= S.dt[2] ? 1 : 2);
+    const bool a0 = a == 0, a1 = a == 1, a2 = a == 2;
+    const float dta = a0 ? S.dt[0] : (a1 ? S.dt[1] : S.dt[2]);
+    const float dtb = a0 ? S.dt[1] : S.dt[0], dtc = a2 ? S.dt[1] : S.dt[2];
+    if (P.dda_legacy || len < 6.0f * dta || fminf(dtb, dtc) < 4.0f * dta) {
+        // ---- voxel walk
+        int i = S.c[0], j = S.c[1], k = S.c[2];
+        const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
+        float tx = S.t[0], ty = S.t[1], tz = S.t[2];
+        const float dtx = S.dt[0], dty = S.dt[1], dtz = S.dt[2];
+        float t = 0.f;
+        // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
+        const long long svx = sx, svy = sy > 0 ? vy : -vy, svz = sz > 0 ? vz : -vz;
+        float* cell = P.jmean + off;
+        for (;;) {
+            const float tn = fminf(tx, fminf(ty, tz));
+            if (tn >= len) {
+                atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
+                break;
+            }
+            atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
+            t = tn;
+            bool out;  // (unsigned)index >= n  <=>  index < 0 or index >= n
+            if (tx <= ty && tx <= tz) { i += sx; cell += svx; tx += dtx; out = (unsigned)i >= (unsigned)P.nxg; }
+            else if (ty <= tz)        { j += sy; cell += svy; ty += dty; out = (unsigned)j >= (unsigned)P.nyg; }
+            else                      { k += sz; cell += svz; tz += dtz; out = (unsigned)k >= (unsigned)P.nzg; }
+            if (out) break;  // :437-440
         }
-        if (P.dda_plain) atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
-        else deposit(cell, 0, fmaxf(tn - t, 0.f) * weight);
-        t = tn;
-        // (unsigned)index >= n  <=>  index < 0 or index >= n
-        if (tx <= ty && tx <= tz) { i += sx; cell += svx; tx += dtx; out = (unsigned)i >= (unsigned)P.nxg; }
-        else if (ty <= tz)        { j += sy; cell += svy; ty += dty; out = (unsigned)j >= (unsigned)P.nyg; }
-        else                      { k += sz; cell += svz; tz += dtz; out = (unsigned)k >= (unsigned)P.nzg; }
-        if (out) break;  // :437-440
+        return;
     }
-    return out;
+    // ---- run walk
+    float ta = a0 ? S.t[0] : (a1 ? S.t[1] : S.t[2]);
+    int ia = a0 ? S.c[0] : (a1 ? S.c[1] : S.c[2]);
+    const int na = a0 ? P.nxg : (a1 ? P.nyg : P.nzg);
+    const float da = a0 ? dx : (a1 ? dy : dz);
+    const long long stra = a0 ? 1ll : (a1 ? vy : vz);
+    float tb = a0 ? S.t[1] : S.t[0], tc = a2 ? S.t[1] : S.t[2];
+    int ib = a0 ? S.c[1] : S.c[0], ic = a2 ? S.c[1] : S.c[2];
+    const int nb = a0 ? P.nyg : P.nxg, nc = a2 ? P.nyg : P.nzg;
+    const float db = a0 ? dy : dx, dc = a2 ? dy : dz;
+    const long long strb = a0 ? vy : 1ll, strc = a2 ? vy : vz;
+    const bool fwd = da > 0.f;
+    const long long sva = fwd ? stra : -stra, svb = db > 0.f ? strb : -strb, svc = dc > 0.f ? strc : -strc;
+    const int sb = db > 0.f ? 1 : -1, sc_ = dc > 0.f ? 1 : -1;
+    long long* const D = a0 ? P.jdiff[0] : (a1 ? P.jdiff[1] : P.jdiff[2]);
+    const float fix = (a0 ? P.jfix[0] : (a1 ? P.jfix[1] : P.jfix[2])) * weight;
+    float t = 0.f;
+    bool used = false;
+    for (;;) {
+        const float tcol = fminf(tb, tc);        // the ray leaves this column (or never: BIG)
+        const float tend = fminf(tcol, len);
+        // faces of axis a crossed before tend: at ta + j dta, j = 0 .. m-1
+        int m = 0;
+        if (ta < tend) {
+            m = (int)fminf((tend - ta) / dta, 1.0e9f) + 1;
+            if (fmaf((float)(m - 1), dta, ta) >= tend) --m;          // rounding of the quotient, one face either way
+            else if (fmaf((float)m, dta, ta) < tend) ++m;
+        }
+        const int room = fwd ? na - 1 - ia : ia;  // faces that can be crossed without leaving the grid
+        const bool leave = m > room;
+        if (leave) m = room;
+        if (m == 0) {
+            atomicAdd(P.jmean + off, fmaxf((leave ? ta : tend) - t, 0.f) * weight);
+        } else {
+            const float p_in = fmaxf(ta - t, 0.f);
+            // the last voxel of a run that leaves the grid is crossed whole
+            const float p_out = leave ? dta : fmaxf(tend - fmaf((float)(m - 1), dta, ta), 0.f);
+            if (m < 3) {  // 2 or 3 voxels: direct deposits are no more atomics than the range update
+                atomicAdd(P.jmean + off, p_in * weight);
+                if (m == 2) atomicAdd(P.jmean + off + sva, dta * weight);
+                atomicAdd(P.jmean + off + (long long)m * sva, p_out * weight);
+            } else {
+                const long long qc = __float2ll_rn(dta * fix);
+                const long long q_in = __float2ll_rn(p_in * fix), q_out = __float2ll_rn(p_out * fix);
+                const long long q_lo = fwd ? q_in : q_out, q_hi = fwd ? q_out : q_in;
+                long long* lo = D + (fwd ? off : off - (long long)m * stra);
+                const int hi_idx = fwd ? ia + m : ia;
+                red_i64(lo, q_lo);
+                red_i64(lo + stra, qc - q_lo);
+                red_i64(lo + (long long)m * stra, q_hi - qc);
+                if (hi_idx + 1 < na) red_i64(lo + (long long)(m + 1) * stra, -q_hi);
+                used = true;
+            }
+            ia += fwd ? m : -m;
+            off += (long long)m * sva;
+            ta = fmaf((float)m, dta, ta);
+        }
+        if (leave || tcol >= len) break;  // :437-440 / end of the segment
+        t = tend;
+        bool out;
+        if (tb <= tc) { ib += sb; off += svb; tb += dtb; out = (unsigned)ib >= (unsigned)nb; }
+        else          { ic += sc_; off += svc; tc += dtc; out = (unsigned)ic >= (unsigned)nc; }
+        if (out) break;
+    }
+    if (used) P.jdiff_used[a] = 1u;
+}
+
+// Prefix sum of one difference grid along its axis, added to jmean; the grid is cleared on the way.
+//   AXIS 0 (x, contiguous): one warp per row, 32 entries per step (shuffle scan + carry)
+//   AXIS 1 / 2: one thread per (x, z) / (x, y) line, neighbouring threads on neighbouring x: coalesced
+template <int AXIS>
+__global__ void jdiff_scan_kernel(long long* __restrict__ D, float* __restrict__ jmean, const unsigned int* used, int nx, int ny, int nz, double unit) {
+    if (!used[AXIS]) return;
+    if (AXIS == 0) {
+        const int lane = threadIdx.x & 31;
+        const long long rows = (long long)ny * nz, warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5,
+                        nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+        for (long long r = warp0; r < rows; r += nwarp) {
+            long long carry = 0;
+            for (int i0 = 0; i0 < nx; i0 += 32) {
+                const int i = i0 + lane;
+                long long v = i < nx ? D[r * nx + i] : 0ll;
+                const bool nz_any = __any_sync(0xffffffffu, v != 0ll);
+                if (nz_any && i < nx) D[r * nx + i] = 0ll;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                v += carry;
+                if (i < nx && v != 0ll) jmean[r * nx + i] += (float)((double)v * unit);
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+    } else {
+        const long long lines = (long long)nx * (AXIS == 1 ? nz : ny), n = AXIS == 1 ? ny : nz;
+        const long long stride = AXIS == 1 ? (long long)nx : (long long)nx * ny;
+        for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < lines; l += (long long)gridDim.x * blockDim.x) {
+            const long long base = AXIS == 1 ? (l % nx) + (l / nx) * (long long)nx * ny : l;
+            long long run = 0;
+            for (long long k = 0; k < n; ++k) {
+                const long long at = base + k * stride;
+                const long long v = D[at];
+                if (v != 0ll) { D[at] = 0ll; run += v; }
+                if (run != 0ll) jmean[at] += (float)((double)run * unit);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ detectors
@@ -555,7 +701,7 @@ __device__ __forceinline__ bool det_plane_hit(const DevDet& D, const float4 pl, 
 __device__ __forceinline__ int det_bin_circle(const DevDet& D, float r) {  // :147-164
     return r <= D.q[0] ? min(nint_pos(r / D.q[1]) + 1, D.nbins) : 0;
 }
-__device__ __noinline__ int det_bin_annulus_fibre(const DevDet* Dp, float r, float denom) {
+static __device__ __noinline__ int det_bin_annulus_fibre(const DevDet* Dp, float r, float denom) {
     const DevDet& D = *Dp;
     if (D.kind == 2) {  // annulus :212-244: not inside r1, inside r2
         if (r <= D.q[0] || !(r <= D.q[1])) return 0;
@@ -579,7 +725,7 @@ __device__ __noinline__ int det_bin_annulus_fibre(const DevDet* Dp, float r, flo
     return min(nint_pos(fabsf(radius) / D.q[10]) + 1, D.nbins);
 }
 // camera :447-469 + record_hit_2D_sub (no pointSep test, bins the segment START, adds 1)
-__device__ __noinline__ int det_bin_camera(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2) {
+static __device__ __noinline__ int det_bin_camera(const DevDet* Dp, float s0, float s1, float s2, float d0, float d1, float d2) {
     const DevDet& D = *Dp;
     const float dn = d0 * D.dir[0] + d1 * D.dir[1] + d2 * D.dir[2];
     const float tt = ((D.pos[0] - s0) * D.dir[0] + (D.pos[1] - s1) * D.dir[1] + (D.pos[2] - s2) * D.dir[2]) / dn;
@@ -646,7 +792,7 @@ struct Emitted {
     float x, y, z, dx, dy, dz;
     bool ok;
 };
-__device__ __noinline__ Emitted emit_packet(const KParams& P, float u0, float u1, float u2) {  // out of line: all source kinds live here
+static __device__ __noinline__ Emitted emit_packet(const KParams& P, float u0, float u1, float u2) {  // out of line: all source kinds live here
     float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
     Emitted e;
     e.ok = emit_packet_v(P, u0, u1, u2, pos, dir);
@@ -772,7 +918,7 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
 #endif
 // optional per-packet record of smcrt_trace_packets (out of line: cold)
-__device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, uint32_t ev, int steps,
+static __device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, uint32_t ev, int steps,
                                            float x, float y, float z) {
     const long long k = (long long)(pid - P.id_offset);
     P.out_fate[k] = fate;
@@ -870,7 +1016,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             w[14 * B] = (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u) | (ev << 11);
             w[15 * B] = (uint32_t)steps | ((uint32_t)bounces << 21);
             w[16 * B] = (uint32_t)pid; w[17 * B] = (uint32_t)(pid >> 32);
-            if (HASDET) { w[18 * B] = __float_as_uint(sx); w[19 * B] = __float_as_uint(sy); w[20 * B] = __float_as_uint(sz); }
+            if (HASDET || PATHLEN) { w[18 * B] = __float_as_uint(sx); w[19 * B] = __float_as_uint(sy); w[20 * B] = __float_as_uint(sz); }
             if (P.survival) w[21 * B] = __float_as_uint(weight);
             __syncthreads();  // (B) all slots written
             if (all_done) break;
@@ -888,7 +1034,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             ev = fl >> 11;
             steps = (int)(r[15 * B] & 0x1fffffu); bounces = (int)(r[15 * B] >> 21);
             pid = (unsigned long long)r[16 * B] | ((unsigned long long)r[17 * B] << 32);
-            if (HASDET) { sx = __uint_as_float(r[18 * B]); sy = __uint_as_float(r[19 * B]); sz = __uint_as_float(r[20 * B]); }
+            if (HASDET || PATHLEN) { sx = __uint_as_float(r[18 * B]); sy = __uint_as_float(r[19 * B]); sz = __uint_as_float(r[20 * B]); }
             if (P.survival) weight = __uint_as_float(r[21 * B]);
             qs = (state == ST_BND_PROBE || state == ST_CROSS) ? dstep : 0.f;
             xiter = go_tail ? XTAIL : xiter + 1u;
@@ -1155,6 +1301,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     }
 }
 
+#ifndef SMCRT_TRACE_TU  // everything below is compiled into engine.cu only (trace_inst.cu holds the trace-kernel instantiations)
 // ------------------------------------------------------------------------------------------------ culling-grid set-up
 // One thread per (cell, top-level SDF): FP64 distance at the cell centre.  The host turns the matrix into candidate lists.
 __global__ void cull_eval_kernel(const __grid_constant__ KParams P, long long n_pairs, double lox, double loy, double loz, double dx, double dy,
@@ -1297,5 +1444,17 @@ __global__ void red_bench_kernel(float* grid, long long nvox, long long stride, 
         atomicAdd(grid + v, 1.0f);
     }
 }
+
+#endif  // SMCRT_TRACE_TU
+
+// Kernel variants: scheduling (one packet per thread / + compaction behind CTA barriers / slot queues) x register
+// budget (2, 3 or 4 resident CTAs per SM = 128, 80 or 64 registers).  The instantiations live in four translation units
+// (trace_inst.cu compiled once per <PATHLEN, HASDET> pair, in parallel); engine.cu gets the kernels through these pickers.
+enum : int { SCHED_PLAIN = 0, SCHED_COMPACT = 1, SCHED_QUEUED = 2 };
+typedef void (*trace_kernel_t)(const KParams);
+trace_kernel_t pick_kernel_pl0_hd0(int sched, int mb, bool need, bool simple, bool lean);
+trace_kernel_t pick_kernel_pl0_hd1(int sched, int mb, bool need, bool simple, bool lean);
+trace_kernel_t pick_kernel_pl1_hd0(int sched, int mb, bool need, bool simple, bool lean);
+trace_kernel_t pick_kernel_pl1_hd1(int sched, int mb, bool need, bool simple, bool lean);
 
 }  // namespace smcrt_dev

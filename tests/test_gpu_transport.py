@@ -347,3 +347,47 @@ def test_kernel_variants_trace_identical_histories_with_fresnel_events(engine, o
         assert a["counters"][k] == b["counters"][k], k
     assert a["counters"]["lost"] == 0 and a["counters"]["bounces"] > n // 2
     assert np.array_equal(a["absorb"], b["absorb"])
+
+
+@pytest.mark.parametrize("deck,n,tol", [("validation1.toml", 20_000, 2e-4), ("sphere.toml", 100_000, 2e-5), ("skin_b200.toml", 50_000, 2e-5),
+                                        ("scat_test.toml", 20_000, 2e-5), ("lens.toml", 50_000, 2e-5)])
+def test_pathlength_run_walker_equals_voxel_walker(engine, oracle, smcrt, monkeypatch, deck, n, tol):
+    """-Dpathlength deposits (inttau2.f90:417-441).  The run walker issues a straight piece as range updates into fixed-point
+    difference grids (4 atomics per run of voxels along the dominant axis) and prefix-sums them before the grid is read; the
+    legacy walker issues one red.global.add.f32 per voxel crossed, as the reference's loop does.  Same packets, same streams:
+    the two fluence grids agree voxel by voxel to float32 accumulation accuracy.  (tol: every packet of the slab's pencil beam
+    adds the same 6e-5 to the same 333 voxels; the voxel walker's float32 sums round each of those adds to ~1e-4 relative, the
+    fixed-point range updates of the run walker do not round at all.)"""
+    cfg = smcrt.Config.load(RES / deck)
+    mode = A.TALLY_PATHLENGTH
+    engine.apply(cfg)
+    engine.run(n, 31, tally_mode=mode)
+    a = engine.fetch(jmean=True, absorb=False)
+    monkeypatch.setenv("SMCRT_DDA_LEGACY", "1")
+    e2 = smcrt.Engine(1)
+    try:
+        e2.apply(cfg)
+        e2.run(n, 31, tally_mode=mode)
+        b = e2.fetch(jmean=True, absorb=False)
+    finally:
+        e2.close()
+    ja, jb = a["jmean"].astype(np.float64), b["jmean"].astype(np.float64)
+    assert a["counters"]["nscatt"] == b["counters"]["nscatt"] and a["counters"]["lost"] == b["counters"]["lost"]
+    assert jb.sum() > 0
+    assert abs(ja.sum() - jb.sum()) < tol * jb.sum()
+    # voxel by voxel: float32 red order / fixed-point rounding only (a face time rounds differently for a handful of voxels:
+    # the two walkers then split the same length differently between two neighbours)
+    err = np.abs(ja - jb)
+    scale = np.maximum(jb, 1e-3 * jb.max())
+    assert np.quantile(err / scale, 0.999) < 1e-3
+    assert err.sum() < 1e-3 * jb.sum()
+    # z-profile (sum over x, y) is insensitive to the neighbour splits
+    za, zb = ja.sum(axis=(0, 1)), jb.sum(axis=(0, 1))
+    assert np.abs(za - zb).max() < 10 * tol * zb.max()
+    # accumulate: a second run on top, then reset -> zero
+    engine.run(n, 31, id_offset=n, tally_mode=mode)
+    c = engine.fetch(jmean=True, absorb=False)["jmean"].astype(np.float64)
+    assert c.sum() > 1.9 * ja.sum()
+    engine.run(1000, 5, tally_mode=mode)  # deposits left in the difference grids are dropped by the reset
+    engine.reset_tallies()
+    assert engine.fetch(jmean=True, absorb=False)["jmean"].sum() == 0

@@ -237,6 +237,12 @@ int smcrt_trace_packets(smcrt_ctx* ctx, int64_t n, uint64_t seed, int64_t id_off
  * with CTA-level event compaction (2 CTAs), 4..5 = queue-scheduled (packets in shared-memory slots, warps pull batches of one
  * state) at 2/3 CTAs; -1 = not timed yet (variant 1 is used).  Environment override: SMCRT_VARIANT_FORCE=0..5. */
 int smcrt_kernel_variant(const smcrt_ctx* ctx, int tally_mode);
+/* -Dpathlength runs (update_grids, inttau2.f90:408-445): how the straight segments of the current scene are deposited.
+ * 0 = the trace kernels record them and a deposit kernel walks the voxels, 1 = the trace kernels walk them inline, -1 = not timed
+ * yet (the first large path-length run of a scene times both on slices of its own packets).  And the measured number of straight
+ * segments per packet, which sizes the launches against the segment buffer (0 = not measured yet). */
+int smcrt_segment_mode(const smcrt_ctx* ctx);
+double smcrt_segments_per_packet(const smcrt_ctx* ctx);
 /* Batched point sources in ONE launch: the body of the escape-function drivers cart_calc_escape_sym / cyl_calc_escape_sym
  * (src/kernelsMod.f90:533-642, 959-1071), which call run_MCRT once per symmetry-grid cell with set_photon(cell centre).
  * pos: n_src x 3 emission points (already rotated/shifted by the caller, :576-585).  Per source, as in the reference:

@@ -373,6 +373,15 @@ class Engine:
         """-1 until the first large run has timed the candidates; then 0..5 (smcrt_kernel_variant)."""
         return int(self._L.smcrt_kernel_variant(self._h, int(tally_mode)))
 
+    @property
+    def segment_mode(self):
+        """-Dpathlength deposits of this scene: 0 = deposit kernel, 1 = inline walks, -1 = not timed yet (smcrt_segment_mode)."""
+        return int(self._L.smcrt_segment_mode(self._h))
+
+    @property
+    def segments_per_packet(self):
+        return float(self._L.smcrt_segments_per_packet(self._h))
+
     def bench_red(self, pattern, span=333, n_ops=1 << 30):
         """red.global.add.f32 operations per second on this context's path-length grid (smcrt_bench_red)."""
         out = C.c_double(0.0)

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -117,6 +118,11 @@ struct DeviceState {
     unsigned int* jdiff_used = nullptr;
     bool jdiff_dirty = false;
     long long jdiff_packets = 0;
+    // segment buffer of the path-length mode: seg_records records of 32 bytes, split evenly between the CTAs of a trace launch
+    float4* seg_buf = nullptr;
+    unsigned int* seg_count = nullptr;   // [SEG_MAX_SHARES]
+    unsigned long long* seg_total = nullptr;
+    size_t seg_records = 0;
     unsigned long long* det_bins = nullptr;
     unsigned long long* counters = nullptr;  // C_COUNT + 1 (work counter last) + 2 x 8 time stamps of the variant trial
     // sparse read-back scratch (smcrt_fetch): device pair list + cursor, pinned host mirror
@@ -174,6 +180,8 @@ struct smcrt_ctx {
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
     bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
+    int seg_inline = -1;        // path-length mode: 1 = the trace kernels walk their segments themselves, 0 = recorded + deposit kernel, -1 = not timed yet
+    double seg_per_packet = 0;  // measured straight segments per packet of the current scene (path-length mode); 0 = not measured
     bool dda_legacy = false;  // SMCRT_DDA_LEGACY at smcrt_create: path-length deposits one red per voxel crossed (A/B switch, tests)
     // kernel-variant choice per tally configuration [pathlength][detectors]: 0 = not timed yet, else 1 + index into VARIANTS
     int tuned_mb[2][2] = {{0, 0}, {0, 0}};
@@ -258,7 +266,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.stream) cudaStreamSynchronize(D.stream);
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
-        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used);
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
         if (D.ev0) cudaEventDestroy(D.ev0);
@@ -474,7 +482,7 @@ extern "C" int smcrt_set_scene(smcrt_ctx* c, int n_nodes, const int32_t* kind, c
         uint64_t h = fnv1a(1469598103934665603ull, c->primsD.data(), c->primsD.size() * sizeof(DevPrimD));
         h = fnv1a(h, c->progD.data(), c->progD.size() * sizeof(DevInstrD));
         h = fnv1a(h, c->tops.data(), c->tops.size() * sizeof(DevTop));
-        if (h != c->scene_hash) std::memset(c->tuned_mb, 0, sizeof c->tuned_mb);
+        if (h != c->scene_hash) { std::memset(c->tuned_mb, 0, sizeof c->tuned_mb); c->seg_per_packet = 0; c->seg_inline = -1; }
         c->scene_hash = h;
     }
     c->opt_mus.assign(mus, mus + n_top); c->opt_mua.assign(mua, mua + n_top);
@@ -839,36 +847,50 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
         P.jfix[a] = (float)(268435456.0 /* 2^28 */ * nn[a] / (2.0 * c->gmax[a]));
     }
     P.jdiff_used = D.jdiff_used;
+    P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     P.max_steps = (int)std::min<long long>(c->max_steps, 1900000ll);  // the compaction step packs sweep count and event index (<= sweeps + 100000 emit retries) into 21 bits each
     return 0;
 }
 
-static int launch_kernel(trace_kernel_t kern, const KParams& P, DeviceState& D, int smem_bytes, bool dry) {
+constexpr int SEG_MAX_SHARES = 148 * 8;  // CTAs of a trace launch (<= SMs x resident CTAs)
+static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D, int smem_bytes, bool dry, bool seg_inline) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
     if (per_sm < 1) return set_err("scene does not fit in shared memory (%d bytes per CTA)", smem_bytes);
     // persistent grid: every SM full, no more; never more threads than packets
     long long blocks = (long long)D.sm_count * per_sm;
-    const long long need = (P.nphotons + SMCRT_BLOCK - 1) / SMCRT_BLOCK;
+    const long long need = (P0.nphotons + SMCRT_BLOCK - 1) / SMCRT_BLOCK;
     if (blocks > need) blocks = std::max<long long>(need, 1);
     if (dry) return 0;  // the attribute/occupancy queries above have loaded the kernel (lazy module loading)
+    KParams P = P0;
+    const bool pathlen = (P.tally_mode & SMCRT_TALLY_PATHLENGTH) != 0;
+    if (pathlen) {
+        if (blocks > SEG_MAX_SHARES) return set_err("trace launch of %lld CTAs exceeds the segment buffer's %d shares", blocks, SEG_MAX_SHARES);
+        // seg_cap = 0: every segment is walked by the lane that made it (the fallback of a full share, for all of them)
+        P.seg_cap = seg_inline ? 0u : (unsigned int)std::min<size_t>(D.seg_records / (size_t)blocks, 0x7fffffffu);
+    }
     kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, D.stream>>>(P);
     CU(cudaGetLastError());
+    if (pathlen && !seg_inline) {  // walk what the launch recorded, then clear the shares for the next launch
+        deposit_segments_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(P, (int)blocks);
+        clear_segment_counts_kernel<<<1, 256, 0, D.stream>>>(D.seg_count, (int)blocks);
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 struct Variant { int sched; int mb; };
 constexpr int NVAR = 6;
 static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
-static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false) {
+static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false, bool seg_inline = false) {
     const Variant v = VARIANTS[var];
     const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
     // LEAN: nothing optional asked of this run (no per-packet records, diagnostics, batched sources, survival biasing)
     const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival;
     trace_kernel_t k = pl ? (hd ? pick_kernel_pl1_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl1_hd0(v.sched, v.mb, need, simple, lean))
                           : (hd ? pick_kernel_pl0_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl0_hd0(v.sched, v.mb, need, simple, lean));
-    return launch_kernel(k, P, D, smem_bytes[v.sched], dry);
+    return launch_kernel(k, P, D, smem_bytes[v.sched], dry, seg_inline);
 }
 
 // Path-length deposits waiting in the difference grids -> jmean (prefix sums along each touched axis; the grids come back zero).
@@ -893,7 +915,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
                          float* out_pos, int* out_sweeps = nullptr, float* out_dbg = nullptr) {
     KParams P;
     fill_params(c, D, P);
-    P.nphotons = nphotons; P.id_offset = (unsigned long long)id_offset;
+    P.nphotons = nphotons; P.id_offset = (unsigned long long)id_offset; P.rec_id0 = P.id_offset;
     P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
     P.tally_mode = tally_mode; P.survival = survival ? 1 : 0;
     P.threshold = (float)(threshold > 0 ? threshold : 0.01);  // THRESHOLD, src/constants.f90:28
@@ -901,8 +923,8 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps; P.out_dbg = out_dbg;
     P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
     CU(cudaSetDevice(D.dev));
-    if ((tally_mode & SMCRT_TALLY_PATHLENGTH) && !P.dda_legacy) {
-        if (!D.jdiff[0]) {  // first path-length run on this grid
+    if (tally_mode & SMCRT_TALLY_PATHLENGTH) {
+        if (!D.jdiff[0] && !P.dda_legacy) {  // first path-length run on this grid
             size_t nv;
             n_voxels(c, &nv);
             if (!D.jdiff_used) { CU(cudaMalloc(&D.jdiff_used, 16)); CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream)); }
@@ -913,14 +935,28 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
             }
             P.jdiff_used = D.jdiff_used;
         }
+        if (!D.seg_buf) {
+            // a quarter of the free memory, 32 MB .. 6 GB (a record is 32 bytes; a packet of sphere.toml makes 3, one of skin 40)
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            size_t bytes = std::min<size_t>(std::max<size_t>(free_b / 4, 32ull << 20), 6ull << 30);
+            if (const char* e = getenv("SMCRT_SEG_MB")) bytes = std::max<size_t>((size_t)atoll(e), 1) << 20;
+            CU(cudaMalloc(&D.seg_buf, bytes));
+            D.seg_records = bytes / 32;
+            CU(cudaMalloc(&D.seg_count, sizeof(unsigned int) * SEG_MAX_SHARES));
+            CU(cudaMemsetAsync(D.seg_count, 0, sizeof(unsigned int) * SEG_MAX_SHARES, D.stream));
+            CU(cudaMalloc(&D.seg_total, 8));
+            CU(cudaMemsetAsync(D.seg_total, 0, 8, D.stream));
+            P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
+        }
         // an entry of a difference grid holds < 2^63 for 2^32 full-chord deposits (2^28 units each, weights <= 1/chance)
         if (D.jdiff_packets + nphotons > (1ll << 32)) { int rc = scan_pathlength(c, D); if (rc) return rc; }
-        D.jdiff_dirty = true;
-        D.jdiff_packets += nphotons;
+        if (!P.dda_legacy) { D.jdiff_dirty = true; D.jdiff_packets += nphotons; }
     }
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
-    const int smem_plain = c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0);
-    P.xchg_off = (smem_plain + 15) & ~15;
+    P.seg_off = (c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0) + 15) & ~15;  // the CTA's segment counter (path-length mode)
+    const int smem_plain = P.seg_off + 16;
+    P.xchg_off = smem_plain;
     const int smem_bytes[3] = {smem_plain, P.xchg_off + 64 + XCHG_WORDS * 4 * SMCRT_BLOCK, P.xchg_off + queued_smem_bytes(SMCRT_BLOCK)};
     CU(cudaEventRecord(D.ev0, D.stream));
     const bool pl = (tally_mode & SMCRT_TALLY_PATHLENGTH) != 0, hd = !c->dets.empty();
@@ -936,10 +972,47 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     else if (force_mb) forced = std::min(std::max(atoi(force_mb), 2), 4) - 2;
     int var = forced >= 0 ? forced : (c->tuned_mb[pl][hd] ? c->tuned_mb[pl][hd] - 1 : 1);
     if (VARIANTS[var].sched != SCHED_PLAIN && !compact_ok) var = 1;
-    int n_launch = 1;
+    int n_launch = 0;
+    long long chunk_max = std::numeric_limits<long long>::max();
+    if (pl) {
+        static const char* force_inline = getenv("SMCRT_SEG_INLINE");  // A/B switch: 0 = deposit kernel, 1 = inline walks
+        if (force_inline) c->seg_inline = atoi(force_inline) ? 1 : 0;
+        if ((c->seg_per_packet <= 0 || (c->seg_inline < 0 && P.nphotons >= (1ll << 23))) && P.nphotons > 0) {
+            // First path-length run of this scene: trace a small chunk and count the segments it makes.  A large run also times
+            // a second chunk with the segments walked inline: which is faster depends on the scene (the pencil beam of the slab
+            // scene makes few, cheap range updates whose atomics hide behind the transport code when issued inline; walking the
+            // voxels of refracted rays inline starves the kernel's instruction cache), and later runs of the scene use the winner.
+            const bool time_both = c->seg_inline < 0 && P.nphotons >= (1ll << 23);
+            const long long n_cal = time_both ? std::min<long long>(std::max<long long>(P.nphotons / 16, 1ll << 20), 1ll << 22) : std::min<long long>(P.nphotons, 1ll << 18);
+            { int rc = launch_variant(pl, hd, var, P, D, smem_bytes, true); if (rc) return rc; }  // load the kernel outside the brackets
+            CU(cudaMemsetAsync(D.seg_total, 0, 8, D.stream));
+            for (int pass = 0; pass < (time_both ? 2 : 1); ++pass) {
+                KParams Q = P;
+                Q.nphotons = n_cal;
+                CU(cudaEventRecord(D.tune_ev[pass], D.stream));
+                int rc = launch_variant(pl, hd, var, Q, D, smem_bytes, false, pass == 1 || c->seg_inline == 1);
+                if (rc) return rc;
+                P.nphotons -= n_cal; P.id_offset += (unsigned long long)n_cal;
+                CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
+                ++n_launch;
+            }
+            CU(cudaEventRecord(D.tune_ev[time_both ? 2 : 1], D.stream));
+            unsigned long long made = 0;
+            CU(cudaMemcpyAsync(&made, D.seg_total, 8, cudaMemcpyDeviceToHost, D.stream));
+            CU(cudaStreamSynchronize(D.stream));
+            c->seg_per_packet = std::max((double)made / (double)(n_cal * (time_both ? 2 : 1)), 0.25);
+            if (time_both) {
+                float t_rec = 0, t_inl = 0;
+                CU(cudaEventElapsedTime(&t_rec, D.tune_ev[0], D.tune_ev[1]));
+                CU(cudaEventElapsedTime(&t_inl, D.tune_ev[1], D.tune_ev[2]));
+                c->seg_inline = t_inl < t_rec ? 1 : 0;
+            }
+        }
+        if (c->seg_inline != 1) chunk_max = std::max<long long>(1ll << 16, (long long)((double)D.seg_records / (1.25 * std::max(c->seg_per_packet, 0.25))));
+    }
     const long long TUNE_MIN = 8ll << 20;
-    if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && nphotons >= TUNE_MIN && D.tuning < 0) {
-        const long long slice = std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 23);
+    if (forced < 0 && compact_ok && !c->tuned_mb[pl][hd] && &D == &c->devs[0] && !out_fate && P.nphotons >= TUNE_MIN && D.tuning < 0) {
+        const long long slice = std::min(std::min<long long>(std::max<long long>(nphotons / 64, 1ll << 20), 1ll << 23), chunk_max);
         for (int k = 0; k < NVAR; ++k) {  // load the kernels first: the load would otherwise sit inside the event brackets
             int rc = launch_variant(pl, hd, k, P, D, smem_bytes, true);
             if (rc) return rc;
@@ -950,20 +1023,33 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
             Q.nphotons = slice; Q.id_offset = P.id_offset + (unsigned long long)(k * slice);
             Q.tstamp = D.counters + C_COUNT + 1 + 2 * k;
             CU(cudaEventRecord(D.tune_ev[k], D.stream));
-            int rc = launch_variant(pl, hd, k, Q, D, smem_bytes);
+            int rc = launch_variant(pl, hd, k, Q, D, smem_bytes, false, c->seg_inline == 1);
             if (rc) return rc;
             CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
         }
         CU(cudaEventRecord(D.tune_ev[NVAR], D.stream));
         D.tuning = (pl ? 2 : 0) | (hd ? 1 : 0);
         P.nphotons -= NVAR * slice; P.id_offset += (unsigned long long)(NVAR * slice);
-        n_launch = NVAR + 1;
+        n_launch += NVAR;
     }
-    int rc = launch_variant(pl, hd, var, P, D, smem_bytes);
-    if (rc) return rc;
+    // Path-length mode: a launch may produce no more segments than the segment buffer holds (a CTA whose share is full walks its
+    // segments inline: correct, but slow), so the run is cut into chunks of packets sized from the scene's measured segments per
+    // packet, with a margin for the spread between CTAs.
+    long long left = P.nphotons;
+    while (left > 0) {
+        const long long chunk = std::min(left, chunk_max);
+        KParams Q = P;
+        Q.nphotons = chunk;
+        int rc = launch_variant(pl, hd, var, Q, D, smem_bytes, false, c->seg_inline == 1);
+        if (rc) return rc;
+        P.id_offset += (unsigned long long)chunk;
+        left -= chunk;
+        ++n_launch;
+        if (left > 0) CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
+    }
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
-    c->launches += n_launch;
+    c->launches += (pl ? 3 : 1) * n_launch;
     c->touched_modes |= tally_mode;
     return 0;
 }
@@ -1051,6 +1137,8 @@ extern "C" int smcrt_kernel_variant(const smcrt_ctx* c, int tally_mode) {
     if (!c) return -1;
     return c->tuned_mb[(tally_mode & SMCRT_TALLY_PATHLENGTH) ? 1 : 0][c->dets.empty() ? 0 : 1] - 1;
 }
+extern "C" int smcrt_segment_mode(const smcrt_ctx* c) { return c ? c->seg_inline : -1; }
+extern "C" double smcrt_segments_per_packet(const smcrt_ctx* c) { return c ? c->seg_per_packet : 0.0; }
 extern "C" double smcrt_last_run_ms(const smcrt_ctx* c) { return c ? c->last_ms : 0.0; }
 extern "C" int64_t smcrt_launch_count(const smcrt_ctx* c) { return c ? c->launches : 0; }
 
@@ -1099,7 +1187,7 @@ static int zero_device_tallies(smcrt_ctx* c, DeviceState& D) {
     size_t nv;
     n_voxels(c, &nv);
     CU(cudaSetDevice(D.dev));
-    if (D.jdiff_dirty) {  // deposits waiting in the difference grids are dropped with the rest
+    if (D.jdiff_dirty && D.jdiff[0]) {  // deposits waiting in the difference grids are dropped with the rest
         for (int a = 0; a < 3; ++a) CU(cudaMemsetAsync(D.jdiff[a], 0, nv * sizeof(long long), D.stream));
         CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream));
         D.jdiff_dirty = false; D.jdiff_packets = 0;

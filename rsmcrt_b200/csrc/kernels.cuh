@@ -62,6 +62,7 @@ struct KParams {
     unsigned long long* tstamp;    // variant trial only: [0] = %globaltimer at kernel start, [1] = when the last packet id is claimed
     long long nphotons;
     unsigned long long id_offset;
+    unsigned long long rec_id0;  // first packet id of the RUN (a run may be several launches): per-packet records are indexed by pid - rec_id0
     uint32_t seed_lo, seed_hi;
     int tally_mode, survival;
     float threshold, chance;
@@ -73,6 +74,14 @@ struct KParams {
     long long* jdiff[3];
     float jfix[3];
     unsigned int* jdiff_used;
+    // -Dpathlength: the trace kernels do not walk voxels, they RECORD the straight segments; deposit_segments_kernel
+    // walks them.  Every CTA owns seg_cap records of seg_buf (2 x float4 each: start + length, direction + weight) and counts
+    // them in shared memory (byte offset seg_off of its dynamic shared memory); the count goes to seg_count[blockIdx.x] at the end.
+    float4* seg_buf;
+    unsigned int* seg_count;
+    unsigned int seg_cap;
+    int seg_off;
+    unsigned long long* seg_total;  // all segments produced (recorded or, when a CTA's share was full, walked inline)
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
     int* out_nscatt;
@@ -668,6 +677,70 @@ __global__ void jdiff_scan_kernel(long long* __restrict__ D, float* __restrict__
     }
 }
 
+// The trace kernels' side of -Dpathlength: append the segment to the CTA's share of the segment buffer; if the share is full (the
+// host sizes the packets per launch from the scene's measured segments per packet, with a margin) walk it here and now.
+__device__ __forceinline__ void record_segment(const KParams& P, unsigned int* seg_cnt, float sx, float sy, float sz, float ux, float uy, float uz,
+                                               float px, float py, float pz, float weight) {
+    const float lx = px - sx, ly = py - sy, lz = pz - sz;
+    const float l2 = lx * lx + ly * ly + lz * lz;
+    if (!(l2 > 0.f)) return;
+    const float len = sqrtf(l2);
+    const unsigned int at = atomicAdd(seg_cnt, 1u);
+    if (at < P.seg_cap) {
+        float4* r = P.seg_buf + 2ull * ((unsigned long long)blockIdx.x * P.seg_cap + at);
+        r[0] = make_float4(sx, sy, sz, len);
+        r[1] = make_float4(ux, uy, uz, weight);
+    } else
+        walk_segment(P, sx, sy, sz, ux, uy, uz, len, weight);
+}
+
+#ifndef SMCRT_TRACE_TU  // (engine.cu only)
+// The deposit kernel: walks the recorded segments.  One warp takes 32 records of a CTA's share at a time (two coalesced 16-byte
+// loads per lane).  Segments with little work -- the free paths of a turbid medium, anything the run walker takes -- are walked
+// by their own lanes, all at once; a segment that crosses many voxels obliquely (a refracted ray through the 200^3 grid of
+// sphere.toml) is SHARED: lane j walks the j-th 32nd of it (a voxel that holds a cut point gets its length in two deposits).
+// A small kernel with a small loop: the voxel walk does not compete with the transport code for the instruction cache (in one
+// kernel the hot code was 39 KB, beyond the 32 KB L1.5 I-cache: 6 stall cycles per issue waiting for instructions).
+__global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int sh = blockIdx.x; sh < n_shares; sh += gridDim.x) {
+        const unsigned int n = min(P.seg_count[sh], P.seg_cap);
+        const float4* recs = P.seg_buf + 2ull * (unsigned long long)sh * P.seg_cap;
+        for (unsigned int base = warp * 32u; base < n; base += nwarp * 32u) {
+            const unsigned int i = base + lane;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f);
+            float work = 0.f;
+            if (i < n) {
+                a = recs[2u * i]; b = recs[2u * i + 1u];
+                // faces crossed per unit length along each axis; a segment the run walker takes only works per COLUMN change
+                const float rx = fabsf(b.x) * P.inv_vox[0], ry = fabsf(b.y) * P.inv_vox[1], rz = fabsf(b.z) * P.inv_vox[2];
+                const float rmax = fmaxf(rx, fmaxf(ry, rz)), rsum = rx + ry + rz;
+                const float rmid = fmaxf(fminf(rx, ry), fminf(fmaxf(rx, ry), rz));
+                const bool runs = !P.dda_legacy && a.w * rmax > 6.0f && rmax > 4.0f * rmid;
+                work = 1.0f + a.w * (runs ? 2.0f * (rsum - rmax) : rsum);
+            }
+            const bool share = work >= 96.0f;
+            if (work > 0.f && !share) walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
+            unsigned pend = __ballot_sync(0xffffffffu, share);
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1u;
+                const float L = __shfl_sync(0xffffffffu, a.w, src), w = __shfl_sync(0xffffffffu, b.w, src);
+                const float ax = __shfl_sync(0xffffffffu, a.x, src), ay = __shfl_sync(0xffffffffu, a.y, src), az = __shfl_sync(0xffffffffu, a.z, src);
+                const float vx = __shfl_sync(0xffffffffu, b.x, src), vy = __shfl_sync(0xffffffffu, b.y, src), vz = __shfl_sync(0xffffffffu, b.z, src);
+                const float t0 = L * ((float)lane * 0.03125f), t1 = lane == 31 ? L : L * ((float)(lane + 1) * 0.03125f);
+                walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w);
+            }
+        }
+    }
+}
+// (the shares are cleared for the next launch by a second tiny kernel: a CTA of the deposit kernel may still be reading a count)
+__global__ void clear_segment_counts_kernel(unsigned int* cnt, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cnt[i] = 0u;
+}
+
+#endif  // SMCRT_TRACE_TU
+
 // ------------------------------------------------------------------------------------------------ detectors
 // One straight segment (start, dir, length) against one detector: record_hit_1D/2D + check_hit_*
 // (src/detectors/detector_base.f90:137-163,206-235; src/detectors/detectors.f90:147-469;
@@ -920,7 +993,7 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 // optional per-packet record of smcrt_trace_packets (out of line: cold)
 static __device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, uint32_t ev, int steps,
                                            float x, float y, float z) {
-    const long long k = (long long)(pid - P.id_offset);
+    const long long k = (long long)(pid - P.rec_id0);
     P.out_fate[k] = fate;
     if (P.out_events) P.out_events[k] = fate == 3 ? -why : (int)ev;
     if (P.out_sweeps) P.out_sweeps[k] = steps;
@@ -943,6 +1016,8 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     unsigned long long* sbins = reinterpret_cast<unsigned long long*>(smem + P.blob_bytes);
+    unsigned int* seg_cnt = reinterpret_cast<unsigned int*>(smem + P.seg_off);  // PATHLEN: segments recorded by this CTA
+    if (PATHLEN && threadIdx.x == 0) *seg_cnt = 0u;
     // compaction scratch (COMPACT only): per-state totals (double buffered) and one slot of XCHG_WORDS words per thread
     uint32_t* xtot = reinterpret_cast<uint32_t*>(smem + P.xchg_off);
     uint32_t* xbuf = xtot + 16;
@@ -975,7 +1050,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 
 #include "step_macros.inc"
     for (;;) {
-#define STEP_EXIT_CHECK if ((!COMPACT || xiter == XTAIL) && __all_sync(__activemask(), state == ST_DONE)) break;
+        // every lane of the warp executes this vote in every iteration (lanes leave the loop together or not at all): full mask, so
+        // that a warp the compiler has not reconverged here cannot lose a subset of its lanes
+#define STEP_EXIT_CHECK if ((!COMPACT || xiter == XTAIL) && __all_sync(0xffffffffu, state == ST_DONE)) break;
 #include "step_body.inc"
 #undef STEP_EXIT_CHECK
 
@@ -1045,6 +1122,10 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 
     // ---- epilogue: flush CTA-private detector bins and per-thread counters
     __syncthreads();
+    if (PATHLEN && threadIdx.x == 0) {
+        P.seg_count[blockIdx.x] = *seg_cnt;
+        atomicAdd(P.seg_total, (unsigned long long)*seg_cnt);
+    }
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
@@ -1103,6 +1184,8 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         for (int i = threadIdx.x; i < P.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     unsigned long long* sbins = reinterpret_cast<unsigned long long*>(smem + P.blob_bytes);
+    unsigned int* seg_cnt = reinterpret_cast<unsigned int*>(smem + P.seg_off);  // PATHLEN: segments recorded by this CTA
+    if (PATHLEN && threadIdx.x == 0) *seg_cnt = 0u;
     static_assert((SMCRT_BLOCK & (SMCRT_BLOCK - 1)) == 0 && SMCRT_BLOCK * QSLOTS_PER_THREAD <= 65536, "ring indices are masked 16-bit slot numbers");
     const int M = blockDim.x * QSLOTS_PER_THREAD;  // packets in flight per CTA (power of two: the rings wrap with a mask)
     QueueCtl* qc = reinterpret_cast<QueueCtl*>(smem + P.xchg_off);
@@ -1287,6 +1370,10 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 
     // ---- epilogue: flush CTA-private detector bins and per-thread counters
     __syncthreads();
+    if (PATHLEN && threadIdx.x == 0) {
+        P.seg_count[blockIdx.x] = *seg_cnt;
+        atomicAdd(P.seg_total, (unsigned long long)*seg_cnt);
+    }
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);

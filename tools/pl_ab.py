@@ -41,7 +41,7 @@ for deck, n in cases:
         fetch_ms = (time.perf_counter() - t0) * 1e3
         sums[legacy] = float(out["jmean"].sum(dtype=np.float64))
         print(json.dumps({"deck": deck, "walker": "voxels" if legacy else "runs", "packets": n, "ms": [round(m, 2) for m in ms],
-                          "packets_per_s": n / min(ms[1:]) * 1e3, "fetch_ms": round(fetch_ms, 2), "jmean_sum": sums[legacy],
-                          "kernel_variant": e.kernel_variant(3), "lost": int(out["counters"]["lost"])}), flush=True)
+                          "packets_per_s": n / min(ms[1:]) * 1e3, "fetch_ms": round(fetch_ms, 2),
+                          "kernel_variant": e.kernel_variant(3), "segment_mode": e.segment_mode, "segs_per_packet": round(e.segments_per_packet, 2), "lost": int(out["counters"]["lost"])}), flush=True)
         e.close()
     print(json.dumps({"deck": deck, "jmean_sum_rel_diff": sums[0] / sums[1] - 1.0}), flush=True)

@@ -187,8 +187,23 @@ class OracleScene:
             self.set_detectors(*detectors[:3])
 
     @classmethod
+    def from_deck(cls, deck):
+        """deck: oracle.scenes.Deck -- the oracle's own TOML -> scene path (no product code involved)."""
+        o = cls(deck.scene, deck.grid, deck.source, deck.detectors)
+        o.deck = deck
+        return o
+
+    @classmethod
+    def from_toml(cls, path, res_dir=None):
+        from . import scenes
+        return cls.from_deck(scenes.load(path, res_dir))
+
+    @classmethod
     def from_config(cls, cfg):
-        return cls(cfg.scene, cfg.grid, cfg.source, cfg.detectors)
+        """cfg: anything with .toml_text (and .res_dir).  Only the deck's TEXT is taken from it: scene, source and detectors are
+        built by oracle/scenes.py, independently of the product's host layer."""
+        from . import scenes
+        return cls.from_deck(scenes.loads(cfg.toml_text, getattr(cfg, "res_dir", None)))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -75,23 +75,26 @@ class Scene:
 class Config:
     """`setup()`'s product: parsed TOML (`state`, `dict`, `dects`) + the scene built by the geom_name dispatch."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, toml_text="", res_dir=None):
         self._h = handle
         self._L = _lib.load()
+        self.toml_text = toml_text  # the deck as read (tests hand it to the oracle's own TOML -> scene path, oracle/scenes.py)
+        self.res_dir = res_dir
 
     @classmethod
     def load(cls, toml_path, res_dir=None):
         L = _lib.load()
         h = C.c_void_p()
         check(L.smcrt_config_load(str(toml_path).encode(), None if res_dir is None else str(res_dir).encode(), C.byref(h)))
-        return cls(h)
+        with open(toml_path, "r") as f:
+            return cls(h, f.read(), res_dir)
 
     @classmethod
     def loads(cls, text, res_dir=None):
         L = _lib.load()
         h = C.c_void_p()
         check(L.smcrt_config_loads(text.encode(), None if res_dir is None else str(res_dir).encode(), C.byref(h)))
-        return cls(h)
+        return cls(h, text, res_dir)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -41,11 +41,24 @@ WORKLOADS = {
     "skin_b200.toml": "BASELINE configs[2]: five refractive tissue layers, uniform source, 200^3 grid",
     "lens.toml": "BASELINE configs[3]: refractive lens (model of two spheres), uniform source, 200^3 grid",
 }
-# flops/packet of the reference algorithm (oracle counters x the table above), as printed by N=1 runs of this file
-ALGORITHMIC_FLOPS = {"validation1.toml": 7399.0}
-# DRAM bytes (read + write) of ONE launch of the dominant kernel at the default packets/step, from the ncu --set full capture of
-# this command (profiles/r01_bench_top_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC_BYTES = {("validation1.toml", 100_000_000): 1039.4e3}  # kernel variant 4, trace_queued<0,1,2,1,1> (what the engine picks for this scene)
+# What an ncu --set full capture of this command says about the dominant kernel (DRAM bytes of one launch, issue-slot utilisation,
+# lanes per instruction), keyed on (scene, packets per step, kernel variant): profiles/bench_ncu.json, written from the capture by
+# tools/ncu_bench_json.py.  A run whose kernel variant has no capture reports null, not a stale constant.
+# Likewise the flops/packet of the REFERENCE algorithm (oracle counters x the op table above): measured by the N=1 run's CPU leg;
+# N>1 runs (no CPU leg) take the value the last N=1 run of the scene printed, from the same file.
+def ncu_facts(scene_name: str, n_step: int, variant: int) -> dict:
+    try:
+        table = json.loads((ROOT / "profiles" / "bench_ncu.json").read_text())
+    except (OSError, ValueError):
+        return {}
+    return table.get(f"{scene_name}:{n_step}:{variant}", {})
+
+
+def committed_reference_flops(scene_name: str):
+    try:
+        return json.loads((ROOT / "profiles" / "bench_ncu.json").read_text()).get("reference_flops_per_packet", {}).get(scene_name)
+    except (OSError, ValueError):
+        return None
 
 
 def flops_per_sweep(scene) -> float:
@@ -126,12 +139,23 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_leg(cfg, seconds_target: float, threads: int = 0):
+def host_threads() -> int:
+    """Host cores this process may use: the affinity mask.  NOT OMP_NUM_THREADS: torch.distributed.run exports OMP_NUM_THREADS=1
+    to every rank, which collapsed the reference arm to one core at N > 1."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        n = max(1, os.cpu_count() or 1)
+    return n   # handed to the oracle as num_threads(n), which overrides the environment's OMP_NUM_THREADS
+
+
+def cpu_leg(deck_path, seconds_target: float, threads: int = 0):
     """Time the oracle (CPU restatement of the reference path) on a bounded sample of the same workload."""
+    threads = threads or host_threads()
     from oracle import binding as O
     O.build()
-    osc = O.OracleScene.from_config(cfg)
-    threads = threads or O.max_threads()
+    osc = O.OracleScene.from_toml(deck_path)
+    cfg = osc.deck
     nv = int(np.prod(cfg.grid[0]))
     # calibrate on a small sample, then size the timed sample for ~seconds_target of CPU work
     r = osc.run(20000, cfg.iseed, rng_mode=1, nthreads=threads, grids=False, tally_mode=1)
@@ -146,12 +170,12 @@ def run_reference(args, rank: int, world: int):
     binary cannot be built in this image (no compiler, un-vendored deps: SURVEY F2/F3), so this is the oracle port."""
     if rank != 0:
         return
-    import rsmcrt_b200 as R
-    cfg = R.Config.load(ROOT / "res" / args.scene)
+    # the oracle's own TOML -> scene path (oracle/scenes.py): this arm never loads the product library
+    threads = host_threads()
     from oracle import binding as O
     O.build()
-    osc = O.OracleScene.from_config(cfg)
-    threads = O.max_threads()
+    osc = O.OracleScene.from_toml(ROOT / "res" / args.scene)
+    cfg = osc.deck
     r = osc.run(20000, cfg.iseed, rng_mode=1, nthreads=threads, grids=False)
     rate = 20000 / max(r["seconds"], 1e-6)
     per_step = int(min(max(rate * args.cpu_seconds, 20_000), 20_000_000))
@@ -172,6 +196,8 @@ def run_reference(args, rank: int, world: int):
                          "sample": f"{per_step} packets/step x {args.steps} steps of res/{args.scene}, xoshiro256** per thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # this arm builds its scene with oracle/scenes.py and must not have loaded the product's shared object
+        "product_library_loaded": any("libsmcrt_gpu" in l for l in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None,
     }
     emit(line)
 
@@ -206,6 +232,7 @@ def main():
     ap.add_argument("--photons", type=float, default=1e8, help="packets per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` array (path-length mode, sphere.toml)")
     ap.add_argument("--pathlength", action="store_true", help="also accumulate path-length fluence (jmean)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -316,17 +343,67 @@ def main():
         eng.set_source(src_k, src_s, src_p)
         eng.set_detectors(kind, dp, nb)            # (also zeroes the detector tallies, like the escape driver's reset)
         eng.run(n_step, seed + 1, id_offset=off, tally_mode=mode)
+        if world > 1:
+            eng.comm_reduce(0)                     # every step produces the COMBINED result: tallies of all ranks summed on rank 0
         # device -> host, the sequence of the Fortran shim: module arrays += device tallies, then reset
-        cn = eng.fetch_into(absorb=h_absorb, det_bins=h_bins, accumulate=True)
-        d2h_actual += eng.last_fetch_bytes
+        if rank == 0:
+            cn = eng.fetch_into(absorb=h_absorb, det_bins=h_bins, accumulate=True)
+            d2h_actual += eng.last_fetch_bytes
+            _ = float(h_bins.sum()) + cn["nscatt"]
         eng.reset_tallies()
-        _ = float(h_bins.sum()) + cn["nscatt"]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = packets / e2e_s
-    absorbed_per_packet = float(h_absorb.sum(dtype=np.float64)) / (n_step * args.steps)  # host array accumulated over the e2e steps
+    # host array accumulated over the e2e steps: at N > 1 rank 0 holds the tallies of all ranks
+    absorbed_per_packet = float(h_absorb.sum(dtype=np.float64)) / (n_step * args.steps * (world if rank == 0 else 1))
     eng.unpin_host(h_absorb)
     eng.unpin_host(h_bins)
+
+    # ---------------- the other BASELINE modes / scenes: path-length mode of the workload scene, sphere.toml both modes
+    extra = []
+    red_peaks = {}
+    try:
+        red_peaks = json.loads((ROOT / "profiles" / "r01_red_peaks.json").read_text())["grids"]
+    except (OSError, KeyError, ValueError):
+        pass
+    if not args.no_configs:
+        for deck, n_x, x_mode in ((args.scene, n_step, A.TALLY_ABSORB | A.TALLY_PATHLENGTH), ("sphere.toml", 50_000_000, A.TALLY_ABSORB),
+                                  ("sphere.toml", 50_000_000, A.TALLY_ABSORB | A.TALLY_PATHLENGTH)):
+            xcfg = cfg if deck == args.scene else R.Config.load(ROOT / "res" / deck)
+            xe = eng if deck == args.scene else R.Engine(1, device_ids=[local_rank])
+            if xe is not eng:
+                xe.apply(xcfg)
+            ms = []
+            for k in range(4):   # run 0 = calibration / variant trial of this (scene, mode); best of the rest
+                xe.reset_tallies()
+                barrier()
+                xe.run(n_x, xcfg.iseed, id_offset=step_offset(k, world, rank, n_x), tally_mode=x_mode)
+                ms.append(max_over_ranks(xe.last_run_ms))
+            xc = xe.fetch(absorb=False, detectors=False)["counters"]
+            rate = n_x * world / (min(ms[1:]) * 1e-3)
+            xnv = int(np.prod(xcfg.grid[0]))
+            entry = {"workload": f"res/{deck}", "tally_mode": x_mode, "mode": "pathlength" if x_mode & A.TALLY_PATHLENGTH else "absorb",
+                     "packets_per_step_per_gpu": n_x, "value": rate, "unit": UNIT, "ms_per_step": min(ms[1:]),
+                     "kernel_variant": xe.kernel_variant(x_mode), "lost_fraction": xc["lost"] / max(xc["launched"], 1.0)}
+            if x_mode & A.TALLY_PATHLENGTH:
+                gkey = "200^3 (32 MB, L2 resident)" if xnv * 4 < 126e6 else "500^3 (500 MB)"
+                pk = red_peaks.get(gkey, {})
+                vox, reds = xc["voxel_crossings"] / xc["launched"], xc["deposit_atomics"] / xc["launched"]
+                # algorithmic deposits = one per voxel crossed (the reference's loop, SURVEY 8d W_atom); issued = what the engine
+                # sent to L2 (a range update covers a run of voxels with 4).  peak: measured red.global.add.f32 ceiling for this
+                # grid size (uniform-random pattern; the hot column of a pencil beam has a lower one, quoted beside it)
+                peak = pk.get("uniform_random")
+                entry["roofline"] = {"red": {"voxel_crossings_per_packet": vox, "atomics_issued_per_packet": reds,
+                                             "algorithmic_red_per_s_per_gpu": rate / world * vox, "issued_red_per_s_per_gpu": rate / world * reds,
+                                             "peak": peak, "peak_hot_column": pk.get("hot_column_333"), "unit": "red.f32/s per GPU",
+                                             "frac": None if not peak else rate / world * vox / peak,
+                                             "frac_issued": None if not peak else rate / world * reds / peak,
+                                             "peak_source": f"profiles/r01_red_peaks.json [{gkey}]"},
+                                     "segment_mode": xe.segment_mode, "segments_per_packet": xe.segments_per_packet}
+            extra.append(entry)
+            if xe is not eng:
+                xe.close()
+        eng.reset_tallies()
 
     if rank != 0:
         if dist is not None:
@@ -335,43 +412,47 @@ def main():
 
     c = res["counters"]
     n_run = c["launched"]
+    variant = eng.kernel_variant(mode)
     # ---------------- CPU baseline (rank 0, N=1 only) + algorithmic work from the oracle's counters
     cpu = None
-    # algorithmic work of the REFERENCE algorithm per packet: measured from the oracle's counters by the N=1 run below;
-    # the committed table is what those runs printed (used when the CPU leg is skipped, i.e. N>1)
-    w_flop = ALGORITHMIC_FLOPS.get(args.scene) or algorithmic_flops_per_packet(scene, len(kind), c, n_run)
-    w_basis = "committed oracle-counter table" if args.scene in ALGORITHMIC_FLOPS else "engine counters"
+    # algorithmic work of the REFERENCE algorithm per packet (SURVEY 8d): measured from the oracle's counters by the N=1 run below;
+    # N>1 runs take what the last committed N=1 run of this scene printed (profiles/bench_ncu.json)
+    w_flop_exec = algorithmic_flops_per_packet(scene, len(kind), c, n_run)   # the same op table on the ENGINE's counters
+    w_flop = committed_reference_flops(args.scene)
+    w_basis = "profiles/bench_ncu.json (what the last N=1 run printed)"
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu, secs, cc, threads = cpu_leg(cfg, args.cpu_seconds)
+        n_cpu, secs, cc, threads = cpu_leg(ROOT / "res" / args.scene, args.cpu_seconds)
         cpu = {"value": n_cpu / secs, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{n_cpu} packets of res/{args.scene} on {threads} OpenMP threads (oracle/oracle.cpp, FP64, xoshiro256**)"}
         w_flop = algorithmic_flops_per_packet(scene, len(kind), cc, float(n_cpu))
-        w_basis = "oracle counters (reference algorithm, eps=1e-8)"
+        w_basis = "oracle counters of this run (reference algorithm, eps=1e-8)"
+    if w_flop is None:
+        w_flop, w_basis = w_flop_exec, "engine counters (no oracle figure available)"
 
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except OSError:
+    except (OSError, ValueError):
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s FP32 FMA at max clock
-    kern_rate = packets / (kernel_ms * 1e-3)
+    fp32_peak_gpu = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s FP32 FMA at max clock, ONE GPU
+    fp32_peak = fp32_peak_gpu * world                    # the job's peak: all its GPUs
+    kern_rate = packets / (kernel_ms * 1e-3)             # all ranks
     achieved = kern_rate * w_flop / 1e12
+    achieved_exec = kern_rate * w_flop_exec / 1e12
+    facts = ncu_facts(args.scene, n_step, variant)
     # secondary ceilings: HBM traffic of the kernel and red.global.add.f32 rate, to show they are NOT the bound
-    traffic = NCU_TRAFFIC_BYTES.get((args.scene, n_step))
+    traffic = facts.get("dram_bytes_per_launch")
     hbm_peak = float(peaks.get("hbm_gbs", 6548.2))
-    hbm = None if traffic is None else {"achieved": traffic / (kernel_ms / args.steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU",
-                                        "frac": traffic / (kernel_ms / args.steps * 1e-3) / 1e9 / hbm_peak}
+    per_launch_s = kernel_ms / args.steps * 1e-3
+    hbm = None if traffic is None else {"achieved": traffic / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU",
+                                        "frac": traffic / per_launch_s / 1e9 / hbm_peak}
     red = None
-    try:
-        rp = json.loads((ROOT / "profiles" / "r01_red_peaks.json").read_text())["grids"]["500^3 (500 MB)"]["uniform_random"]
+    rp = red_peaks.get("500^3 (500 MB)" if nv * 4 > 126e6 else "200^3 (32 MB, L2 resident)", {}).get("uniform_random")
+    if rp and absorbed_per_packet > 0:
         # absorb mode: one red.f32 per absorbed packet (detector bins are CTA-private shared-memory counters, flushed once)
-        absorbed = absorbed_per_packet
-        if absorbed > 0:
-            red = {"reds_per_packet": absorbed, "achieved": kern_rate / world * absorbed, "peak": rp, "unit": "red.f32/s per GPU",
-                   "frac": kern_rate / world * absorbed / rp, "peak_source": "profiles/r01_red_peaks.json (tools/red_peak.py, uniform-random voxels of a 500^3 grid)"}
-    except (OSError, KeyError, ValueError):
-        pass
+        red = {"reds_per_packet": absorbed_per_packet, "achieved": kern_rate / world * absorbed_per_packet, "peak": rp, "unit": "red.f32/s per GPU",
+               "frac": kern_rate / world * absorbed_per_packet / rp, "peak_source": "profiles/r01_red_peaks.json (tools/red_peak.py, uniform-random voxels)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -380,21 +461,29 @@ def main():
                    "packets_per_step_per_gpu": n_step, "tally_mode": mode, "parallelism": f"packets sharded over {world} GPU(s), NCCL reduce at end",
                    "l2_note": f"no HBM-resident input stream: the scene lives in shared memory; tally grid {nv * 4 / 1e6:.0f} MB "
                               + ("> L2" if nv * 4 > 126e6 else "(L2 resident)"),
-                   "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms, "kernel_variant": eng.kernel_variant(mode)},
+                   "wall_ms_timed_region": wall_ms, "nccl_reduce_ms": red_ms, "kernel_variant": variant},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_actual // args.steps),
                 "d2h_note": "absorb grid read back as (index, value) pairs of its non-zero voxels after a device-side scan (smcrt_fetch); "
-                            f"the dense array would be {nv * 4} bytes"},
+                            f"the dense array would be {nv * 4} bytes",
+                "note": "every step: scene/source/detector upload, run" + (", NCCL reduce of all ranks' tallies to rank 0 (sparse pair exchange "
+                        "when the grid is < 1/64 full)" if world > 1 else "") + ", read-back into pinned host arrays on rank 0, reset"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                     "traffic": traffic, "hbm": hbm, "red": red,
-                     "note": "path is FP32/SFU-issue bound, not HBM or tensor (SURVEY 8d); achieved = packets/s x algorithmic flops/packet "
-                             f"({w_flop:.0f}, from {w_basis} x frozen op table in bench.py); peak = 148 SM x 128 lanes x 2 x sm_max_mhz "
-                             "(nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",
-                     "flops_per_packet": w_flop,
+                     "achieved_executed": achieved_exec, "frac_executed": achieved_exec / fp32_peak,
+                     "issue_slot_utilisation": facts.get("issue_slots_busy"), "lanes_per_instruction": facts.get("lanes_per_instruction"),
+                     "peak_per_gpu": fp32_peak_gpu, "traffic": traffic, "hbm": hbm, "red": red,
+                     "note": "path is FP32/SFU-issue bound, not HBM or tensor (SURVEY 8d).  frac = packets/s x flops/packet of the REFERENCE "
+                             f"algorithm ({w_flop:.0f}: {w_basis}; ~63 plain sphere-tracing sweeps per packet) / peak: the contract figure.  "
+                             f"frac_executed = the same op table on the ENGINE's own counters ({w_flop_exec:.0f} flops/packet: its directional "
+                             "step bounds need ~6 sweeps): what the FMA pipes actually execute.  issue_slot_utilisation / lanes_per_instruction: "
+                             "ncu on this command and kernel variant (profiles/bench_ncu.json; null when that variant has no capture).  "
+                             f"peak = {world} GPU(s) x 148 SM x 128 lanes x 2 x sm_max_mhz (nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",
+                     "flops_per_packet": w_flop, "flops_per_packet_executed": w_flop_exec,
                      "engine_sweeps_per_packet": c["sweeps"] / n_run, "engine_nscatt_per_packet": c["nscatt"] / n_run,
                      "engine_lost_fraction": c["lost"] / n_run},
         "cpu_baseline": cpu,
+        "configs": extra,
     }
     emit(line)
     if dist is not None:

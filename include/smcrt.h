@@ -116,6 +116,8 @@ typedef struct smcrt_counters {
     double lost;          /* packets killed by an engine guard (step cap / bounces>1000 / layer 0) */
     double sweeps;        /* eval-all sweeps executed (engine instrumentation; == sdf_evals / n_top) */
     double det_hits;      /* detector hits recorded */
+    double voxel_crossings; /* -Dpathlength: voxels the straight segments crossed = deposits of the reference's loop (inttau2.f90:417-441) */
+    double deposit_atomics; /* -Dpathlength: atomics the engine issued for them (range updates cover many voxels with four) */
 } smcrt_counters;
 
 /* ---- life cycle ---------------------------------------------------------------------------- */

@@ -22,7 +22,7 @@ DET_PARAMS = 20
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_double) for n in
-                ("nscatt", "sdf_evals", "bounces", "launched", "emit_retries", "lost", "sweeps", "det_hits")]
+                ("nscatt", "sdf_evals", "bounces", "launched", "emit_retries", "lost", "sweeps", "det_hits", "voxel_crossings", "deposit_atomics")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -47,13 +47,16 @@ namespace nccl {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat32 = 7, ncclUint64 = 5, ncclSum = 0 };
+enum { ncclFloat32 = 7, ncclUint64 = 5, ncclUint32 = 3, ncclSum = 0 };
 static void* lib = nullptr;
 static ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 static ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 static ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
 static ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 static ncclResult_t (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+static ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+static ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+static ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 static ncclResult_t (*GroupStart)() = nullptr;
 static ncclResult_t (*GroupEnd)() = nullptr;
 static const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -73,6 +76,9 @@ static int load() {
     SYM(CommInitAll, "ncclCommInitAll")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Reduce, "ncclReduce")
+    SYM(AllGather, "ncclAllGather")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -132,6 +138,11 @@ struct DeviceState {
     unsigned int* nz_idx_h = nullptr;
     float* nz_val_h = nullptr;
     size_t nz_cap = 0;
+    // sparse reduce (reduce_buffers): every rank's pair count, and on the root the pairs received from the others
+    unsigned long long* nz_counts = nullptr;
+    unsigned int* rx_idx = nullptr;
+    float* rx_val = nullptr;
+    size_t rx_cap = 0;
     int* cull_start = nullptr;
     int* cull_items = nullptr;
     float* cull_far = nullptr;
@@ -193,6 +204,7 @@ struct smcrt_ctx {
     uint64_t cull_key = 0;  // what the current culling grid was built for (scene hash, grid box)
     bool cull_key_valid = false;
     int touched_modes = 0;   // OR of the tally modes run since the last reset: only those grids are reduced
+    int dirty_modes = 7;     // grids that may hold non-zero voxels on SOME device (cleared by smcrt_reset_tallies)
     long long dbg_pid = -1;
     float* dbg_log = nullptr;
     int dbg_cap = 0;
@@ -269,6 +281,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
+        cudaFree(D.nz_counts); cudaFree(D.rx_idx); cudaFree(D.rx_val);
         if (D.ev0) cudaEventDestroy(D.ev0);
         if (D.ev1) cudaEventDestroy(D.ev1);
         for (cudaEvent_t e : D.tune_ev) if (e) cudaEventDestroy(e);
@@ -295,19 +308,24 @@ extern "C" int smcrt_set_grid(smcrt_ctx* c, int nxg, int nyg, int nzg, double xm
         CU(cudaMemsetAsync(D.emission, 0, bytes, D.stream));
         CU(cudaStreamSynchronize(D.stream));
     }
-    {  // scratch of the sparse read-back (smcrt_fetch), device 0 only: pair list for up to 1/64 of the voxels + pinned mirror
-        DeviceState& D = c->devs[0];
+    // scratch of the sparse read-back (smcrt_fetch, device 0) and of the sparse reduce (every device): pair list for up to 1/64 of
+    // the voxels; pinned host mirror on device 0
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceState& D = c->devs[g];
         const size_t nv = (size_t)nxg * nyg * nzg;
         CU(cudaSetDevice(D.dev));
-        cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
+        cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h); cudaFree(D.rx_idx); cudaFree(D.rx_val);
         D.nz_idx = nullptr; D.nz_val = nullptr; D.nz_idx_h = nullptr; D.nz_val_h = nullptr; D.nz_cap = 0;
+        D.rx_idx = nullptr; D.rx_val = nullptr; D.rx_cap = 0;
         if (nv < (1ull << 32) && nv >= (1u << 16)) {
             const size_t cap = std::max<size_t>(nv / 64, 4096);
             if (!D.nz_cursor) CU(cudaMalloc(&D.nz_cursor, 8));
             CU(cudaMalloc(&D.nz_idx, cap * 4));
             CU(cudaMalloc(&D.nz_val, cap * 4));
-            CU(cudaMallocHost(&D.nz_idx_h, cap * 4));
-            CU(cudaMallocHost(&D.nz_val_h, cap * 4));
+            if (g == 0) {
+                CU(cudaMallocHost(&D.nz_idx_h, cap * 4));
+                CU(cudaMallocHost(&D.nz_val_h, cap * 4));
+            }
             D.nz_cap = cap;
             cudaFuncAttributes fa;
             CU(cudaFuncGetAttributes(&fa, nnz_pack_kernel));  // loads the kernel now rather than inside the first fetch
@@ -1051,6 +1069,7 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     D.ran = true;
     c->launches += (pl ? 3 : 1) * n_launch;
     c->touched_modes |= tally_mode;
+    c->dirty_modes |= tally_mode;
     return 0;
 }
 
@@ -1143,22 +1162,98 @@ extern "C" double smcrt_last_run_ms(const smcrt_ctx* c) { return c ? c->last_ms 
 extern "C" int64_t smcrt_launch_count(const smcrt_ctx* c) { return c ? c->launches : 0; }
 
 // ---- reduce + fetch --------------------------------------------------------------------------------------
-static int reduce_buffers(smcrt_ctx* c, int root_rank_or_dev) {
-    // one grouped ncclReduce per tally buffer; root receives in place
+// Sum of one float tally grid over the ranks into the root's.  A pencil-beam slab run touches ~2000 of 1.25e8 voxels: when every
+// rank's grid has fewer non-zero voxels than the pair scratch holds (1/64 of the grid) the ranks exchange (index, value) pairs --
+// one scan at HBM speed, an all-gather of the counts, grouped send/recv of a few KB, a scatter-add on the root -- instead of
+// reducing 500 MB over NVLink (1.0-1.6 ms per grid at 8 GPUs, the limiter of a one-step job's scaling).  Dense grids take
+// ncclReduce.  `me` lists this process's devices with their ranks in the communicator.
+static int reduce_grid(smcrt_ctx* c, float* DeviceState::*grid, int root, int nranks, const std::vector<int>& ranks) {
     size_t nv;
     n_voxels(c, &nv);
-    for (DeviceState& D : c->devs) { int rc = scan_pathlength(c, D); if (rc) return rc; }
+    static const bool no_sparse = getenv("SMCRT_NO_SPARSE_REDUCE") != nullptr;
+    bool sparse = !no_sparse && nranks > 1;
+    for (DeviceState& D : c->devs) sparse = sparse && D.nz_cap > 0;
+    std::vector<unsigned long long> counts((size_t)nranks, 0ull);
+    if (sparse) {
+        for (DeviceState& D : c->devs) {
+            CU(cudaSetDevice(D.dev));
+            if (!D.nz_counts) CU(cudaMalloc(&D.nz_counts, sizeof(unsigned long long) * 64));
+            if (nranks > 64) return set_err("sparse reduce: more than 64 ranks");
+            CU(cudaMemsetAsync(D.nz_cursor, 0, 8, D.stream));
+            nnz_pack_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(D.*grid, (long long)nv, D.nz_idx, D.nz_val, D.nz_cursor, (unsigned long long)D.nz_cap);
+            CU(cudaGetLastError());
+        }
+        NC(nccl::GroupStart());
+        for (DeviceState& D : c->devs) {
+            CU(cudaSetDevice(D.dev));
+            NC(nccl::AllGather(D.nz_cursor, D.nz_counts, 1, nccl::ncclUint64, D.comm, D.stream));
+        }
+        NC(nccl::GroupEnd());
+        DeviceState& D0 = c->devs[0];
+        CU(cudaSetDevice(D0.dev));
+        CU(cudaMemcpyAsync(counts.data(), D0.nz_counts, sizeof(unsigned long long) * nranks, cudaMemcpyDeviceToHost, D0.stream));
+        CU(cudaStreamSynchronize(D0.stream));
+        for (int r = 0; r < nranks; ++r) sparse = sparse && counts[r] <= c->devs[0].nz_cap;  // (the scan gives up beyond the cap)
+    }
+    if (!sparse) {
+        NC(nccl::GroupStart());
+        for (DeviceState& D : c->devs) {
+            CU(cudaSetDevice(D.dev));
+            NC(nccl::Reduce(D.*grid, D.*grid, nv, nccl::ncclFloat32, nccl::ncclSum, root, D.comm, D.stream));
+        }
+        NC(nccl::GroupEnd());
+        return 0;
+    }
+    size_t total = 0;
+    for (int r = 0; r < nranks; ++r) if (r != root) total += counts[r];
+    DeviceState* R = nullptr;
+    for (size_t g = 0; g < c->devs.size(); ++g) if (ranks[g] == root) R = &c->devs[g];
+    if (R && total > R->rx_cap) {
+        CU(cudaSetDevice(R->dev));
+        cudaFree(R->rx_idx); cudaFree(R->rx_val);
+        R->rx_cap = std::max<size_t>(total, 4096) * 2;
+        CU(cudaMalloc(&R->rx_idx, R->rx_cap * 4));
+        CU(cudaMalloc(&R->rx_val, R->rx_cap * 4));
+    }
     NC(nccl::GroupStart());
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceState& D = c->devs[g];
         CU(cudaSetDevice(D.dev));
-        // only the grids a run could have written (every rank runs the same modes, so the collectives match up)
-        if (c->touched_modes & SMCRT_TALLY_PATHLENGTH)
-            NC(nccl::Reduce(D.jmean, D.jmean, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
-        if (c->touched_modes & SMCRT_TALLY_ABSORB)
-            NC(nccl::Reduce(D.absorb, D.absorb, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
-        if (c->touched_modes & SMCRT_TALLY_EMISSION)
-            NC(nccl::Reduce(D.emission, D.emission, nv, nccl::ncclFloat32, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
+        if (ranks[g] == root) {
+            size_t off = 0;
+            for (int r = 0; r < nranks; ++r) {
+                if (r == root || !counts[r]) continue;
+                NC(nccl::Recv(D.rx_idx + off, counts[r], nccl::ncclUint32, r, D.comm, D.stream));
+                NC(nccl::Recv(D.rx_val + off, counts[r], nccl::ncclFloat32, r, D.comm, D.stream));
+                off += counts[r];
+            }
+        } else if (counts[ranks[g]]) {
+            NC(nccl::Send(D.nz_idx, counts[ranks[g]], nccl::ncclUint32, root, D.comm, D.stream));
+            NC(nccl::Send(D.nz_val, counts[ranks[g]], nccl::ncclFloat32, root, D.comm, D.stream));
+        }
+    }
+    NC(nccl::GroupEnd());
+    if (R && total) {
+        CU(cudaSetDevice(R->dev));
+        scatter_add_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, R->stream>>>(R->*grid, R->rx_idx, R->rx_val, (long long)total);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+static int reduce_buffers(smcrt_ctx* c, int root_rank_or_dev) {
+    // root receives in place; only the grids a run could have written (every rank runs the same modes, so the collectives match up)
+    for (DeviceState& D : c->devs) { int rc = scan_pathlength(c, D); if (rc) return rc; }
+    std::vector<int> ranks(c->devs.size());
+    for (size_t g = 0; g < c->devs.size(); ++g) ranks[g] = c->comm_rank ? c->rank : (int)g;
+    const int nranks = c->comm_rank ? c->nranks : (int)c->devs.size();
+    int rc = 0;
+    if ((c->touched_modes & SMCRT_TALLY_PATHLENGTH) && (rc = reduce_grid(c, &DeviceState::jmean, root_rank_or_dev, nranks, ranks))) return rc;
+    if ((c->touched_modes & SMCRT_TALLY_ABSORB) && (rc = reduce_grid(c, &DeviceState::absorb, root_rank_or_dev, nranks, ranks))) return rc;
+    if ((c->touched_modes & SMCRT_TALLY_EMISSION) && (rc = reduce_grid(c, &DeviceState::emission, root_rank_or_dev, nranks, ranks))) return rc;
+    NC(nccl::GroupStart());
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceState& D = c->devs[g];
+        CU(cudaSetDevice(D.dev));
         NC(nccl::Reduce(D.det_bins, D.det_bins, (size_t)std::max<long long>(c->det_total, 1), nccl::ncclUint64, nccl::ncclSum,
                         root_rank_or_dev, D.comm, D.stream));
         NC(nccl::Reduce(D.counters, D.counters, (size_t)C_COUNT, nccl::ncclUint64, nccl::ncclSum, root_rank_or_dev, D.comm, D.stream));
@@ -1192,9 +1287,10 @@ static int zero_device_tallies(smcrt_ctx* c, DeviceState& D) {
         CU(cudaMemsetAsync(D.jdiff_used, 0, 16, D.stream));
         D.jdiff_dirty = false; D.jdiff_packets = 0;
     }
-    CU(cudaMemsetAsync(D.jmean, 0, nv * 4, D.stream));
-    CU(cudaMemsetAsync(D.absorb, 0, nv * 4, D.stream));
-    CU(cudaMemsetAsync(D.emission, 0, nv * 4, D.stream));
+    // (only the grids a run has written since they were last cleared: a 500^3 grid is 500 MB)
+    if (c->dirty_modes & SMCRT_TALLY_PATHLENGTH) CU(cudaMemsetAsync(D.jmean, 0, nv * 4, D.stream));
+    if (c->dirty_modes & SMCRT_TALLY_ABSORB) CU(cudaMemsetAsync(D.absorb, 0, nv * 4, D.stream));
+    if (c->dirty_modes & SMCRT_TALLY_EMISSION) CU(cudaMemsetAsync(D.emission, 0, nv * 4, D.stream));
     CU(cudaMemsetAsync(D.det_bins, 0, sizeof(unsigned long long) * (size_t)std::max<long long>(c->det_total, 1), D.stream));
     CU(cudaMemsetAsync(D.counters, 0, sizeof(unsigned long long) * C_COUNT, D.stream));
     CU(cudaStreamSynchronize(D.stream));
@@ -1318,10 +1414,13 @@ extern "C" int smcrt_fetch(smcrt_ctx* c, float* jmean, float* absorb, float* emi
         k.emit_retries = (double)raw[C_RETRIES];
         k.lost = (double)raw[C_LOST];
         k.det_hits = (double)raw[C_DETHITS];
+        k.voxel_crossings = (double)raw[C_VOXELS];
+        k.deposit_atomics = (double)raw[C_REDS];
         if (accumulate) {
             counters->nscatt += k.nscatt; counters->sdf_evals += k.sdf_evals; counters->bounces += k.bounces;
             counters->launched += k.launched; counters->emit_retries += k.emit_retries; counters->lost += k.lost;
             counters->sweeps += k.sweeps; counters->det_hits += k.det_hits;
+            counters->voxel_crossings += k.voxel_crossings; counters->deposit_atomics += k.deposit_atomics;
         } else
             *counters = k;
     }
@@ -1334,6 +1433,7 @@ extern "C" int smcrt_reset_tallies(smcrt_ctx* c) {
     c->touched_modes = 0;
     for (DeviceState& D : c->devs)
         if ((rc = zero_device_tallies(c, D))) return rc;
+    c->dirty_modes = 0;
     return 0;
 }
 

@@ -94,7 +94,7 @@ struct KParams {
     int dbg_cap;
 };
 
-enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE /* trace_queued watchdog */, C_DETHITS, C_COUNT };
+enum : int { C_NSCATT = 0, C_SWEEPS, C_BOUNCES, C_LAUNCHED, C_RETRIES, C_LOST, C_SPARE /* trace_queued watchdog */, C_DETHITS, C_VOXELS, C_REDS, C_COUNT };
 enum : int { TALLY_ABSORB = 1, TALLY_PATHLENGTH = 2, TALLY_EMISSION = 4 };
 constexpr float TWOPI_F = 6.283185307179586f;
 constexpr float DET_FIX = 16777216.0f;  // 2^24: detector bins are Q40.24 fixed point
@@ -531,8 +531,9 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
 // full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
 __device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-static __device__ __noinline__ void walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
-    if (!in_grid(P, fx, fy, fz)) return;  // :411-415
+// -> (voxels crossed, atomics issued) for the counters
+static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+    if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
     const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
     long long off = (long long)S.c[0] + vy * (long long)S.c[1] + vz * (long long)S.c[2];
@@ -551,8 +552,10 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
         // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
         const long long svx = sx, svy = sy > 0 ? vy : -vy, svz = sz > 0 ? vz : -vz;
         float* cell = P.jmean + off;
+        unsigned int nvox = 0u;
         for (;;) {
             const float tn = fminf(tx, fminf(ty, tz));
+            ++nvox;
             if (tn >= len) {
                 atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
                 break;
@@ -565,7 +568,7 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
             else                      { k += sz; cell += svz; tz += dtz; out = (unsigned)k >= (unsigned)P.nzg; }
             if (out) break;  // :437-440
         }
-        return;
+        return make_uint2(nvox, nvox);
     }
     // ---- run walk
     float ta = a0 ? S.t[0] : (a1 ? S.t[1] : S.t[2]);
@@ -585,6 +588,7 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
     const float fix = (a0 ? P.jfix[0] : (a1 ? P.jfix[1] : P.jfix[2])) * weight;
     float t = 0.f;
     bool used = false;
+    unsigned int nvox = 0u, nred = 0u;
     for (;;) {
         const float tcol = fminf(tb, tc);        // the ray leaves this column (or never: BIG)
         const float tend = fminf(tcol, len);
@@ -598,8 +602,10 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
         const int room = fwd ? na - 1 - ia : ia;  // faces that can be crossed without leaving the grid
         const bool leave = m > room;
         if (leave) m = room;
+        nvox += (unsigned int)m + 1u;
         if (m == 0) {
             atomicAdd(P.jmean + off, fmaxf((leave ? ta : tend) - t, 0.f) * weight);
+            ++nred;
         } else {
             const float p_in = fmaxf(ta - t, 0.f);
             // the last voxel of a run that leaves the grid is crossed whole
@@ -608,6 +614,7 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
                 atomicAdd(P.jmean + off, p_in * weight);
                 if (m == 2) atomicAdd(P.jmean + off + sva, dta * weight);
                 atomicAdd(P.jmean + off + (long long)m * sva, p_out * weight);
+                nred += (unsigned int)m + 1u;
             } else {
                 const long long qc = __float2ll_rn(dta * fix);
                 const long long q_in = __float2ll_rn(p_in * fix), q_out = __float2ll_rn(p_out * fix);
@@ -618,6 +625,7 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
                 red_i64(lo + stra, qc - q_lo);
                 red_i64(lo + (long long)m * stra, q_hi - qc);
                 if (hi_idx + 1 < na) red_i64(lo + (long long)(m + 1) * stra, -q_hi);
+                nred += 4u;
                 used = true;
             }
             ia += fwd ? m : -m;
@@ -632,6 +640,7 @@ static __device__ __noinline__ void walk_segment(const KParams& P, float fx, flo
         if (out) break;
     }
     if (used) P.jdiff_used[a] = 1u;
+    return make_uint2(nvox, nred);
 }
 
 // Prefix sum of one difference grid along its axis, added to jmean; the grid is cleared on the way.
@@ -680,7 +689,7 @@ __global__ void jdiff_scan_kernel(long long* __restrict__ D, float* __restrict__
 // The trace kernels' side of -Dpathlength: append the segment to the CTA's share of the segment buffer; if the share is full (the
 // host sizes the packets per launch from the scene's measured segments per packet, with a margin) walk it here and now.
 __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* seg_cnt, float sx, float sy, float sz, float ux, float uy, float uz,
-                                               float px, float py, float pz, float weight) {
+                                               float px, float py, float pz, float weight, unsigned int& c_vox, unsigned int& c_red) {
     const float lx = px - sx, ly = py - sy, lz = pz - sz;
     const float l2 = lx * lx + ly * ly + lz * lz;
     if (!(l2 > 0.f)) return;
@@ -690,8 +699,10 @@ __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* s
         float4* r = P.seg_buf + 2ull * ((unsigned long long)blockIdx.x * P.seg_cap + at);
         r[0] = make_float4(sx, sy, sz, len);
         r[1] = make_float4(ux, uy, uz, weight);
-    } else
-        walk_segment(P, sx, sy, sz, ux, uy, uz, len, weight);
+    } else {
+        const uint2 w = walk_segment(P, sx, sy, sz, ux, uy, uz, len, weight);
+        c_vox += w.x; c_red += w.y;
+    }
 }
 
 #ifndef SMCRT_TRACE_TU  // (engine.cu only)
@@ -703,6 +714,7 @@ __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* s
 // kernel the hot code was 39 KB, beyond the 32 KB L1.5 I-cache: 6 stall cycles per issue waiting for instructions).
 __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    unsigned long long c_vox = 0ull, c_red = 0ull;
     for (int sh = blockIdx.x; sh < n_shares; sh += gridDim.x) {
         const unsigned int n = min(P.seg_count[sh], P.seg_cap);
         const float4* recs = P.seg_buf + 2ull * (unsigned long long)sh * P.seg_cap;
@@ -720,7 +732,10 @@ __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_cons
                 work = 1.0f + a.w * (runs ? 2.0f * (rsum - rmax) : rsum);
             }
             const bool share = work >= 96.0f;
-            if (work > 0.f && !share) walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
+            if (work > 0.f && !share) {
+                const uint2 w = walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
+                c_vox += w.x; c_red += w.y;
+            }
             unsigned pend = __ballot_sync(0xffffffffu, share);
             while (pend) {
                 const int src = __ffs(pend) - 1;
@@ -729,10 +744,14 @@ __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_cons
                 const float ax = __shfl_sync(0xffffffffu, a.x, src), ay = __shfl_sync(0xffffffffu, a.y, src), az = __shfl_sync(0xffffffffu, a.z, src);
                 const float vx = __shfl_sync(0xffffffffu, b.x, src), vy = __shfl_sync(0xffffffffu, b.y, src), vz = __shfl_sync(0xffffffffu, b.z, src);
                 const float t0 = L * ((float)lane * 0.03125f), t1 = lane == 31 ? L : L * ((float)(lane + 1) * 0.03125f);
-                walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w);
+                const uint2 wk = walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w);
+                c_vox += wk.x; c_red += wk.y;
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c_vox += __shfl_xor_sync(0xffffffffu, c_vox, o); c_red += __shfl_xor_sync(0xffffffffu, c_red, o); }
+    if (lane == 0 && c_vox) { atomicAdd(&P.counters[C_VOXELS], c_vox); atomicAdd(&P.counters[C_REDS], c_red); }
 }
 // (the shares are cleared for the next launch by a second tiny kernel: a CTA of the deposit kernel may still be reading a count)
 __global__ void clear_segment_counts_kernel(unsigned int* cnt, int n) {
@@ -1046,7 +1065,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     unsigned long long pid = 0;
     uint32_t ev = 0;
     // per-thread event counters (< 2^32 each); the rare ones (bounces, emit retries, lost) go straight to the global counters
-    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
+    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0, c_vox = 0, c_red = 0;
 
 #include "step_macros.inc"
     for (;;) {
@@ -1131,7 +1150,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
     // every id below nphotons was claimed exactly once
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[C_LAUNCHED], (unsigned long long)P.nphotons);
-    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits};
+    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits, c_vox, c_red};
 #pragma unroll
     for (int c = 0; c < C_COUNT; ++c) {
         unsigned long long v = cs[c];
@@ -1210,7 +1229,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     const unsigned full = 0xffffffffu;
     constexpr bool NEED = false;  // (the plain kernels win on the scenes that use it)
     const unsigned int mask = (unsigned int)M - 1u;
-    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0;
+    unsigned int c_nscatt = 0, c_sweeps = 0, c_dethits = 0, c_vox = 0, c_red = 0;
 
 #include "step_macros.inc"
     // The warp keeps the packets that stay in its current class in registers from one iteration to the next and only moves the
@@ -1378,7 +1397,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x)
             if (sbins[i]) atomicAdd(&P.det_bins[i], sbins[i]);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[C_LAUNCHED], (unsigned long long)P.nphotons);
-    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits};
+    unsigned long long cs[C_COUNT] = {c_nscatt, c_sweeps, 0ull, 0ull, 0ull, 0ull, 0ull, c_dethits, c_vox, c_red};
 #pragma unroll
     for (int c = 0; c < C_COUNT; ++c) {
         unsigned long long v = cs[c];
@@ -1508,6 +1527,11 @@ __global__ void nnz_pack_kernel(const float* __restrict__ g, long long n, unsign
                 const unsigned long long at = atomicAdd(cursor, 1ull);
                 if (at < cap) { idx[at] = (unsigned int)i; val[at] = g[i]; }
             }
+}
+
+// sparse reduce (engine.cu: reduce_grid): the root adds the (index, value) pairs received from the other ranks to its grid
+__global__ void scatter_add_kernel(float* __restrict__ g, const unsigned int* __restrict__ idx, const float* __restrict__ val, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) atomicAdd(g + idx[i], val[i]);
 }
 
 // red.global.add.f32 throughput microbenchmark (the secondary bound of path-length mode).

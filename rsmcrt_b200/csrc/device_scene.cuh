@@ -16,7 +16,10 @@
 
 namespace smcrt_dev {
 
-enum : int { XF_IDENTITY = 0, XF_TRANSLATE = 1, XF_AFFINE = 2 };
+// XF_AFFINE: rigid (orthonormal 3x3 block + translation); XF_NONRIGID: anything else (scale, shear).  The reference accepts any
+// 4x4 transform and steps by |d| (src/inttau2.f90:155-192); the closed-form ray bounds and hit geometry of this engine assume that
+// the local ray direction is a unit vector, which only a rigid transform guarantees: non-rigid primitives keep plain sphere tracing.
+enum : int { XF_IDENTITY = 0, XF_TRANSLATE = 1, XF_AFFINE = 2, XF_NONRIGID = 3 };
 
 template <typename T>
 struct PrimT {
@@ -316,6 +319,12 @@ __device__ __forceinline__ float eval_prim_ray(const PrimT<float>& P, float x, f
         vz = P.m[8] * ux + P.m[9] * uy + P.m[10] * uz;
     }
     const float* q = P.p;
+    if (P.xf == XF_NONRIGID) {  // |v| != 1: local ray parameters are not world distances
+        const float d = eval_prim<float>(P, x, y, z);
+        bound = fabsf(d);
+        exact = false;
+        return d;
+    }
     exact = true;
     if (P.kind == 1) return sphere_ray(px, py, pz, vx, vy, vz, q[0], bound);
     if (P.kind == 2) return box_ray(px, py, pz, vx, vy, vz, q[0], q[1], q[2], bound);

@@ -345,7 +345,13 @@ static void fold_transform(const double* xf /*16, Fortran order*/, double m[12],
     }
     const bool rot_id = m[0] == 1 && m[1] == 0 && m[2] == 0 && m[4] == 0 && m[5] == 1 && m[6] == 0 && m[8] == 0 && m[9] == 0 && m[10] == 1;
     const bool no_t = m[3] == 0 && m[7] == 0 && m[11] == 0;
-    *cls = rot_id ? (no_t ? XF_IDENTITY : XF_TRANSLATE) : XF_AFFINE;
+    bool rigid = true;  // rows of the 3x3 block orthonormal
+    for (int a = 0; a < 3; ++a)
+        for (int b = a; b < 3; ++b) {
+            const double dot = m[4 * a] * m[4 * b] + m[4 * a + 1] * m[4 * b + 1] + m[4 * a + 2] * m[4 * b + 2];
+            if (std::fabs(dot - (a == b ? 1.0 : 0.0)) > 1e-9) rigid = false;
+        }
+    *cls = rot_id ? (no_t ? XF_IDENTITY : XF_TRANSLATE) : (rigid ? XF_AFFINE : XF_NONRIGID);
 }
 
 struct Compiler {
@@ -789,7 +795,7 @@ static int upload_scene(smcrt_ctx* c) {
             if (T.mode != 0) { h.code = HOT_PROGRAM; h.idx[1] = T.count; }
             else {
                 const DevPrim& Q = c->prims[T.first];
-                if (Q.xf != XF_AFFINE && (Q.kind == 1 || Q.kind == 2)) {
+                if (Q.xf <= XF_TRANSLATE && (Q.kind == 1 || Q.kind == 2)) {
                     h.code = Q.kind == 1 ? HOT_SPHERE : HOT_BOX;
                     h.t[0] = h.t[1] = h.t[2] = 0.f;
                     if (Q.xf == XF_TRANSLATE) { h.t[0] = Q.m[3]; h.t[1] = Q.m[7]; h.t[2] = Q.m[11]; }
@@ -828,7 +834,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     for (const DevTop& T : c->tops) if (T.mode == 0 && (c->prims[T.first].kind == 6 || c->prims[T.first].kind == 7)) P.has_capsule = 1;
     P.simple_scene = 1;  // every top-level SDF is a sphere or box the sweep evaluates inline (same test as the DevHot records)
     for (const DevTop& T : c->tops)
-        if (T.mode != 0 || c->prims[T.first].xf == XF_AFFINE || (c->prims[T.first].kind != 1 && c->prims[T.first].kind != 2)) P.simple_scene = 0;
+        if (T.mode != 0 || c->prims[T.first].xf > XF_TRANSLATE || (c->prims[T.first].kind != 1 && c->prims[T.first].kind != 2)) P.simple_scene = 0;
     P.off_tops = c->off_tops; P.off_prog = c->off_prog; P.off_dets = c->off_dets; P.off_hot = c->off_hot; P.off_detp = c->off_detp;
     P.primsD = D.primsD; P.progD = D.progD;
     P.nxg = c->nxg; P.nyg = c->nyg; P.nzg = c->nzg;
@@ -867,6 +873,8 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.jdiff_used = D.jdiff_used;
     P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
+    static const char* wd_env = getenv("SMCRT_WATCHDOG_MS");  // (tests trip the watchdog with a tiny period)
+    P.watchdog_ns = wd_env ? (unsigned long long)(atof(wd_env) * 1e6) : 20000000000ull;  // 20 s
     P.max_steps = (int)std::min<long long>(c->max_steps, 1900000ll);  // the compaction step packs sweep count and event index (<= sweeps + 100000 emit retries) into 21 bits each
     return 0;
 }
@@ -1106,9 +1114,13 @@ extern "C" int smcrt_run_async(smcrt_ctx* c, int64_t nphotons, uint64_t seed, in
 extern "C" int smcrt_wait(smcrt_ctx* c) {
     if (!c) return set_err("null ctx");
     double ms = 0;
-    for (DeviceState& D : c->devs) {
+    for (DeviceState& D : c->devs) {  // every device first: an error below must not leave another device's run in flight
         CU(cudaSetDevice(D.dev));
         CU(cudaStreamSynchronize(D.stream));
+    }
+    int wd_dev = -1;
+    for (DeviceState& D : c->devs) {
+        CU(cudaSetDevice(D.dev));
         if (D.ran) {
             float t = 0;
             CU(cudaEventElapsedTime(&t, D.ev0, D.ev1));
@@ -1119,8 +1131,8 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
             CU(cudaMemcpy(&wd, D.counters + C_SPARE, sizeof wd, cudaMemcpyDeviceToHost));
             if (wd) {
                 CU(cudaMemset(D.counters + C_SPARE, 0, sizeof wd));
-                c->pending = false;
-                return set_err("queue-scheduled kernel: watchdog fired on device %d (a warp found no work for ~10 s); this run's tallies are incomplete", D.dev);
+                wd_dev = D.dev;
+                D.tuning = -1;  // (a trial that tripped it is void)
             }
         }
         if (D.tuning >= 0) {  // the trial slices of run_on_device: keep the fastest kernel variant
@@ -1143,6 +1155,9 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
     }
     if (c->pending) c->last_ms = ms;
     c->pending = false;
+    if (wd_dev >= 0)
+        return set_err("queue-scheduled kernel: watchdog fired on device %d (a warp found the queues empty for the whole watchdog period); "
+                       "this run's tallies are incomplete", wd_dev);
     return 0;
 }
 extern "C" int smcrt_run(smcrt_ctx* c, int64_t nphotons, uint64_t seed, int64_t id_offset, int tally_mode, int survival_bias,

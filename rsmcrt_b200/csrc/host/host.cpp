@@ -917,7 +917,10 @@ int smcrt_escape_cell_centre(int m, int n, int o, int nxg, int nyg, int nzg, dou
 }
 int smcrt_normalise_fluence(float* array, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, int64_t nphotons) {
     const double num = (2.0 * xmax * 2.0 * ymax * 2.0 * zmax);
-    const double den = ((double)(int32_t)nphotons * (2.0 * xmax / nxg) * (2.0 * ymax / nyg) * (2.0 * zmax / nzg));
+    // (the reference's nphotons is a default integer; this engine takes 64-bit counts and traces 4e9 packets in a second, so the
+    // count is NOT narrowed: a 3e9-packet job would otherwise normalise by a negative number)
+    if (nphotons <= 0) return host_fail("smcrt_normalise_fluence: nphotons must be positive");
+    const double den = ((double)nphotons * (2.0 * xmax / nxg) * (2.0 * ymax / nyg) * (2.0 * zmax / nzg));
     const double f = num / den;
     const size_t n = (size_t)nxg * nyg * nzg;
     for (size_t i = 0; i < n; ++i) array[i] = (float)((double)array[i] * f);
@@ -1036,7 +1039,7 @@ int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* o
         toml_path = nullptr;  // (the deck's own name is used for later checkpoints)
         cfg->c.ckpt_deck = name;
     } else
-        cfg->c.ckpt_deck = toml_path;
+        cfg->c.ckpt_deck = toml_path ? toml_path : "";
     Config& c = cfg->c;
     if (nphotons > 0) c.nphotons = nphotons;
     smcrt_ctx* ctx = nullptr;
@@ -1088,14 +1091,18 @@ int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* o
     smcrt_counters cn{};
     if ((rc = smcrt_fetch(ctx, jmean.data(), absorb.data(), emission.data(), bins.data(), &cn, 1))) return cleanup(rc);
     if (counters) *counters = cn;
-    std::printf(" Average # of scatters per photon: %.10g\n", cn.nscatt / (double)c.nphotons);
+    // A resumed run restores jmean from the checkpoint, but absorb, emission, the detector bins and the scatter count cover only the
+    // packets traced NOW (ids photons_done .. nphotons).  The reference keeps them consistent by reducing state%nphotons by the
+    // packets already run (kernelsMod.f90:72); the same count is used here for everything but jmean, which holds the whole job.
+    const int64_t n_total = c.nphotons, n_traced = c.nphotons - photons_done;
+    std::printf(" Average # of scatters per photon: %.10g\n", cn.nscatt / (double)std::max<int64_t>(n_traced, 1));
     // finalise: metadata then files (kernelsMod.f90:2376-2392)
     {
         char b[128];
         c.dict_sets("grid_data", "fluence map");
         std::snprintf(b, sizeof b, "%.7f %.7f %.7f", c.xmax, c.ymax, c.zmax);
         c.dict_sets("real_size", b);
-        c.dict_seti("nphotons", c.nphotons);
+        c.dict_seti("nphotons", n_traced);
         c.dict_sets("source", c.source);
         c.dict_sets("experiment", c.geom);
         build_meta(c);
@@ -1104,10 +1111,11 @@ int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* o
     for (const char* sub : {"/jmean", "/emission", "/absorb", "/detectors"})
         if (!mkdir_p(od + sub)) return cleanup(host_fail("cannot create output directory " + od + sub));
     if (tally_mode & SMCRT_TALLY_PATHLENGTH) {
-        smcrt_normalise_fluence(jmean.data(), c.nxg, c.nyg, c.nzg, c.xmax, c.ymax, c.zmax, c.nphotons);
+        smcrt_normalise_fluence(jmean.data(), c.nxg, c.nyg, c.nzg, c.xmax, c.ymax, c.zmax, n_total);
         if ((rc = smcrt_write_nrrd_f32((od + "/jmean/" + c.outfile).c_str(), jmean.data(), c.nxg, c.nyg, c.nzg, c.meta_text.c_str())))
             return cleanup(rc);
     }
+    c.nphotons = std::max<int64_t>(n_traced, 1);  // emission, detector-file headers: the packets traced by this invocation
     smcrt_normalise_fluence(emission.data(), c.nxg, c.nyg, c.nzg, c.xmax, c.ymax, c.zmax, c.nphotons);
     if ((rc = smcrt_write_nrrd_f32((od + "/emission/" + c.rendersourcefile).c_str(), emission.data(), c.nxg, c.nyg, c.nzg, c.meta_text.c_str())))
         return cleanup(rc);

@@ -68,6 +68,7 @@ struct KParams {
     float threshold, chance;
     float eps0, eps_rel;
     int max_steps;
+    unsigned long long watchdog_ns;  // trace_queued: how long a warp may find the queues empty / a publication pending (%globaltimer)
     int xchg_off;   // byte offset of the compaction scratch in dynamic shared memory (16-byte aligned)
     int dda_legacy;  // 1: path-length deposits one red.global.add.f32 per voxel crossed (SMCRT_DDA_LEGACY; cross-check of the run walker)
     // run walker (walk_dda_runs): fixed-point difference grids per axis, their scale (2^28 / voxel edge) and "touched" flags
@@ -212,7 +213,7 @@ __device__ __forceinline__ bool closed_form_prim(const KParams& P, const SceneVi
     const DevTop T = sc.tops[t];
     if (T.mode != 0) return false;
     Q = P.primsD + T.first;
-    return Q->xf != XF_AFFINE && (Q->kind == 1 || Q->kind == 2);
+    return Q->xf <= XF_TRANSLATE && (Q->kind == 1 || Q->kind == 2);
 }
 static __device__ __noinline__ double polish_hit(const KParams& P, const SceneView& sc, int t, double X, double Y, double Z, double ux, double uy,
                                           double uz, double tmax) {
@@ -1289,9 +1290,17 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
             __syncwarp(grp);
             if (lane == lead) {
                 __threadfence_block();  // slot contents and ring entries before the publication
-                unsigned int spins = 0u;  // publish in reservation order (bounded: see the watchdog below)
-                while (atomicCAS(&qc->published[cls], start, start + (unsigned int)cnt) != start)
-                    if (++spins > (1u << 28)) { atomicAdd(&P.counters[C_SPARE], 1ull); break; }
+                // publish in reservation order.  Bounded by the watchdog period (see below): the wait is for another warp's
+                // few-instruction publication, so only a lost queue entry can make it long
+                unsigned int spins = 0u;
+                unsigned long long t_wd = 0ull;
+                while (atomicCAS(&qc->published[cls], start, start + (unsigned int)cnt) != start) {
+                    if ((++spins & 0xfffu) == 0u) {
+                        const unsigned long long now = globaltimer_ns();
+                        if (!t_wd) t_wd = now;
+                        else if (now - t_wd > P.watchdog_ns) { atomicAdd(&P.counters[C_SPARE], 1ull); break; }
+                    }
+                }
             }
             has = false;
             state = ST_DONE;
@@ -1317,6 +1326,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                     h0 = vq->head[q];
                     n = min(vq->published[q] - h0, (unsigned int)want);
                     if (n && atomicCAS(&qc->head[q], h0, h0 + n) != h0) n = 0;  // another warp was faster: next iteration looks again
+                    if (n) __threadfence_block();  // the producers' slot / ring stores (fenced before their publication) before our loads
                 }
             }
             n = __shfl_sync(full, n, 0);
@@ -1351,25 +1361,32 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         }
         wc = c;
         if (!__any_sync(full, has)) {  // nothing held, nothing to take
-            if (vq->retired == (unsigned int)M) break;  // every slot has found the pool empty: the CTA is done
-            // watchdog: waiting is normal only while other warps finish the last histories (milliseconds).  ~10 s of it means the
-            // queues have lost a slot; leave with an error flag (smcrt_wait reports it) rather than hang the device.
-            // (the wait has its own loop: its counter is not live state of the hot loop)
-            bool stalled = false;
-            for (unsigned int spins = 0u;; ++spins) {
-                unsigned int a = 0u;
-                if (lane < Q_COUNT) {
-                    const unsigned int h = vq->head[lane];
-                    a = vq->published[lane] - h;
+            // Warp-wide control flow is decided by ONE lane's reads of the shared counters, broadcast: per-lane volatile reads could
+            // see different values and split a warp whose later votes and shuffles all use the full mask.
+            // watchdog: waiting is normal only while other warps finish the last histories (milliseconds; seconds for a long tail
+            // with a raised step cap).  P.watchdog_ns of %globaltimer without any queue entry appearing means the queues have
+            // lost a slot: leave with an error flag (smcrt_wait reports it) rather than hang the device.
+            // (the wait has its own loop: its state is not live state of the hot loop)
+            int verdict = 0;  // 1: work appeared, 2: every slot retired -> the CTA is done, 3: watchdog
+            unsigned long long t_wd = 0ull;
+            for (unsigned int spins = 0u; !verdict; ++spins) {
+                if (lane == 0) {
+                    unsigned int a = 0u;
+#pragma unroll
+                    for (int k = 0; k < Q_COUNT; ++k) a |= vq->published[k] - vq->head[k];
+                    if (vq->retired == (unsigned int)M) verdict = 2;
+                    else if (a) verdict = 1;
+                    else if ((spins & 0xfu) == 0u) {  // (%globaltimer is a slow read: every 16th look)
+                        const unsigned long long now = globaltimer_ns();
+                        if (!t_wd) t_wd = now;
+                        else if (now - t_wd > P.watchdog_ns) verdict = 3;
+                    }
                 }
-                if (__any_sync(full, a != 0u) || vq->retired == (unsigned int)M) break;
-                if (spins > (1u << 26)) { stalled = true; break; }
-                __nanosleep(40);
+                verdict = __shfl_sync(full, verdict, 0);
+                if (!verdict) __nanosleep(40);
             }
-            if (stalled) {
-                if (lane == 0) atomicAdd(&P.counters[C_SPARE], 1ull);
-                break;
-            }
+            if (verdict == 3 && lane == 0) atomicAdd(&P.counters[C_SPARE], 1ull);
+            if (verdict >= 2) break;
             continue;
         }
 

@@ -133,3 +133,56 @@ def test_checkpoint_and_resume_is_the_same_job(smcrt, tmp_path, monkeypatch):
     assert a.sum() > 0
     assert abs(a.sum() - b.sum()) <= 1e-5 * a.sum()                 # float atomics: same deposits, different order
     assert np.abs(a - b).max() <= 1e-4 * a.max()
+
+
+def test_nonrigid_transform_takes_plain_sphere_tracing(engine, oracle, smcrt):
+    """A scaled primitive: the reference accepts any 4x4 transform and steps by |d| (inttau2.f90:155-192).  The engine's
+    closed-form ray bounds assume a unit local direction, which only a rigid transform keeps: a non-rigid primitive must report
+    bound = |d|, exact = false, and a scene with one must trace like the oracle's."""
+    from common import random_dirs
+    scale = np.diag([0.5, 0.5, 0.5, 1.0])                      # local = 0.5 * world: a sphere of radius 0.25 becomes one of 0.5
+    shear = np.eye(4); shear[0, 1] = 0.3                       # and a sheared box
+    scene = A.Scene.from_primitives([(A.SPHERE, scale.reshape(-1, order="F"), [0.25]), (A.BOX, shear.reshape(-1, order="F"), [0.9, 0.9, 0.9]),
+                                     (A.BOX, None, [1.0, 1.0, 1.0])],
+                                    [(5.0, 0.5, 0.6, 1.33), (1.0, 0.1, 0.0, 1.2), (0.0, 0.0, 0.0, 1.0)])
+    engine.set_grid(50, 50, 50, 1.0, 1.0, 1.0)
+    engine.set_scene(scene)
+    sp = np.zeros(24); sp[0:3] = [0.05, -0.02, 0.03]
+    engine.set_source(A.SRC_POINT, 0, sp)
+    engine.set_detectors([], np.zeros((0, 20)), [])
+    rng = np.random.default_rng(3)
+    pos, dirs = rng.uniform(-0.9, 0.9, (20000, 3)), random_dirs(rng, 20000)
+    for top in (1, 2):
+        d, b, ex = engine.probe_ray(top, pos, dirs)
+        assert (ex == 0).all() and np.allclose(b, np.abs(d), rtol=1e-6, atol=1e-7)
+    d3, b3, ex3 = engine.probe_ray(3, pos, dirs)                # the untransformed box keeps its exact ray bound
+    assert (ex3 == 1).all() and (b3 >= np.abs(d3) - 1e-6).all()
+    osc = oracle.OracleScene(scene, ((50, 50, 50), (1.0, 1.0, 1.0)), (A.SRC_POINT, 0, sp))
+    n = 20000
+    g = engine.trace_packets(n, 9)
+    o = osc.run(n, 9, per_packet=True, grids=False)
+    same = (g["fate"] == o["fate"]) & (g["nscatt"] == o["nscatt"])
+    assert same.mean() > 0.97, same.mean()
+    assert (g["fate"] == A.FATE_LOST).mean() < 2e-3
+    ensemble_close(g, o, n)
+
+
+def test_queue_watchdog_reports_an_error(tmp_path):
+    """trace_queued's watchdog (kernels.cuh): a warp that finds every queue empty for the whole watchdog period leaves and the run is
+    reported as failed by smcrt_wait instead of hanging the device.  Tripped here on purpose with a period of one microsecond
+    (warps idle for longer than that whenever the last histories of a run finish), in a subprocess: the period is read once."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import rsmcrt_b200 as R\n"
+            "e = R.Engine(1); e.apply(R.Config.load(%r))\n"
+            "try:\n"
+            "    e.run(2000000, 1)\n"
+            "    print('NO ERROR')\n"
+            "except R.SmcrtError as ex:\n"
+            "    print('ERROR:', ex)\n"
+            "e.reset_tallies(); e.close()\n") % (str(RES.parent), str(RES / "jacques.toml"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMCRT_WATCHDOG_MS="0.001", SMCRT_VARIANT_FORCE="4"),
+                       capture_output=True, text=True, timeout=120)
+    assert "ERROR:" in r.stdout and "watchdog" in r.stdout, (r.stdout, r.stderr[-500:])

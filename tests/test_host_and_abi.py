@@ -307,3 +307,14 @@ def test_host_builder_matches_the_oracles_own_builder(smcrt, deck, tmp_path):
     assert np.array_equal(da[0], db[0]) and np.array_equal(da[2], db[2]) and list(da[3]) == list(db[3])
     assert np.allclose(da[1], db[1], rtol=1e-15, atol=0)
     assert (cfg.nphotons, cfg.iseed, cfg.geom_name, cfg.source_name) == (d.nphotons, d.iseed, d.geom_name, d.source_name)
+
+
+def test_normalise_fluence_takes_64_bit_packet_counts():
+    """normalise_fluence (src/writer.f90:25-52): x nx*ny*nz / nphotons.  The reference's nphotons is a default integer; the engine's
+    counts are 64-bit (it traces 4e9 packets per second), and a 3e9-packet job must not normalise by a wrapped negative number
+    (ADVICE r1)."""
+    a = np.full((4, 5, 6), 3.0e9, np.float32)
+    out = A.normalise_fluence(a, (4, 5, 6), (1.0, 2.0, 3.0), 3_000_000_000)
+    assert np.allclose(out, 4 * 5 * 6, rtol=1e-6)
+    with pytest.raises(A.SmcrtError):
+        A.normalise_fluence(a, (4, 5, 6), (1.0, 2.0, 3.0), 0)

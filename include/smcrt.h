@@ -65,7 +65,9 @@ enum smcrt_source_kind {
     SMCRT_SRC_UNIFORM = 3,  /* photon.f90:566-649 */
     SMCRT_SRC_CIRCULAR = 4, /* photon.f90:214-308 */
     SMCRT_SRC_FOCUS = 5,    /* photon.f90:361-563 */
-    SMCRT_SRC_ANNULUS = 6   /* photon.f90:850-1043 */
+    SMCRT_SRC_ANNULUS = 6,  /* photon.f90:850-1043 */
+    SMCRT_SRC_DSLIT = 7,    /* photon.f90:712-780  double slit, hard-coded geometry in units of the wavelength */
+    SMCRT_SRC_APERTURE = 8  /* photon.f90:782-848  square aperture, idem */
 };
 /* source parameter block, 24 doubles (what `photon_origin` + the emitters' dict keys hold) */
 enum smcrt_source_slot {
@@ -74,7 +76,7 @@ enum smcrt_source_slot {
     SMCRT_SP_P1 = 6,        /* [6..8]  dict pos1%x..z  (uniform)    photon.f90:596-606 */
     SMCRT_SP_P2 = 9,        /* [9..11] dict pos2 */
     SMCRT_SP_P3 = 12,       /* [12..14] dict pos3 */
-    SMCRT_SP_RADIUS = 15,   /* dict radius (circular) */
+    SMCRT_SP_RADIUS = 15,   /* dict radius (circular); dslit / aperture: this%wavelength (constant spectrum, parse_spectrum.f90:52-117) */
     SMCRT_SP_FOCAL = 16,    /* dict focalLength */
     SMCRT_SP_BEAM = 17,     /* dict beam_size */
     SMCRT_SP_RLO = 18,      /* dict rlo */

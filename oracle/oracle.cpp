@@ -44,7 +44,7 @@ constexpr double REF_CHANCE = 0.1;
 enum { K_SPHERE = 1, K_BOX, K_TORUS, K_CYLINDER, K_TRIPRISM, K_SEGMENT, K_CAPSULE, K_CONE, K_EGG, K_PLANE,
        K_UNION = 20, K_SMOOTHUNION, K_SUBTRACTION, K_INTERSECTION,
        K_REVOLUTION = 30, K_EXTRUDE, K_ONION, K_TWIST, K_BEND, K_ELONGATE };
-enum { SRC_POINT = 1, SRC_PENCIL, SRC_UNIFORM, SRC_CIRCULAR, SRC_FOCUS, SRC_ANNULUS };
+enum { SRC_POINT = 1, SRC_PENCIL, SRC_UNIFORM, SRC_CIRCULAR, SRC_FOCUS, SRC_ANNULUS, SRC_DSLIT, SRC_APERTURE };
 enum { SP_POS = 0, SP_DIR = 3, SP_P1 = 6, SP_P2 = 9, SP_P3 = 12, SP_RADIUS = 15, SP_FOCAL = 16, SP_BEAM = 17,
        SP_RLO = 18, SP_RHI = 19, SP_SIGMA = 20, SP_ROT = 21, SP_N = 24 };
 enum { DET_CIRCLE = 1, DET_ANNULUS, DET_FIBRE, DET_CAMERA };
@@ -419,8 +419,9 @@ struct Philox {
                  n3 = (uint32_t)p0;
         c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
     }
-    static void block(uint64_t seed, uint64_t id, uint32_t event, uint32_t out[4]) {
-        uint32_t c[4] = {event, (uint32_t)id, (uint32_t)(id >> 32), 0u};
+    // `sub`: 0 = the event's block; 1 = its second block (emitters that draw more than three uniforms: dslit, aperture)
+    static void block(uint64_t seed, uint64_t id, uint32_t event, uint32_t out[4], uint32_t sub = 0u) {
+        uint32_t c[4] = {event, (uint32_t)id, (uint32_t)(id >> 32), sub};
         uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
         for (int r = 0; r < 10; ++r) {
             round(c, k);
@@ -476,6 +477,14 @@ struct Rng {
         }
     }
     double draw(int slot) { return mode == 0 ? u01(w[slot]) : xo.uni(); }
+    // uniforms 4 and 5 of an emission (dslit / aperture): words 0, 1 of the event's second Philox block
+    void draw_extra(double out[2]) {
+        if (mode == 0) {
+            uint32_t x[4];
+            Philox::block(seed, id, event - 1u, x, 1u);
+            out[0] = u01(x[0]); out[1] = u01(x[1]);
+        } else { out[0] = xo.uni(); out[1] = xo.uni(); }
+    }
     double draw_tau() { return mode == 0 ? u01_open0(w[3]) : xo.uni(); }
 };
 
@@ -860,9 +869,10 @@ void aim_and_clip(const Scene& s, Packet& pk, V3 dir, int counter_cap) {
         ++counter;
     }
 }
-// Emit one packet.  xi[0..2] are the uniforms of the event block (slot meaning per source in DESIGN.md §RNG).
+// Emit one packet.  xi[0..2] are the uniforms of the event block (slot meaning per source in DESIGN.md §RNG), xi[3..4] two more
+// for the emitters that draw five (dslit) or four (aperture).
 // Returns false when a rejection step inside the emitter (gaussian annulus, rang) wants a fresh block.
-bool emit(const Scene& s, Packet& pk, const double xi[3]) {
+bool emit(const Scene& s, Packet& pk, const double xi[5]) {
     const Grid& g = s.grid;
     const double* sp = s.src.p;
     V3 opos{sp[SP_POS], sp[SP_POS + 1], sp[SP_POS + 2]};
@@ -934,6 +944,43 @@ bool emit(const Scene& s, Packet& pk, const double xi[3]) {
             dir = dir * fsign(1.0, focal);
             dir = magnitude(dir);
             aim_and_clip(s, pk, dir, 4);
+            break;
+        }
+        case SRC_DSLIT:       // :712-780   (draw order: slit pick, x1, y1, x2, y2)
+        case SRC_APERTURE: {  // :782-848   (draw order: x1, y1, x2, y2)
+            // phase experiments with hard-coded geometry in units of the wavelength (sp[SP_RADIUS] carries it: the slot is unused
+            // by these two kinds); ranu(a, b) = a + xi (b - a), also with b < a (random_mod.f90:126-135)
+            const double lam = sp[SP_RADIUS];
+            auto ranu = [](double a, double b, double u) { return a + u * (b - a); };
+            double x1, y1, z1, x2, y2, z2;
+            if (s.src.kind == SRC_DSLIT) {
+                const double a = 60.0 * lam, b = 20.0 * lam;
+                if (xi[0] > 0.5) x1 = ranu(a / 2.0, a / 2.0 + b, xi[1]);
+                else x1 = ranu(-a / 2.0, -a / 2.0 - b, xi[1]);
+                y1 = ranu(-b * 0.5, b * 0.5, xi[2]);
+                z2 = 5.0 - (1.e-5 * (2.0 * (5.0 / 400.0)));
+                x2 = ranu(-5.0, 5.0, xi[3]);
+                y2 = ranu(-5.0, 5.0, xi[4]);
+                z1 = (10000.0 * lam) - 5.0;
+            } else {
+                const double apwid = 200e-6, b = apwid / 2.0, F = 4.95;
+                x1 = ranu(-b, b, xi[0]);
+                y1 = ranu(-b, b, xi[1]);
+                z1 = (1.0 / ((((F / apwid) * (F / apwid)) / 2.0) * lam)) - 0.5;
+                x2 = ranu(-0.5, 0.5, xi[2]);
+                y2 = ranu(-0.5, 0.5, xi[3]);
+                z2 = 0.5 - (1.e-5 * (2.0 * 0.5 / 400.0));
+            }
+            pk.pos = V3{x2, y2, z2};
+            pk.phase = std::sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1));
+            pk.nxp = (x2 - x1) / pk.phase;
+            pk.nyp = (y2 - y1) / pk.phase;
+            pk.nzp = -std::fabs(z2 - z1) / pk.phase;
+            pk.cost = pk.nzp;
+            pk.sint = std::sqrt(1.0 - pk.cost * pk.cost);
+            pk.phi = std::atan2(pk.nyp, pk.nxp);
+            pk.cosp = std::cos(pk.phi);
+            pk.sinp = std::sin(pk.phi);
             break;
         }
         case SRC_ANNULUS: {  // :850-1043
@@ -1165,7 +1212,8 @@ void propagate(const Scene& s, Tally& T, ThreadCounters& C, Rng& rng, Work& W, b
     auto emit_once = [&]() {
         for (;;) {
             rng.begin_event();
-            double xi[3] = {rng.draw(0), rng.draw(1), rng.draw(2)};
+            double xi[5] = {rng.draw(0), rng.draw(1), rng.draw(2), 0.0, 0.0};
+            if (s.src.kind >= SRC_DSLIT) rng.draw_extra(xi + 3);
             if (emit(s, pk, xi)) return;
             C.retries += 1;
         }
@@ -1396,7 +1444,9 @@ void orc_emit(void* h, int64_t n, const double* xi4, double* pos, double* dir, i
     Scene* s = (Scene*)h;
     for (int64_t i = 0; i < n; ++i) {
         Packet pk{};
-        bool r = emit(*s, pk, xi4 + 4 * i);
+        // probe convention for the five-uniform emitters: uniforms 4 and 5 are xi4[3] and 1 - xi4[3] (smcrt_probe_emit does the same)
+        const double xi[5] = {xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], xi4[4 * i + 3], 1.0 - xi4[4 * i + 3]};
+        bool r = emit(*s, pk, xi);
         if (ok) ok[i] = r ? 1 : 0;
         pos[3 * i] = pk.pos.x; pos[3 * i + 1] = pk.pos.y; pos[3 * i + 2] = pk.pos.z;
         dir[3 * i] = pk.nxp; dir[3 * i + 1] = pk.nyp; dir[3 * i + 2] = pk.nzp;
@@ -1499,7 +1549,8 @@ double orc_test_kernel(void* h, int64_t nphotons, uint64_t seed, int end_early, 
             Packet pk{};
             for (;;) {
                 rng.begin_event();
-                double xi[3] = {rng.draw(0), rng.draw(1), rng.draw(2)};
+                double xi[5] = {rng.draw(0), rng.draw(1), rng.draw(2), 0.0, 0.0};
+                if (s->src.kind >= SRC_DSLIT) rng.draw_extra(xi + 3);
                 if (emit(*s, pk, xi)) break;
             }
             pk.step = 0;

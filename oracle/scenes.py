@@ -206,7 +206,7 @@ def parse_source(t):
         elif name == "uniform":
             raise ValueError(f"Uniform source requires {key} variable")
     p[6:9], p[9:12], p[12:15] = corners
-    p[15] = t.get("radius", 0.5)
+    p[15] = t.get("wavelength", 500.0) if name in ("dslit", "aperture") else t.get("radius", 0.5)   # slot 15: see include/smcrt.h
     p[16] = t.get("focalLength", 1.0)
     p[17] = t.get("beam_size", 0.5)
     p[18] = t.get("rlo", 0.5)

@@ -21,7 +21,7 @@ FATE_ABSORBED, FATE_ESCAPED, FATE_ROULETTE, FATE_LOST = 0, 1, 2, 3
 SPHERE, BOX, TORUS, CYLINDER, TRIPRISM, SEGMENT, CAPSULE, CONE, EGG, PLANE = range(1, 11)
 MODEL_UNION, MODEL_SMOOTHUNION, MODEL_SUBTRACTION, MODEL_INTERSECTION = 20, 21, 22, 23
 MOD_REVOLUTION, MOD_EXTRUDE, MOD_ONION, MOD_TWIST, MOD_BEND, MOD_ELONGATE = 30, 31, 32, 33, 34, 35
-SRC_POINT, SRC_PENCIL, SRC_UNIFORM, SRC_CIRCULAR, SRC_FOCUS, SRC_ANNULUS = range(1, 7)
+SRC_POINT, SRC_PENCIL, SRC_UNIFORM, SRC_CIRCULAR, SRC_FOCUS, SRC_ANNULUS, SRC_DSLIT, SRC_APERTURE = range(1, 9)
 DET_CIRCLE, DET_ANNULUS, DET_FIBRE, DET_CAMERA = 1, 2, 3, 4
 
 

@@ -527,7 +527,7 @@ extern "C" int smcrt_set_optprops(smcrt_ctx* c, int top_index, double mus, doubl
 // ---- source ----------------------------------------------------------------------------------------------
 extern "C" int smcrt_set_source(smcrt_ctx* c, int kind, int subtype, const double* p) {
     if (!c || !p) return set_err("smcrt_set_source: null argument");
-    if (kind < SMCRT_SRC_POINT || kind > SMCRT_SRC_ANNULUS) return set_err("No such source!");  // init_source, photon.f90:155
+    if (kind < SMCRT_SRC_POINT || kind > SMCRT_SRC_APERTURE) return set_err("No such source!");  // init_source, photon.f90:155
     if ((kind == SMCRT_SRC_FOCUS || kind == SMCRT_SRC_ANNULUS) && (subtype < 1 || subtype > 3)) return set_err("No such beam type!");
     c->src_kind = kind; c->src_sub = subtype; c->src_alt = 0;
     for (int i = 0; i < 24; ++i) c->sp[i] = (float)p[i];

@@ -317,21 +317,21 @@ void parse_source(const Table& root, Config& c) {
     c.nphotons = get_int(t, "nphotons", 1000000);
     static const std::pair<const char*, int> kinds[] = {{"point", SMCRT_SRC_POINT},     {"pencil", SMCRT_SRC_PENCIL},
                                                          {"uniform", SMCRT_SRC_UNIFORM}, {"circular", SMCRT_SRC_CIRCULAR},
-                                                         {"focus", SMCRT_SRC_FOCUS},     {"annulus", SMCRT_SRC_ANNULUS}};
+                                                         {"focus", SMCRT_SRC_FOCUS},     {"annulus", SMCRT_SRC_ANNULUS},
+                                                         {"dslit", SMCRT_SRC_DSLIT},     {"aperture", SMCRT_SRC_APERTURE}};
     c.src_kind = 0;
     for (auto& k : kinds)
         if (c.source == k.first) c.src_kind = k.second;
     if (c.src_kind == 0) {
-        if (c.source == "slm" || c.source == "dslit" || c.source == "aperture")
-            cfg_fail("source '" + c.source + "' (image / phase experiments, src/photon.f90:159-212,712-848) is outside the "
-                     "hot-path scope of this engine");
+        if (c.source == "slm")
+            cfg_fail("source 'slm' (image-driven emitter, src/photon.f90:159-212) is outside the hot-path scope of this engine");
         cfg_fail("No such source!");  // init_source, src/photon.f90:155
     }
     double pos[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, rot[3] = {0, 0, 0};
     if (c.source != "uniform") {
         if (!get_vec3(t, "position", pos)) cfg_fail("source needs a 'position' vector");
     }
-    if (c.source == "focus" || c.source == "annulus") {
+    if (c.source == "focus" || c.source == "annulus" || c.source == "dslit" || c.source == "aperture") {
         if (!get_vec3(t, "rotation", rot)) cfg_fail("Source requires rotation variable");
         double l = std::sqrt(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2]);
         if (l < 1e-8) cfg_fail("Need to specify rotation that has length greater than 0.0");
@@ -398,7 +398,8 @@ void parse_source(const Table& root, Config& c) {
         s[SMCRT_SP_P3 + i] = corners[2][i];
         s[SMCRT_SP_ROT + i] = rot[i];
     }
-    s[SMCRT_SP_RADIUS] = radius; s[SMCRT_SP_FOCAL] = focal; s[SMCRT_SP_BEAM] = beam;
+    s[SMCRT_SP_RADIUS] = (c.src_kind == SMCRT_SRC_DSLIT || c.src_kind == SMCRT_SRC_APERTURE) ? c.wavelength : radius;  // (see smcrt.h)
+    s[SMCRT_SP_FOCAL] = focal; s[SMCRT_SP_BEAM] = beam;
     s[SMCRT_SP_RLO] = rlo; s[SMCRT_SP_RHI] = rhi; s[SMCRT_SP_SIGMA] = sigma;
     c.src_subtype = 0;
     if (c.src_kind == SMCRT_SRC_FOCUS) {

@@ -880,21 +880,62 @@ __device__ __forceinline__ void xform_pos(const float T[12], const float l[3], f
     o[1] = T[4] * l[0] + T[5] * l[1] + T[6] * l[2] + T[7];
     o[2] = T[8] * l[0] + T[9] * l[1] + T[10] * l[2] + T[11];
 }
-__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]);
+__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float u3, float u4, float pos[3], float dir[3]);
 struct Emitted {
     float x, y, z, dx, dy, dz;
     bool ok;
 };
-static __device__ __noinline__ Emitted emit_packet(const KParams& P, float u0, float u1, float u2) {  // out of line: all source kinds live here
+// (pid, event): dslit / aperture draw five / four uniforms; the two beyond the event's block come from its SECOND Philox block
+// (counter word 3 = 1), words 0 and 1
+static __device__ __noinline__ Emitted emit_packet(const KParams& P, float u0, float u1, float u2, unsigned long long pid, uint32_t event) {  // out of line: all source kinds live here
     float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
     Emitted e;
-    e.ok = emit_packet_v(P, u0, u1, u2, pos, dir);
+    float u3 = 0.f, u4 = 0.f;
+    if (P.src_kind >= 7) {
+        uint32_t x[4];
+        philox4x32_10(event, (uint32_t)pid, (uint32_t)(pid >> 32), 1u, P.seed_lo, P.seed_hi, x);
+        u3 = u01(x[0]); u4 = u01(x[1]);
+    }
+    e.ok = emit_packet_v(P, u0, u1, u2, u3, u4, pos, dir);
     e.x = pos[0]; e.y = pos[1]; e.z = pos[2]; e.dx = dir[0]; e.dy = dir[1]; e.dz = dir[2];
     return e;
 }
-__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float pos[3], float dir[3]) {
+__device__ __forceinline__ bool emit_packet_v(const KParams& P, float u0, float u1, float u2, float u3, float u4, float pos[3], float dir[3]) {
     const float* sp = P.sp;
     switch (P.src_kind) {
+        case 7:    // dslit :712-780 (draws: slit pick, x1, y1, x2, y2)
+        case 8: {  // aperture :782-848 (draws: x1, y1, x2, y2)
+            // hard-coded geometry in units of the wavelength (sp[15]); the source point (x1, y1, z1) is 1e3..1e7 grid units away, so
+            // the direction is formed in FP64: (x2 - x1) / |.| with |x2 - x1| << |z2 - z1| would lose its digits in FP32
+            const double lam = (double)sp[15];
+            double x1, y1, z1, x2, y2, z2;
+            if (P.src_kind == 7) {
+                const double a = 60.0 * lam, b = 20.0 * lam;
+                x1 = u0 > 0.5f ? a * 0.5 + (double)u1 * b : -a * 0.5 - (double)u1 * b;   // ranu(lo, hi) = lo + xi (hi - lo), hi < lo allowed
+                y1 = -b * 0.5 + (double)u2 * b;
+                z2 = 5.0 - (1.e-5 * (2.0 * (5.0 / 400.0)));
+                x2 = -5.0 + 10.0 * (double)u3;
+                y2 = -5.0 + 10.0 * (double)u4;
+                z1 = 10000.0 * lam - 5.0;
+            } else {
+                const double apwid = 200e-6, b = apwid * 0.5, F = 4.95;
+                x1 = -b + (double)u0 * apwid;
+                y1 = -b + (double)u1 * apwid;
+                z1 = 1.0 / ((((F / apwid) * (F / apwid)) * 0.5) * lam) - 0.5;
+                x2 = -0.5 + (double)u2;
+                y2 = -0.5 + (double)u3;
+                z2 = 0.5 - (1.e-5 * (2.0 * 0.5 / 400.0));
+            }
+            const double ex = x2 - x1, ey = y2 - y1, ez = z2 - z1;
+            const double il = rsqrt(ex * ex + ey * ey + ez * ez);
+            pos[0] = (float)x2; pos[1] = (float)y2; pos[2] = (float)z2;
+            // z2 = zmax - 2.5e-7 (resp. - 2.5e-8) rounds ONTO the grid face in FP32: same inset as the other emitters
+            nudge_face(pos[0], P.gmax[0]); nudge_face(pos[1], P.gmax[1]); nudge_face(pos[2], P.gmax[2]);
+            dir[0] = (float)(ex * il); dir[1] = (float)(ey * il); dir[2] = (float)(-fabs(ez) * il);
+            const float nl = rsqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);  // unit in FP32 as well
+            dir[0] *= nl; dir[1] *= nl; dir[2] *= nl;
+            return true;
+        }
         case 1: {  // point :311-359
             pos[0] = sp[0]; pos[1] = sp[1]; pos[2] = sp[2];
             float sinp, cosp;
@@ -1494,12 +1535,14 @@ __global__ void probe_scatter_kernel(long long n, const float* dir, const float*
 __global__ void probe_emit_kernel(const __grid_constant__ KParams P, long long n, const float* xi4, float* pos, float* dir, int* cell) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
-        emit_packet_v(P, xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], p, d);
+        // (probe convention for the five-uniform emitters: uniforms 4 and 5 are xi4[3] and 1 - xi4[3])
+        emit_packet_v(P, xi4[4 * i], xi4[4 * i + 1], xi4[4 * i + 2], xi4[4 * i + 3], 1.0f - xi4[4 * i + 3], p, d);
         for (int a = 0; a < 3; ++a) { pos[3 * i + a] = p[a]; dir[3 * i + a] = d[a]; }
         // get_voxel_cart (src/grid.f90:51-78)
         const int dims[3] = {P.nxg, P.nyg, P.nzg};
         for (int a = 0; a < 3; ++a) {
             int c = (int)floorf((p[a] + P.gmax[a]) * P.inv_vox[a]) + 1;
+            if (c == dims[a] + 1 && p[a] < P.gmax[a]) c = dims[a];  // the scaled form rounds up within ~n ulp of the upper face (cf. in_grid / voxel_of)
             if (c < 1 || c > dims[a]) c = -1;
             cell[3 * i + a] = c;
         }

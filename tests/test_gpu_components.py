@@ -278,3 +278,54 @@ def test_closed_form_normals_reproduce_the_reference_stencil(engine, oracle):
     o = pos - centres[1]
     plain = o / np.linalg.norm(o, axis=1, keepdims=True)
     assert np.abs(plain - osc.normal(2, pos)).max() > 1e-4
+
+
+@pytest.mark.parametrize("kind,half,lam", [("dslit", 5.0, 500.0), ("dslit", 5.0, 0.05), ("aperture", 0.5, 500.0), ("aperture", 0.5, 6.3e-5)])
+def test_emit_dslit_and_aperture(engine, oracle, smcrt, kind, half, lam):
+    """The phase-experiment emitters (src/photon.f90:712-780 double slit, :782-848 square aperture): hard-coded geometry in units
+    of the wavelength, five resp. four uniforms per packet (the two beyond the event's block come from its second Philox block).
+    Deterministic from fixed uniforms -> launch point and direction against the oracle (north-star 1e-6 bar), and a whole run on
+    the same streams."""
+    from rsmcrt_b200 import api as A
+    p = np.zeros(24)
+    p[0:3] = [0.0, 0.0, 0.0]
+    p[3:6] = [0.0, 0.0, -1.0]
+    p[15] = lam                                  # SMCRT_SP_RADIUS slot: this%wavelength for these two kinds (include/smcrt.h)
+    p[21:24] = [0.0, 0.0, -1.0]
+    k = A.SRC_DSLIT if kind == "dslit" else A.SRC_APERTURE
+    scene = A.Scene.from_primitives([(A.BOX, None, [half, half, half])], [(0.3 / half, 0.05 / half, 0.0, 1.0)])
+    engine.set_grid(100, 100, 100, half, half, half)
+    engine.set_scene(scene)
+    engine.set_source(k, 0, p)
+    engine.set_detectors([], np.zeros((0, 20)), [])
+    osc = oracle.OracleScene(scene, ((100, 100, 100), (half, half, half)), (k, 0, p))
+    rng = np.random.default_rng(8)
+    xi = rng.random((20000, 4)).astype(np.float32).astype(np.float64)
+    xi[0], xi[1] = 0.0, 1.0 - 2.0 ** -24
+    pg, dg, cg = engine.probe_emit(xi)
+    pr, dr, cr, ok = osc.emit(xi)
+    assert ok.all()
+    assert np.abs(pg - pr).max() < 2e-6 * half
+    assert np.abs(dg - dr).max() < 1e-6
+    assert (cg == cr).mean() > 0.999            # start voxel (grid%get_voxel): FP32 vs FP64 at a voxel face
+    assert np.abs(np.linalg.norm(dg, axis=1) - 1.0).max() < 1e-6 and (dg[:, 2] < 0).all()
+    # whole histories on the same streams (the extra Philox block included)
+    n = 20000
+    g = engine.trace_packets(n, 12)
+    o = osc.run(n, 12, per_packet=True, grids=False)
+    same = (g["fate"] == o["fate"]) & (g["nscatt"] == o["nscatt"])
+    assert same.mean() > 0.99, same.mean()
+
+
+def test_dslit_deck_parses(smcrt):
+    """[source] name = "dslit" / "aperture" need position, direction and rotation like the reference's parser asks
+    (src/parse/parse_source.f90:100-150); the wavelength travels in the radius slot."""
+    from conftest import RES
+    from rsmcrt_b200 import api as A
+    text = (RES / "scat_test.toml").read_text().replace('name = "point"', 'name = "dslit"\nrotation = [0.0, 0.0, -1.0]\ndirection = "-z"').replace("wavelength = 500.0", "wavelength = 0.05")
+    cfg = smcrt.Config.loads(text)
+    k, s, p = cfg.source
+    assert k == A.SRC_DSLIT and p[15] == 0.05 and list(p[21:24]) == [0.0, 0.0, -1.0]
+    from oracle import scenes
+    d = scenes.loads(text)
+    assert d.source[0] == k and np.allclose(d.source[2], p)

@@ -258,6 +258,22 @@ double smcrt_segments_per_packet(const smcrt_ctx* ctx);
 int smcrt_run_sources(smcrt_ctx* ctx, int64_t n_src, const double* pos, int64_t nphotons_per_source, uint64_t seed,
                       int64_t id_offset, int tally_mode, int survival_bias, double threshold, double chance,
                       double* det_totals, int32_t* layer_out);
+/* inverse_MCRT (src/kernelsMod.f90:1462-1751): search for the optical properties of ONE top-level SDF that make the detectors read
+ * their target values.  The reference's loop is the skeleton of a LIPO search: every step draws a trial point uniformly inside
+ * fixed bounds for the properties being sought (mus, mua in [0,100], g in [-1,1], n in [1,20]; :1604-1611), runs run_MCRT, and
+ * scores it with inverse_evaluate = -mean_i |total_i / nphotons - target_i| over the detectors whose target is not -1
+ * (:1753-1787); detectors are reset between steps (:1646).  Same here, in one call:
+ *   top_index   1-based index into array(:) (the reference looks it up from [inverse] layer, :1582-1592)
+ *   find_mask   1 = mus, 2 = mua, 4 = g, 8 = n are sought; the others keep the scene's values
+ *   bounds      {mus_lo, mus_hi, mua_lo, mua_hi, g_lo, g_hi, n_lo, n_hi} or NULL for the reference's
+ *   targets     per detector, -1 = no target (detector%targetValue)
+ *   table       max_steps x 5 (row-major): mus, mua, g, n, error of every step -- gradDescentData(:, 1:5)
+ *   best_step   0-based row with the largest (least negative) error
+ * Step k traces packet ids [id_offset, id_offset + nphotons) with seed + k.  One deliberate difference: the reference draws the
+ * trial into its table but runs every step with the ORIGINAL properties (`mono(mus, mua, hgg, n)`, :1694 -- the trial values
+ * never reach the scene); here the trial is what runs.  The scene's properties are restored on return.  Blocking. */
+int smcrt_inverse_mcrt(smcrt_ctx* ctx, int top_index, int find_mask, const double* bounds, int max_steps, int64_t nphotons, uint64_t seed,
+                       int tally_mode, const double* targets, double* table, int* best_step);
 /* red.global.add.f32 throughput of device 0 on the context's own path-length grid (the secondary bound of -Dpathlength mode,
  * update_grids src/inttau2.f90:417-441).  pattern 0: uniform-random voxels; 1: every thread walks the same z-column of `span`
  * voxels (beam axis of a pencil source); 2: runs of `span` x-consecutive voxels from random starts (DDA-like).  Zeroes jmean. */

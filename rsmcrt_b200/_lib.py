@@ -47,6 +47,8 @@ PROTOTYPES = {
     "smcrt_run_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double]),
     "smcrt_wait": (C.c_int, [C.c_void_p]),
     "smcrt_last_run_ms": (C.c_double, [C.c_void_p]),
+    "smcrt_inverse_mcrt": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int64, C.c_uint64, C.c_int, c_double_p, c_double_p,
+                                     C.POINTER(C.c_int)]),
     "smcrt_segment_mode": (C.c_int, [C.c_void_p]),
     "smcrt_segments_per_packet": (C.c_double, [C.c_void_p]),
     "smcrt_launch_count": (C.c_int64, [C.c_void_p]),

@@ -376,6 +376,16 @@ class Engine:
         """-1 until the first large run has timed the candidates; then 0..5 (smcrt_kernel_variant)."""
         return int(self._L.smcrt_kernel_variant(self._h, int(tally_mode)))
 
+    def inverse_mcrt(self, top_index, find_mask, targets, max_steps, nphotons, seed, bounds=None, tally_mode=TALLY_ABSORB):
+        """inverse_MCRT's search loop (smcrt_inverse_mcrt). -> (table (max_steps, 5): mus, mua, g, n, error; best row)."""
+        t = _f64(targets)
+        table = np.zeros((int(max_steps), 5))
+        best = C.c_int(0)
+        b = None if bounds is None else _f64(bounds)
+        check(self._L.smcrt_inverse_mcrt(self._h, int(top_index), int(find_mask), None if b is None else _p(b, C.c_double), int(max_steps),
+                                         int(nphotons), int(seed), int(tally_mode), _p(t, C.c_double), _p(table, C.c_double), C.byref(best)))
+        return table, int(best.value)
+
     @property
     def segment_mode(self):
         """-Dpathlength deposits of this scene: 0 = deposit kernel, 1 = inline walks, -1 = not timed yet (smcrt_segment_mode)."""

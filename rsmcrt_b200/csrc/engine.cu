@@ -1733,6 +1733,56 @@ extern "C" int smcrt_run_sources(smcrt_ctx* c, int64_t n_src, const double* pos,
     c->src_kind = keep_kind; c->src_sub = keep_sub; c->src_alt = keep_alt;
     return err ? err : wrc;
 }
+extern "C" int smcrt_inverse_mcrt(smcrt_ctx* c, int top_index, int find_mask, const double* bounds, int max_steps, int64_t nphotons,
+                                  uint64_t seed, int tally_mode, const double* targets, double* table, int* best_step) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (top_index < 1 || top_index > (int)c->tops.size()) return set_err("smcrt_inverse_mcrt: top_index %d out of range", top_index);
+    if (!(find_mask & 15)) return set_err("Please select at least one of mus, mua, hgg, n to find with inverse MCRT");  // :1577
+    if (max_steps < 1 || nphotons < 1 || !targets || !table) return set_err("smcrt_inverse_mcrt: invalid arguments");
+    const int n_det = (int)c->hdets.size();
+    int n_target = 0;
+    for (int d = 0; d < n_det; ++d) n_target += targets[d] != -1.0;
+    if (!n_target) return set_err("smcrt_inverse_mcrt: no detector has a target value");
+    static const double ref_bounds[8] = {0.0, 100.0, 0.0, 100.0, -1.0, 1.0, 1.0, 20.0};  // :1604-1611
+    const double* B = bounds ? bounds : ref_bounds;
+    const int t = top_index - 1;
+    const double keep[4] = {c->opt_mus[t], c->opt_mua[t], c->opt_hgg[t], c->opt_n[t]};
+    uint64_t s = seed ^ 0x696E7665727365ull;  // trial points: SplitMix64 (the reference's ran2 stream is unpinned)
+    auto uni = [&]() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    };
+    std::vector<double> bins((size_t)std::max<long long>(c->det_total, 1));
+    int best = 0;
+    for (int k = 0; k < max_steps && !rc; ++k) {
+        double v[4];
+        for (int q = 0; q < 4; ++q) v[q] = (find_mask >> q) & 1 ? uni() * (B[2 * q + 1] - B[2 * q]) + B[2 * q] : keep[q];
+        if ((rc = smcrt_set_optprops(c, top_index, v[0], v[1], v[2], v[3]))) break;
+        if ((rc = smcrt_reset_tallies(c))) break;                                   // reset(dects), :1646
+        if ((rc = smcrt_run(c, nphotons, seed + (uint64_t)k, 0, tally_mode, 0, -1.0, -1.0))) break;
+        if ((rc = smcrt_fetch(c, nullptr, nullptr, nullptr, bins.data(), nullptr, 0))) break;
+        double e = 0.0;                                                              // inverse_evaluate, :1753-1787
+        for (int d = 0; d < n_det; ++d) {
+            if (targets[d] == -1.0) continue;
+            double total = 0.0;
+            for (long long b = 0; b < c->hdets[d].count; ++b) total += bins[(size_t)(c->hdets[d].offset + b)];
+            e += std::fabs(total / (double)nphotons - targets[d]);
+        }
+        e = -e / n_target;
+        for (int q = 0; q < 4; ++q) table[5 * k + q] = v[q];
+        table[5 * k + 4] = e;
+        if (e > table[5 * best + 4]) best = k;
+    }
+    const int rc2 = smcrt_set_optprops(c, top_index, keep[0], keep[1], keep[2], keep[3]);
+    if (!rc) smcrt_reset_tallies(c);
+    if (best_step) *best_step = best;
+    return rc ? rc : rc2;
+}
 extern "C" int smcrt_bench_red(smcrt_ctx* c, int pattern, int span, int64_t n_ops, double* ops_per_s) {
     if (!c || !ops_per_s) return set_err("smcrt_bench_red: null argument");
     if (c->nxg == 0) return set_err("smcrt_bench_red: no grid set (smcrt_set_grid)");

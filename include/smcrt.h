@@ -258,6 +258,24 @@ double smcrt_segments_per_packet(const smcrt_ctx* ctx);
 int smcrt_run_sources(smcrt_ctx* ctx, int64_t n_src, const double* pos, int64_t nphotons_per_source, uint64_t seed,
                       int64_t id_offset, int tally_mode, int survival_bias, double threshold, double chance,
                       double* det_totals, int32_t* layer_out);
+/* trackHistory (src/historyStack.f90:89-108,184-226; [[detectors]] trackHistory, parse_detectors.f90:175-182).  The reference
+ * pushes (position, step) at the launch and at every interaction point (kernelsMod.f90:1954,1959) and writes the list when the
+ * packet hits a detector that tracks histories (detector_base.f90:157-160) -- serial builds only ("incompatable with OpenMP").
+ * Here the transport kernels only NOTE which packet hit which tracking detector (16 bytes per hit); because a packet's random
+ * stream depends on (seed, packet id) alone, its vertex list is then produced by tracing just those packets AGAIN with recording
+ * switched on: no per-packet vertex storage for the 1e8 packets that hit nothing.
+ *   smcrt_set_track_history   one flag per detector of the current table (a new smcrt_set_detectors clears them)
+ *   smcrt_history_hits        (packet id, 1-based detector) of up to max_hits hits since the last reset, sorted by id; *total = all
+ *                             hits seen (2^20 are kept per GPU)
+ *   smcrt_history_replay      vertices: n x max_vertices x 4 floats (x, y, z, event index; the launch point first, every interaction
+ *                             point, then the hit point on the detector plane with the detector's 1-based index as 4th component);
+ *                             n_vertices: how many each packet produced up to the END of its history (may exceed max_vertices:
+ *                             the rest is not stored); hit_vertex: the vertex count at its first tracked hit (-1 = none).  seed and
+ *                             survival_bias must be those of the run.  Tallies and counters of the context are left untouched. */
+int smcrt_set_track_history(smcrt_ctx* ctx, int n_det, const int32_t* track);
+int smcrt_history_hits(smcrt_ctx* ctx, int64_t max_hits, uint64_t* packet_ids, int32_t* det_index, int64_t* total);
+int smcrt_history_replay(smcrt_ctx* ctx, int64_t n, const uint64_t* packet_ids, uint64_t seed, int survival_bias, int max_vertices,
+                         float* vertices, int32_t* n_vertices, int32_t* hit_vertex);
 /* inverse_MCRT (src/kernelsMod.f90:1462-1751): search for the optical properties of ONE top-level SDF that make the detectors read
  * their target values.  The reference's loop is the skeleton of a LIPO search: every step draws a trial point uniformly inside
  * fixed bounds for the properties being sought (mus, mua in [0,100], g in [-1,1], n in [1,20]; :1604-1611), runs run_MCRT, and

@@ -66,6 +66,15 @@ int smcrt_normalise_fluence(float* array, int nxg, int nyg, int nzg, double xmax
 int smcrt_write_nrrd_f32(const char* path, const float* data, int nxg, int nyg, int nzg, const char* meta);
 /* write_detected_photons (writer.f90:55-134): out_dir/detector_<i>.dat for every non-camera detector */
 int smcrt_write_detectors(const smcrt_config* cfg, const double* det_bins, const char* out_dir);
+/* history_stack_t%write / %finish (src/historyStack.f90:163-226): the vertex lists of the detected packets as ONE file, type by
+   extension like init_historyStack (:47-55): .obj ("v x y z" lines, then one "l i j k ..." polyline per packet, 1-based vertex
+   indices), .ply (ascii header with the final vertex / edge counts, vertices, then vertex-index pairs) or .json ({"<k>_0": [[x,y,z],
+   ...], ...}), numbers as es15.8e2 like the reference's writers.  vertices: n x max_vertices x 4 floats, counts[k] <= max_vertices
+   vertices of packet k are written. */
+int smcrt_history_write(const char* path, int64_t n, int max_vertices, const float* vertices, const int32_t* counts);
+/* [[detectors]] trackHistory of detector i (dects(:) order) and the [[detectors]] historyFileName (default "photPos.obj") */
+int smcrt_config_detector_track(const smcrt_config* cfg, int i);
+const char* smcrt_config_history_filename(const smcrt_config* cfg);
 /* metadata text written into NRRD headers (the `dict` toml dump, kernelsMod.f90:2378-2382) */
 const char* smcrt_config_metadata(const smcrt_config* cfg);
 

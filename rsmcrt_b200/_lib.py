@@ -47,6 +47,9 @@ PROTOTYPES = {
     "smcrt_run_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double]),
     "smcrt_wait": (C.c_int, [C.c_void_p]),
     "smcrt_last_run_ms": (C.c_double, [C.c_void_p]),
+    "smcrt_set_track_history": (C.c_int, [C.c_void_p, C.c_int, c_int32_p]),
+    "smcrt_history_hits": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), c_int32_p, C.POINTER(C.c_int64)]),
+    "smcrt_history_replay": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.c_int, c_float_p, c_int32_p, c_int32_p]),
     "smcrt_inverse_mcrt": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int64, C.c_uint64, C.c_int, c_double_p, c_double_p,
                                      C.POINTER(C.c_int)]),
     "smcrt_segment_mode": (C.c_int, [C.c_void_p]),
@@ -101,6 +104,9 @@ PROTOTYPES = {
     "smcrt_checkpoint_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, c_float_p, C.c_int64]),
     "smcrt_checkpoint_read": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), c_float_p, C.c_int64]),
     "smcrt_config_metadata": (C.c_char_p, [C.c_void_p]),
+    "smcrt_history_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, c_float_p, c_int32_p]),
+    "smcrt_config_detector_track": (C.c_int, [C.c_void_p, C.c_int]),
+    "smcrt_config_history_filename": (C.c_char_p, [C.c_void_p]),
     "smcrt_default_mcrt": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, c_double_p,
                                      C.POINTER(Counters)]),
 }

@@ -376,6 +376,27 @@ class Engine:
         """-1 until the first large run has timed the candidates; then 0..5 (smcrt_kernel_variant)."""
         return int(self._L.smcrt_kernel_variant(self._h, int(tally_mode)))
 
+    # ---- trackHistory ------------------------------------------------------------------------------
+    def set_track_history(self, flags):
+        f = _i32(flags)
+        check(self._L.smcrt_set_track_history(self._h, len(f), _p(f, C.c_int32) if len(f) else None))
+
+    def history_hits(self, max_hits=1 << 20):
+        """-> (packet ids, 1-based detector indices, total hits seen) since the last reset, sorted by packet id."""
+        ids, det, total = np.zeros(max_hits, np.uint64), np.zeros(max_hits, np.int32), C.c_int64(0)
+        check(self._L.smcrt_history_hits(self._h, max_hits, _p(ids, C.c_uint64), _p(det, C.c_int32), C.byref(total)))
+        n = min(max_hits, int(total.value))
+        return ids[:n], det[:n], int(total.value)
+
+    def history_replay(self, ids, seed, survival_bias=False, max_vertices=256):
+        """-> (vertices (n, max_vertices, 4), n_vertices (n,), hit_vertex (n,))   (smcrt_history_replay)"""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        n = len(ids)
+        v, nv, hv = np.zeros((n, max_vertices, 4), np.float32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        check(self._L.smcrt_history_replay(self._h, n, _p(ids, C.c_uint64), int(seed), int(survival_bias), int(max_vertices),
+                                           _p(v, C.c_float), _p(nv, C.c_int32), _p(hv, C.c_int32)))
+        return v, nv, hv
+
     def inverse_mcrt(self, top_index, find_mask, targets, max_steps, nphotons, seed, bounds=None, tally_mode=TALLY_ABSORB):
         """inverse_MCRT's search loop (smcrt_inverse_mcrt). -> (table (max_steps, 5): mus, mua, g, n, error; best row)."""
         t = _f64(targets)

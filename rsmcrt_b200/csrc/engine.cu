@@ -124,6 +124,10 @@ struct DeviceState {
     unsigned int* jdiff_used = nullptr;
     bool jdiff_dirty = false;
     long long jdiff_packets = 0;
+    // trackHistory: (packet id, detector) of every hit on a history-tracking detector since the last reset
+    unsigned long long* hist_ids = nullptr;
+    int* hist_det = nullptr;
+    unsigned long long* hist_n = nullptr;
     // segment buffer of the path-length mode: seg_records records of 32 bytes, split evenly between the CTAs of a trace launch
     float4* seg_buf = nullptr;
     unsigned int* seg_count = nullptr;   // [SEG_MAX_SHARES]
@@ -191,6 +195,8 @@ struct smcrt_ctx {
     bool pending = false;
     // culling grid (built at upload time for scenes with many top-level SDFs)
     bool cull_on = false, cull_allowed = true, scene_lipschitz = true, compact_allowed = false;
+    std::vector<int32_t> track;  // per detector: trackHistory
+    bool any_track = false;
     int seg_inline = -1;        // path-length mode: 1 = the trace kernels walk their segments themselves, 0 = recorded + deposit kernel, -1 = not timed yet
     double seg_per_packet = 0;  // measured straight segments per packet of the current scene (path-length mode); 0 = not measured
     bool dda_legacy = false;  // SMCRT_DDA_LEGACY at smcrt_create: path-length deposits one red per voxel crossed (A/B switch, tests)
@@ -205,6 +211,11 @@ struct smcrt_ctx {
     bool cull_key_valid = false;
     int touched_modes = 0;   // OR of the tally modes run since the last reset: only those grids are reduced
     int dirty_modes = 7;     // grids that may hold non-zero voxels on SOME device (cleared by smcrt_reset_tallies)
+    const unsigned long long* replay_ids = nullptr;  // set for the duration of smcrt_history_replay (device pointers)
+    float4* replay_vert = nullptr;
+    int *replay_nvert = nullptr, *replay_hit = nullptr;
+    unsigned long long* replay_bins = nullptr;
+    int replay_max_vert = 0;
     long long dbg_pid = -1;
     float* dbg_log = nullptr;
     int dbg_cap = 0;
@@ -278,7 +289,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.stream) cudaStreamSynchronize(D.stream);
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
-        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.hist_ids); cudaFree(D.hist_det); cudaFree(D.hist_n); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
         cudaFree(D.nz_counts); cudaFree(D.rx_idx); cudaFree(D.rx_val);
@@ -622,12 +633,14 @@ extern "C" int smcrt_set_detectors(smcrt_ctx* c, int n, const int32_t* kind, con
             default: return set_err("Invalid detector type. Valid types are [circle, annulus, camera]");
         }
         D.q[13] = (float)((double)D.pos[0] * (double)D.dir[0] + (double)D.pos[1] * (double)D.dir[1] + (double)D.pos[2] * (double)D.dir[2]);
+        D.pad_ = 0;  // trackHistory: set by smcrt_set_track_history (a new detector table clears it, like a new dects(:))
         D.offset = (int)off;
         hd[i] = HostDet{kind[i], nb, stored, count, off};
         off += count;
         if (off > (1ll << 30)) return set_err("smcrt_set_detectors: too many detector bins");
     }
     c->dets.swap(dets); c->hdets.swap(hd); c->det_total = off;
+    c->track.assign((size_t)n, 0); c->any_track = false;
     {
         const uint64_t h = fnv1a(1469598103934665603ull, c->dets.data(), c->dets.size() * sizeof(DevDet));
         if (h != c->det_hash) std::memset(c->tuned_mb, 0, sizeof c->tuned_mb);
@@ -824,6 +837,7 @@ static int upload_scene(smcrt_ctx* c) {
     return build_cull(c);
 }
 
+static const unsigned long long HIST_CAP = 1ull << 20;  // tracked hits kept per device between resets (beyond: counted only)
 static const int SMEM_BIN_CAP = 8192;  // 64 KB of CTA-private Q40.24 bins at most
 
 static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
@@ -872,6 +886,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     }
     P.jdiff_used = D.jdiff_used;
     P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
+    if (c->any_track) { P.hist_ids = D.hist_ids; P.hist_det = D.hist_det; P.hist_n = D.hist_n; P.hist_cap = HIST_CAP; }
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     static const char* wd_env = getenv("SMCRT_WATCHDOG_MS");  // (tests trip the watchdog with a tiny period)
     P.watchdog_ns = wd_env ? (unsigned long long)(atof(wd_env) * 1e6) : 20000000000ull;  // 20 s
@@ -913,7 +928,7 @@ static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceSta
     const Variant v = VARIANTS[var];
     const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
     // LEAN: nothing optional asked of this run (no per-packet records, diagnostics, batched sources, survival biasing)
-    const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival;
+    const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival && !P.out_vert && !P.id_list;
     trace_kernel_t k = pl ? (hd ? pick_kernel_pl1_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl1_hd0(v.sched, v.mb, need, simple, lean))
                           : (hd ? pick_kernel_pl0_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl0_hd0(v.sched, v.mb, need, simple, lean));
     return launch_kernel(k, P, D, smem_bytes[v.sched], dry, seg_inline);
@@ -948,6 +963,10 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     P.chance = (float)(chance > 0 ? chance : 0.1);            // CHANCE, src/constants.f90:30
     P.out_fate = out_fate; P.out_nscatt = out_nscatt; P.out_events = out_events; P.out_pos = out_pos; P.out_sweeps = out_sweeps; P.out_dbg = out_dbg;
     P.dbg_pid = c->dbg_pid; P.dbg_log = c->dbg_log; P.dbg_cap = c->dbg_cap;
+    if (c->replay_ids) {  // smcrt_history_replay: these packets only, vertex lists out, nothing noted, nothing tallied
+        P.id_list = c->replay_ids; P.id_list_n = nphotons; P.out_vert = c->replay_vert; P.out_nvert = c->replay_nvert; P.out_hit = c->replay_hit;
+        P.max_vert = c->replay_max_vert; P.hist_n = nullptr; P.det_bins = c->replay_bins; P.det_in_smem = 0;
+    }
     CU(cudaSetDevice(D.dev));
     if (tally_mode & SMCRT_TALLY_PATHLENGTH) {
         if (!D.jdiff[0] && !P.dda_legacy) {  // first path-length run on this grid
@@ -1308,6 +1327,7 @@ static int zero_device_tallies(smcrt_ctx* c, DeviceState& D) {
     if (c->dirty_modes & SMCRT_TALLY_EMISSION) CU(cudaMemsetAsync(D.emission, 0, nv * 4, D.stream));
     CU(cudaMemsetAsync(D.det_bins, 0, sizeof(unsigned long long) * (size_t)std::max<long long>(c->det_total, 1), D.stream));
     CU(cudaMemsetAsync(D.counters, 0, sizeof(unsigned long long) * C_COUNT, D.stream));
+    if (D.hist_n) CU(cudaMemsetAsync(D.hist_n, 0, 8, D.stream));
     CU(cudaStreamSynchronize(D.stream));
     return 0;
 }
@@ -1732,6 +1752,103 @@ extern "C" int smcrt_run_sources(smcrt_ctx* c, int64_t n_src, const double* pos,
     }
     c->src_kind = keep_kind; c->src_sub = keep_sub; c->src_alt = keep_alt;
     return err ? err : wrc;
+}
+// ---- trackHistory (src/historyStack.f90, src/detectors/detector_base.f90:157-162) --------------------------------------------
+extern "C" int smcrt_set_track_history(smcrt_ctx* c, int n, const int32_t* track) {
+    if (!c) return set_err("null ctx");
+    if (n != (int)c->dets.size() || (n > 0 && !track)) return set_err("smcrt_set_track_history: %d flags for %d detectors", n, (int)c->dets.size());
+    c->any_track = false;
+    for (int i = 0; i < n; ++i) {
+        c->track[(size_t)i] = track[i] ? 1 : 0;
+        c->dets[(size_t)i].pad_ = track[i] ? 1 : 0;
+        c->any_track = c->any_track || track[i];
+    }
+    c->scene_dirty = true;  // the detector records live in the scene blob
+    if (c->any_track)
+        for (DeviceState& D : c->devs) {
+            CU(cudaSetDevice(D.dev));
+            if (D.hist_n) continue;
+            CU(cudaMalloc(&D.hist_ids, HIST_CAP * 8));
+            CU(cudaMalloc(&D.hist_det, HIST_CAP * 4));
+            CU(cudaMalloc(&D.hist_n, 8));
+            CU(cudaMemset(D.hist_n, 0, 8));
+        }
+    return 0;
+}
+extern "C" int smcrt_history_hits(smcrt_ctx* c, int64_t max_hits, uint64_t* ids, int32_t* det, int64_t* total) {
+    if (!c || !total) return set_err("smcrt_history_hits: null argument");
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (c->pending && (rc = smcrt_wait(c))) return rc;
+    std::vector<std::pair<uint64_t, int32_t>> all;
+    int64_t seen = 0;
+    for (DeviceState& D : c->devs) {
+        if (!D.hist_n) continue;
+        CU(cudaSetDevice(D.dev));
+        unsigned long long n = 0;
+        CU(cudaMemcpy(&n, D.hist_n, 8, cudaMemcpyDeviceToHost));
+        seen += (int64_t)n;
+        const size_t k = (size_t)std::min<unsigned long long>(n, HIST_CAP);
+        std::vector<unsigned long long> hi(k);
+        std::vector<int> hd(k);
+        if (k) {
+            CU(cudaMemcpy(hi.data(), D.hist_ids, k * 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(hd.data(), D.hist_det, k * 4, cudaMemcpyDeviceToHost));
+        }
+        for (size_t i = 0; i < k; ++i) all.emplace_back((uint64_t)hi[i], (int32_t)hd[i] + 1);  // 1-based detector index
+    }
+    std::sort(all.begin(), all.end());  // by packet id: the order does not depend on the schedule
+    *total = seen;
+    for (int64_t i = 0; i < std::min<int64_t>(max_hits, (int64_t)all.size()); ++i) {
+        if (ids) ids[i] = all[(size_t)i].first;
+        if (det) det[i] = all[(size_t)i].second;
+    }
+    return 0;
+}
+extern "C" int smcrt_history_replay(smcrt_ctx* c, int64_t n, const uint64_t* ids, uint64_t seed, int survival_bias, int max_vertices,
+                                    float* vertices, int32_t* n_vertices, int32_t* hit_vertex) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (n < 1 || !ids || max_vertices < 2 || !vertices || !n_vertices) return set_err("smcrt_history_replay: invalid arguments");
+    if (c->pending) return set_err("smcrt_history_replay: a run is pending");
+    std::vector<unsigned long long> sorted(ids, ids + n);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    const int64_t m = (int64_t)sorted.size();
+    DeviceState& D = c->devs[0];
+    CU(cudaSetDevice(D.dev));
+    DevBuf bi, bv, bn, bh, bb;
+    if (bi.alloc((size_t)m * 8) || bv.alloc((size_t)m * max_vertices * 16) || bn.alloc((size_t)m * 4) || bh.alloc((size_t)m * 4) ||
+        bb.alloc((size_t)std::max<long long>(c->det_total, 1) * 8))
+        return PROBE_FAIL();
+    CU(cudaMemcpy(bi.p, sorted.data(), (size_t)m * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(bn.p, 0, (size_t)m * 4));
+    CU(cudaMemset(bh.p, 0xff, (size_t)m * 4));
+    c->replay_ids = bi.as<unsigned long long>(); c->replay_vert = bv.as<float4>(); c->replay_nvert = bn.as<int>(); c->replay_hit = bh.as<int>();
+    c->replay_bins = bb.as<unsigned long long>(); c->replay_max_vert = max_vertices;
+    const int keep_touched = c->touched_modes, keep_dirty = c->dirty_modes;
+    DevBuf bc;  // the run's counters are put back afterwards: a replay is not part of the job
+    if (bc.alloc(sizeof(unsigned long long) * C_COUNT)) return PROBE_FAIL();
+    CU(cudaMemcpyAsync(bc.p, D.counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToDevice, D.stream));
+    rc = run_on_device(c, D, m, seed, 0, 0 /* no voxel tallies */, survival_bias, -1, -1, nullptr, nullptr, nullptr, nullptr);
+    c->replay_ids = nullptr; c->replay_vert = nullptr; c->replay_nvert = nullptr; c->replay_hit = nullptr; c->replay_bins = nullptr;
+    c->touched_modes = keep_touched; c->dirty_modes = keep_dirty;
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(D.stream));
+    CU(cudaMemcpy(D.counters, bc.p, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToDevice));
+    // back in the caller's order
+    std::vector<float> hv((size_t)m * max_vertices * 4);
+    std::vector<int> hn((size_t)m), hh((size_t)m);
+    CU(cudaMemcpy(hv.data(), bv.p, hv.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hn.data(), bn.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hh.data(), bh.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+        const size_t k = (size_t)(std::lower_bound(sorted.begin(), sorted.end(), (unsigned long long)ids[i]) - sorted.begin());
+        std::memcpy(vertices + (size_t)i * max_vertices * 4, hv.data() + k * (size_t)max_vertices * 4, (size_t)max_vertices * 16);
+        n_vertices[i] = hn[k];
+        if (hit_vertex) hit_vertex[i] = hh[k];
+    }
+    return 0;
 }
 extern "C" int smcrt_inverse_mcrt(smcrt_ctx* c, int top_index, int find_mask, const double* bounds, int max_steps, int64_t nphotons,
                                   uint64_t seed, int tally_mode, const double* targets, double* table, int* best_step) {

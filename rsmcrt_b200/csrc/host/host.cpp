@@ -199,6 +199,7 @@ struct DetCfg {
     double p[SMCRT_DET_PARAMS] = {0};
     int nbins = 100;
     int layer = 1;
+    bool track = false;  // trackHistory
 };
 struct Config {
     // [source]  (parse_source.f90:58-255)
@@ -229,6 +230,7 @@ struct Config {
     // [simulation] (parse.f90:170-184)
     int64_t iseed = 123456789;
     bool tev = false, absorb = false, loadckpt = false;
+    std::string history_file = "photPos.obj";  // [[detectors]] historyFileName
     std::string ckptfile = "check.ckpt", ckpt_deck;  // ckpt_deck: the input deck's name as written into checkpoints
     int64_t ckptfreq = 1000000;
     // derived
@@ -488,8 +490,10 @@ void parse_detectors(const Table& root, Config& c) {
         DetCfg d;
         d.id = get_str(t, "ID", "none");
         d.layer = (int)get_int(t, "layer", 1);
-        if (get_bool(t, "trackHistory", false))
-            cfg_fail("Track history currently incompatable with OpenMP!");  // same guard as the parallel reference build
+        // (the parallel reference build refuses trackHistory, parse_detectors.f90:178-181; the engine records the hits and replays
+        // those packets, include/smcrt.h)
+        d.track = get_bool(t, "trackHistory", false);
+        if (const Value* hv = find(t, "historyFileName"); hv && hv->kind == Value::STRING) c.history_file = hv->s;
         double pos[3], dir[3] = {0, 0, -1};
         if (type == "circle") {
             if (!get_vec3(t, "position", pos)) cfg_fail("detector needs a position");
@@ -884,7 +888,63 @@ int smcrt_config_apply(const smcrt_config* cfg, smcrt_ctx* ctx) {
         nb.push_back(d.nbins);
         p.insert(p.end(), d.p, d.p + SMCRT_DET_PARAMS);
     }
-    return smcrt_set_detectors(ctx, (int)c.dets.size(), kind.data(), p.data(), nb.data());
+    rc = smcrt_set_detectors(ctx, (int)c.dets.size(), kind.data(), p.data(), nb.data());
+    if (rc) return rc;
+    std::vector<int32_t> track;
+    bool any = false;
+    for (auto& d : c.dets) { track.push_back(d.track ? 1 : 0); any = any || d.track; }
+    return any ? smcrt_set_track_history(ctx, (int)track.size(), track.data()) : 0;
+}
+int smcrt_config_detector_track(const smcrt_config* cfg, int i) {
+    return (cfg && i >= 0 && i < (int)cfg->c.dets.size() && cfg->c.dets[(size_t)i].track) ? 1 : 0;
+}
+const char* smcrt_config_history_filename(const smcrt_config* cfg) { return cfg ? cfg->c.history_file.c_str() : ""; }
+
+int smcrt_history_write(const char* path, int64_t n, int max_vertices, const float* vertices, const int32_t* counts) {
+    if (!path || n < 0 || max_vertices < 1 || (n > 0 && (!vertices || !counts))) return host_fail("smcrt_history_write: invalid arguments");
+    const std::string p = path;
+    const bool obj = p.find("obj") != std::string::npos, ply = p.find("ply") != std::string::npos, json = p.find("json") != std::string::npos;
+    if (!obj && !ply && !json) return host_fail("Unsupported filetype for track History!");  // init_historyStack, :55
+    FILE* f = std::fopen(path, "w");
+    if (!f) return host_fail(std::string("cannot open ") + path);
+    auto cnt = [&](int64_t k) { return std::min<int32_t>(std::max<int32_t>(counts[k], 0), max_vertices); };
+    auto v = [&](int64_t k, int j) { return vertices + ((size_t)k * max_vertices + (size_t)j) * 4; };
+    int64_t nv = 0, ne = 0;
+    for (int64_t k = 0; k < n; ++k) { nv += cnt(k); ne += std::max(cnt(k) - 1, 0); }
+    if (obj) {  // obj_writer :184-226 + finish: all "v" lines, then the "l" lines
+        for (int64_t k = 0; k < n; ++k)
+            for (int j = 0; j < cnt(k); ++j) std::fprintf(f, "v %15.8E %15.8E %15.8E \n", v(k, j)[0], v(k, j)[1], v(k, j)[2]);
+        int64_t base = 1;
+        for (int64_t k = 0; k < n; ++k) {
+            if (cnt(k) >= 2) {
+                std::fputs("l ", f);
+                for (int j = 0; j < cnt(k); ++j) std::fprintf(f, "%lld ", (long long)(base + j));
+                std::fputs("\n", f);
+            }
+            base += cnt(k);
+        }
+    } else if (ply) {  // ply_writer :228-273 + the header fix-up of finish
+        std::fprintf(f, "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\nelement edge %lld\n"
+                        "property int vertex1\nproperty int vertex2\nend_header\n", (long long)nv, (long long)ne);
+        for (int64_t k = 0; k < n; ++k)
+            for (int j = 0; j < cnt(k); ++j) std::fprintf(f, "%15.8E %15.8E %15.8E \n", v(k, j)[0], v(k, j)[1], v(k, j)[2]);
+        int64_t base = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            for (int j = 0; j + 1 < cnt(k); ++j) std::fprintf(f, "%lld %lld \n", (long long)(base + j), (long long)(base + j + 1));
+            base += cnt(k);
+        }
+    } else {  // json_writer :275-311 + finish
+        std::fputs("{\n", f);
+        for (int64_t k = 0; k < n; ++k) {
+            std::fprintf(f, "%s\"%lld_0\": [\n", k ? ",\n" : "", (long long)k);
+            for (int j = 0; j < cnt(k); ++j)
+                std::fprintf(f, "[%15.8E,%15.8E,%15.8E]%s\n", v(k, j)[0], v(k, j)[1], v(k, j)[2], j + 1 < cnt(k) ? "," : "");
+            std::fputs("]\n", f);
+        }
+        std::fputs("}\n", f);
+    }
+    std::fclose(f);
+    return 0;
 }
 
 // normalise_fluence, src/writer.f90:25-52.  The factor mixes real32 literals (2._sp) with real64 extents;
@@ -1124,6 +1184,26 @@ int smcrt_default_mcrt(const char* toml_path, const char* res_dir, const char* o
         return cleanup(rc);
     if (!c.dets.empty())
         if ((rc = smcrt_write_detectors(cfg, bins.data(), (od + "/detectors").c_str()))) return cleanup(rc);
+    bool any_track = false;
+    for (auto& d : c.dets) any_track = any_track || d.track;
+    if (any_track) {  // history%write for every packet that hit a tracking detector; "<name>_000.<ext>" like init_historyStack (:44-45)
+        int64_t total = 0;
+        if ((rc = smcrt_history_hits(ctx, 0, nullptr, nullptr, &total))) return cleanup(rc);
+        const int64_t keep = std::min<int64_t>(total, 100000);  // (a file of polylines: a diagnostic, not a tally)
+        std::vector<uint64_t> ids((size_t)std::max<int64_t>(keep, 1));
+        std::vector<int32_t> det((size_t)std::max<int64_t>(keep, 1));
+        if ((rc = smcrt_history_hits(ctx, keep, ids.data(), det.data(), &total))) return cleanup(rc);
+        const int maxv = 256;
+        std::vector<float> verts((size_t)std::max<int64_t>(keep, 1) * maxv * 4);
+        std::vector<int32_t> nvert((size_t)std::max<int64_t>(keep, 1), 0), hit((size_t)std::max<int64_t>(keep, 1), 0);
+        if (keep > 0 && (rc = smcrt_history_replay(ctx, keep, ids.data(), (uint64_t)c.iseed, survival_bias, maxv, verts.data(), nvert.data(), hit.data())))
+            return cleanup(rc);
+        for (int64_t k = 0; k < keep; ++k) nvert[(size_t)k] = hit[(size_t)k] > 0 ? hit[(size_t)k] : 0;  // the list as it stood at the hit
+        std::string name = c.history_file;
+        const size_t dot = name.find('.');
+        if (dot != std::string::npos) name = name.substr(0, dot) + "_000" + name.substr(dot);
+        if ((rc = smcrt_history_write((od + "/" + name).c_str(), keep, maxv, verts.data(), nvert.data()))) return cleanup(rc);
+    }
     return cleanup(0);
 }
 

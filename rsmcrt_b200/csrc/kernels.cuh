@@ -89,6 +89,21 @@ struct KParams {
     int* out_events;
     int* out_sweeps;
     float* out_pos;
+    // trackHistory (src/historyStack.f90): the first pass only notes WHICH packets hit a history-tracking detector
+    // (hist_ids / hist_det, cursor hist_n, capacity hist_cap); their vertex lists are produced by tracing those few packets again
+    // (streams depend on (seed, id) only): id_list = the packet ids of the replay (sorted; per-packet records are indexed by the
+    // position in it), out_vert / out_nvert / out_hit = max_vert vertices (x, y, z, scatter index) per packet, how many were
+    // written, and the vertex count at the first tracked hit (-1: none).
+    unsigned long long* hist_ids;
+    int* hist_det;
+    unsigned long long* hist_n;
+    unsigned long long hist_cap;
+    const unsigned long long* id_list;
+    long long id_list_n;
+    float4* out_vert;
+    int* out_nvert;
+    int* out_hit;
+    int max_vert;
     float* out_dbg;  // 12 floats per packet, written when a packet hits the step cap (engine diagnostics)
     long long dbg_pid;  // engine diagnostics: log the boundary events of this one packet into dbg_log (16 floats each)
     float* dbg_log;
@@ -1052,9 +1067,27 @@ enum : int { LOST_STEPS = 1, LOST_NO_SURFACE = 2, LOST_BOUNCES = 3, LOST_NO_LAYE
 #define SMCRT_MINBLOCKS 3    // resident CTAs per SM the register allocation is tuned for (80 registers; measured +5 % over 2)
 #endif
 // optional per-packet record of smcrt_trace_packets (out of line: cold)
+// index of a packet's per-packet records: its offset in the run, or its position in the (sorted) id list of a replay
+__device__ __forceinline__ long long rec_index(const KParams& P, unsigned long long pid) {
+    if (!P.id_list) return (long long)(pid - P.rec_id0);
+    long long lo = 0, hi = P.id_list_n - 1;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (P.id_list[mid] < pid) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// trackHistory: history%push(vec4(packet%pos, packet%step)) (kernelsMod.f90:1954,1959) for a replayed packet
+static __device__ __noinline__ void push_vertex(const KParams& P, unsigned long long pid, float x, float y, float z, float step) {
+    const long long k = rec_index(P, pid);
+    const int n = P.out_nvert[k];
+    if (n < P.max_vert) P.out_vert[k * (long long)P.max_vert + n] = make_float4(x, y, z, step);
+    P.out_nvert[k] = n + 1;  // (beyond max_vert: counted, not stored)
+}
 static __device__ __noinline__ void record_packet(const KParams& P, unsigned long long pid, int fate, int why, uint32_t ev, int steps,
                                            float x, float y, float z) {
-    const long long k = (long long)(pid - P.rec_id0);
+    const long long k = rec_index(P, pid);
     P.out_fate[k] = fate;
     if (P.out_events) P.out_events[k] = fate == 3 ? -why : (int)ev;
     if (P.out_sweeps) P.out_sweeps[k] = steps;

@@ -17,7 +17,7 @@ LIB_DIR = ROOT / "lib"
 OBJ_DIR = ROOT / "build"
 LIB_PATH = LIB_DIR / "libsmcrt_gpu.so"
 
-SOURCES = [CSRC / "engine.cu", CSRC / "trace_inst.cu", CSRC / "host" / "host.cpp", CSRC / "host" / "history.cpp"]
+SOURCES = [CSRC / "engine.cu", CSRC / "trace_inst.cu", CSRC / "host" / "host.cpp"]
 HEADERS = [CSRC / "kernels.cuh", CSRC / "step_body.inc", CSRC / "step_macros.inc", CSRC / "step_macros_undef.inc", CSRC / "device_scene.cuh",
            CSRC / "host_math.hpp", CSRC / "host" / "toml_lite.hpp", ROOT.parent / "include" / "smcrt.h", ROOT.parent / "include" / "smcrt_host.h"]
 
@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 # (object name, source, extra defines)
 UNITS = [("engine", CSRC / "engine.cu", [])] + \
         [(f"trace_pl{pl}_hd{hd}", CSRC / "trace_inst.cu", [f"-DSMCRT_INST_PL={pl}", f"-DSMCRT_INST_HD={hd}"]) for pl in (0, 1) for hd in (0, 1)] + \
-        [("host", CSRC / "host" / "host.cpp", []), ("history", CSRC / "host" / "history.cpp", [])]
+        [("host", CSRC / "host" / "host.cpp", [])]
 
 
 def _nvcc() -> str:

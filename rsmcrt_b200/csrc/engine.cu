@@ -125,6 +125,7 @@ struct DeviceState {
     bool jdiff_dirty = false;
     long long jdiff_packets = 0;
     // trackHistory: (packet id, detector) of every hit on a history-tracking detector since the last reset
+    FirstFlight* ff = nullptr;  // first flight of a pencil source (first_flight_kernel)
     unsigned long long* hist_ids = nullptr;
     int* hist_det = nullptr;
     unsigned long long* hist_n = nullptr;
@@ -289,7 +290,7 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.stream) cudaStreamSynchronize(D.stream);
         if (D.comm && nccl::CommDestroy) nccl::CommDestroy(D.comm);
         free_grids(D);
-        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.hist_ids); cudaFree(D.hist_det); cudaFree(D.hist_n); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
+        cudaFree(D.blob); cudaFree(D.primsD); cudaFree(D.progD); cudaFree(D.det_bins); cudaFree(D.counters); cudaFree(D.jdiff_used); cudaFree(D.ff); cudaFree(D.hist_ids); cudaFree(D.hist_det); cudaFree(D.hist_n); cudaFree(D.seg_buf); cudaFree(D.seg_count); cudaFree(D.seg_total);
         cudaFree(D.cull_start); cudaFree(D.cull_items); cudaFree(D.cull_far); cudaFree(D.cull_clear);
         cudaFree(D.nz_idx); cudaFree(D.nz_val); cudaFree(D.nz_cursor); cudaFreeHost(D.nz_idx_h); cudaFreeHost(D.nz_val_h);
         cudaFree(D.nz_counts); cudaFree(D.rx_idx); cudaFree(D.rx_val);
@@ -997,6 +998,13 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
         // an entry of a difference grid holds < 2^63 for 2^32 full-chord deposits (2^28 units each, weights <= 1/chance)
         if (D.jdiff_packets + nphotons > (1ll << 32)) { int rc = scan_pathlength(c, D); if (rc) return rc; }
         if (!P.dda_legacy) { D.jdiff_dirty = true; D.jdiff_packets += nphotons; }
+    }
+    static const bool no_ff = getenv("SMCRT_NO_FIRST_FLIGHT") != nullptr;  // A/B switch: every packet takes the ordinary launch sweeps
+    if (P.src_kind == SMCRT_SRC_PENCIL && !no_ff) {
+        if (!D.ff) CU(cudaMalloc(&D.ff, sizeof(FirstFlight)));
+        first_flight_kernel<<<1, 32, 0, D.stream>>>(P, D.ff);
+        CU(cudaGetLastError());
+        P.ff = D.ff;
     }
     CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     P.seg_off = (c->blob_bytes + (P.det_in_smem ? (int)c->det_total * 8 : 0) + 15) & ~15;  // the CTA's segment counter (path-length mode)

@@ -15,6 +15,11 @@
 namespace smcrt_dev {
 
 // ------------------------------------------------------------------------------------------------ params
+// What the launch sweeps of a fixed-ray (pencil) source lead to: first_flight_kernel computes it once per run
+struct FirstFlight {
+    int ok, layer, exact, pad_;
+    float kap, d0, s, eps;
+};
 struct KParams {
     // scene blob (global) and its carve-up; copied to shared memory by every CTA
     const unsigned char* blob;
@@ -68,6 +73,7 @@ struct KParams {
     float threshold, chance;
     float eps0, eps_rel;
     int max_steps;
+    const FirstFlight* ff;  // nullptr: every packet takes the ordinary launch sweeps
     unsigned long long watchdog_ns;  // trace_queued: how long a warp may find the queues empty / a publication pending (%globaltimer)
     int xchg_off;   // byte offset of the compaction scratch in dynamic shared memory (16-byte aligned)
     int dda_legacy;  // 1: path-length deposits one red.global.add.f32 per voxel crossed (SMCRT_DDA_LEGACY; cross-check of the run walker)
@@ -1123,6 +1129,11 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     constexpr uint32_t XTAIL = 0xffffffffu;
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
+    __shared__ FirstFlight ff;
+    if (threadIdx.x == 0) {
+        ff.ok = 0;
+        if (P.ff) ff = *P.ff;
+    }
     __syncthreads();
     const SceneView sc = make_view(smem, P);
     const int lane = threadIdx.x & 31;
@@ -1297,6 +1308,11 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     }
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
+    __shared__ FirstFlight ff;
+    if (threadIdx.x == 0) {
+        ff.ok = 0;
+        if (P.ff) ff = *P.ff;
+    }
     __syncthreads();
     const SceneView sc = make_view(smem, P);
     const int lane = threadIdx.x & 31;
@@ -1500,6 +1516,54 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
 
 #ifndef SMCRT_TRACE_TU  // everything below is compiled into engine.cu only (trace_inst.cu holds the trace-kernel instantiations)
 // ------------------------------------------------------------------------------------------------ culling-grid set-up
+// First flight of a fixed-ray source.  A pencil source launches EVERY packet from the same point in the same
+// direction (src/photon.f90:652-710), so the sweeps that start a history -- the launch sweep and, for a source that sits on a
+// surface (validation1.toml: on the slab's face), the boundary probe behind it -- evaluate the same points for every packet: 2 of
+// the slab scene's 5.9 sweeps per packet.  ONE thread does them once per run, with the trace kernels' own sweep code, and leaves
+// what the transitions need: the layer the flight happens in, the probe length already behind the packet (d0), the step to the next
+// surface (s) and whether it is exact.  The EMIT step (step_body.inc) then plays the first move directly -- the expressions of the
+// ST_MARCH / ST_CROSS transitions on these constants and the packet's own tau -- and the packet enters the loop where its history
+// starts to differ from the others'.  Anything unusual at the launch point (Fresnel surface, creep, forward nudge, camera, batched
+// sources) leaves ok = 0 and the packets take the ordinary path.  A kernel of its own: the same constants for every kernel variant.
+__global__ void first_flight_kernel(const __grid_constant__ KParams P, FirstFlight* out) {
+    if (blockIdx.x || threadIdx.x) return;
+    FirstFlight f;
+    f.ok = 0; f.layer = 0; f.exact = 0; f.pad_ = 0; f.kap = 0.f; f.d0 = 0.f; f.s = 0.f; f.eps = 0.f;
+    const SceneView sc = make_view(P.blob, P);
+    if (P.src_kind == 2 && !P.src_table && !P.has_camera) {
+        const Emitted em = emit_packet(P, 0.f, 0.f, 0.f, 0ull, 0u);
+        if (em.ok && in_grid(P, em.x, em.y, em.z)) {
+            const float e_ = fmaxf(P.eps0, P.eps_rel * fmaxf(fabsf(em.x), fmaxf(fabsf(em.y), fabsf(em.z))));
+            const Sweep S1 = sweep_all<false>(P, sc, em.x, em.y, em.z, em.dx, em.dy, em.dz, SMCRT_BIG);
+            f.eps = e_;
+            if (S1.L != 0) {
+                if (S1.amin < e_) {  // on a boundary: the probe of :77-84, taken as the crossing probe it is (step_body.inc, ST_CROSS)
+                    const float d0 = S1.amin + 2.0f * e_;
+                    const float qx = (float)((double)em.x + (double)d0 * (double)em.dx), qy = (float)((double)em.y + (double)d0 * (double)em.dy),
+                                qz = (float)((double)em.z + (double)d0 * (double)em.dz);
+                    const Sweep S2 = sweep_all<false>(P, sc, qx, qy, qz, em.dx, em.dy, em.dz, SMCRT_BIG);
+                    if (S2.L != S1.L && S2.L != 0 && S2.amin >= e_ && sc.tops[S1.L - 1].n == sc.tops[S2.L - 1].n) {
+                        f.layer = S2.L;
+                        f.kap = sc.tops[S2.L - 1].kappa;
+                        f.d0 = d0;
+                        f.s = S2.bmin < SMCRT_BIG ? fmaxf(S2.amin, S2.bmin - (0.25f * e_ + 2.4e-7f * S2.bmin)) : S2.amin;
+                        f.exact = S2.bexact ? 1 : 0;
+                        f.ok = 1;
+                    }
+                } else {            // inside a layer: the first sphere-trace step (:155-176)
+                    f.layer = S1.L;
+                    f.kap = sc.tops[S1.L - 1].kappa;
+                    f.d0 = 0.f;
+                    f.s = S1.bmin < SMCRT_BIG ? fmaxf(S1.amin, S1.bmin - (0.25f * e_ + 2.4e-7f * S1.bmin)) : S1.amin;
+                    f.exact = S1.bexact ? 1 : 0;
+                    f.ok = 1;
+                }
+            }
+        }
+    }
+    *out = f;
+}
+
 // One thread per (cell, top-level SDF): FP64 distance at the cell centre.  The host turns the matrix into candidate lists.
 __global__ void cull_eval_kernel(const __grid_constant__ KParams P, long long n_pairs, double lox, double loy, double loz, double dx, double dy,
                                  double dz, int nx, int ny, float* out) {

@@ -40,7 +40,21 @@ WORKLOADS = {
     "sphere.toml": "BASELINE configs[0]: 40 spheres n=1.37 in a box, uniform source, 200^3 grid, default build (absorb tallies)",
     "skin_b200.toml": "BASELINE configs[2]: five refractive tissue layers, uniform source, 200^3 grid",
     "lens.toml": "BASELINE configs[3]: refractive lens (model of two spheres), uniform source, 200^3 grid",
+    "vessels.toml": "BASELINE configs[4]: vessel tree (240 capsules, seeded synthetic data in the reference's file formats) in a dermis box, 200^3 grid",
 }
+
+
+def deck_res_dir(scene_name: str):
+    """vessels.toml reads edges / nodes / radii.dat, which the reference does not ship: a seeded synthetic tree is
+    written to a scratch directory in the reference's file formats (tools/make_vessels.py), the same on every rank."""
+    if scene_name != "vessels.toml":
+        return None
+    import tempfile
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_vessels
+    d = Path(tempfile.mkdtemp(prefix="smcrt_vessels_"))
+    make_vessels.make(d, 240, 7)
+    return d
 # What an ncu --set full capture of this command says about the dominant kernel (DRAM bytes of one launch, issue-slot utilisation,
 # lanes per instruction), keyed on (scene, packets per step, kernel variant): profiles/bench_ncu.json, written from the capture by
 # tools/ncu_bench_json.py.  A run whose kernel variant has no capture reports null, not a stale constant.
@@ -154,7 +168,7 @@ def cpu_leg(deck_path, seconds_target: float, threads: int = 0):
     threads = threads or host_threads()
     from oracle import binding as O
     O.build()
-    osc = O.OracleScene.from_toml(deck_path)
+    osc = O.OracleScene.from_toml(deck_path, deck_res_dir(Path(deck_path).name))
     cfg = osc.deck
     nv = int(np.prod(cfg.grid[0]))
     # calibrate on a small sample, then size the timed sample for ~seconds_target of CPU work
@@ -174,7 +188,7 @@ def run_reference(args, rank: int, world: int):
     threads = host_threads()
     from oracle import binding as O
     O.build()
-    osc = O.OracleScene.from_toml(ROOT / "res" / args.scene)
+    osc = O.OracleScene.from_toml(ROOT / "res" / args.scene, deck_res_dir(args.scene))
     cfg = osc.deck
     r = osc.run(20000, cfg.iseed, rng_mode=1, nthreads=threads, grids=False)
     rate = 20000 / max(r["seconds"], 1e-6)
@@ -256,7 +270,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    cfg = R.Config.load(ROOT / "res" / args.scene)
+    cfg = R.Config.load(ROOT / "res" / args.scene, res_dir=deck_res_dir(args.scene))
     scene = cfg.scene
     kind, dp, nb, _ids = cfg.detectors
     eng = R.Engine(1, device_ids=[local_rank])

@@ -1029,7 +1029,8 @@ bool tauint2(const Scene& s, Tally& T, ThreadCounters& C, Packet& pk, Rng& rng, 
     V3 pos = pk.pos, oldpos = pos, startPos = pos;
     V3 dir{pk.nxp, pk.nyp, pk.nzp};
     const double eps = 1e-8;                      // :56
-    const double tau = -std::log(rng.draw_tau());  // :58
+    // (> 0 strictly, like the engine: the Philox uniform of the tau draw can round to exactly 1; ran2() of the reference cannot)
+    const double tau = std::max(-std::log(rng.draw_tau()), 1e-30);  // :58
     double taurun = 0.0, d_sdf, t_sdf;
     auto kappa = [&](int layer) { return s.opt[layer - 1].kappa; };
     auto eval_all = [&](V3 p, double* out) {

@@ -742,6 +742,18 @@ static int build_cull(smcrt_ctx* c) {
         if (cls[a] != cls[b]) return cls_count[cls[a]] != cls_count[cls[b]] ? cls_count[cls[a]] < cls_count[cls[b]] : cls[a] < cls[b];
         return a < b;
     };
+    // Transparent scenes (the space between the bodies neither scatters nor absorbs: sphere.toml) are crossed in steps of `far`, the
+    // distance to the nearest UNLISTED surface -- one sweep iteration each.  Listing every SDF that comes within `reach` of the
+    // cell makes far >= reach: fewer, longer sweeps.  Measured on sphere.toml (SMCRT_CULL_REACH = 0 / 0.1 / 0.2 / 0.3 / 0.45 of the
+    // half extent): 15.2 / 14.8 / 13.6 / 12.4 / 11.0 sweeps per packet but 7.31 / 7.27 / 6.81 / 6.43 / 5.64e8 packets/s -- the
+    // longer lists cost more than the saved sweeps (the floor is ~8 sweeps: two per surface crossing).  Off by default.
+    double reach = 0.0;
+    {
+        double kap_max = 0.0;
+        for (const DevTop& T : c->tops) kap_max = std::max(kap_max, (double)T.kappa);
+        static const char* reach_env = getenv("SMCRT_CULL_REACH");  // fraction of the largest half extent (tuning / A-B switch)
+        if (kap_max * ext < 1.0) reach = (reach_env ? atof(reach_env) : 0.0) * ext;
+    }
     for (long long cell = 0; cell < ncell; ++cell) {
         const float* d = dc.data() + cell * nt;
         double U = 1e300, M = -1e300;
@@ -751,7 +763,7 @@ static int build_cull(smcrt_ctx* c) {
         }
         double f = 3.0e38;
         for (int j = 0; j < nt; ++j) {
-            const bool A = std::fabs((double)d[j]) - h <= U;
+            const bool A = std::fabs((double)d[j]) - h <= std::max(U, reach);
             const bool B = (d[j] - h < 0) && (d[j] + h >= M);
             if (A || B) items.push_back(j);
             else f = std::min(f, std::fabs((double)d[j]) - h);

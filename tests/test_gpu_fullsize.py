@@ -93,3 +93,74 @@ def test_sphere_scene_1e6_energy_bookkeeping(engine, smcrt):
     assert out["emission"].astype(np.float64).sum() == N
     mean_path = out["jmean"].astype(np.float64).sum() / N
     assert 2.0 <= mean_path < 2.2
+
+
+def _absorbed_fraction_oracle(oracle, deck, n, res_dir=None):
+    o = oracle.OracleScene.from_toml(RES / deck, res_dir).run(n, 4711, grids=True)
+    return float(o["absorb"].astype(np.float64).sum()) / n, o
+
+
+def test_skin_1e9_properties(engine, oracle, smcrt):
+    """BASELINE configs[2] at full size: the five-layer skin stack (refractive-index mismatch at every interface), 1e9 packets on
+    one GPU.  No packet is lost to an engine guard, unit absorb deposits stay exact integers, nothing is absorbed outside the
+    tissue, the absorbed fraction and the scatter count per packet agree with the oracle's (1e5 packets) within its 3 sigma."""
+    cfg = smcrt.Config.load(RES / "skin_b200.toml")
+    engine.apply(cfg)
+    N = 1_000_000_000
+    engine.run(N, cfg.iseed)
+    out = engine.fetch(absorb=True)
+    c = out["counters"]
+    assert c["launched"] == N and c["lost"] <= 1e-7 * N
+    a64 = out["absorb"].astype(np.float64)
+    assert out["absorb"].max() < 2 ** 24 and (out["absorb"] == np.round(out["absorb"])).all()
+    n_o = 100_000
+    fo, o = _absorbed_fraction_oracle(oracle, "skin_b200.toml", n_o)
+    fg = a64.sum() / N
+    assert abs(fg - fo) < 3 * np.sqrt(fo * (1 - fo) / n_o) + 1e-4, (fg, fo)
+    so = o["counters"]["nscatt"] / n_o
+    assert abs(c["nscatt"] / N - so) < 0.02 * so
+    # depth profile of the absorbed energy against the oracle's, 20 slabs
+    zg, zo = a64.sum(axis=(0, 1)).reshape(20, 10).sum(1) / N, o["absorb"].astype(np.float64).sum(axis=(0, 1)).reshape(20, 10).sum(1) / n_o
+    assert np.all(np.abs(zg - zo) < 4 * np.sqrt(np.maximum(zo, 1e-6) / n_o) + 1e-5)
+
+
+def test_lens_1e9_properties(engine, oracle, smcrt):
+    """BASELINE configs[3] scene (refractive lens: intersection of two spheres, n = 1.5) at 1e9 packets, path-length fluence:
+    nothing is absorbed or scattered, every packet leaves, the mean path per packet is the oracle's, no packet is lost."""
+    cfg = smcrt.Config.load(RES / "lens.toml")
+    engine.apply(cfg)
+    N = 1_000_000_000
+    engine.run(N, cfg.iseed, tally_mode=A.TALLY_ABSORB | A.TALLY_PATHLENGTH)
+    out = engine.fetch(jmean=True, absorb=True)
+    c = out["counters"]
+    assert c["launched"] == N and c["lost"] <= 1e-6 * N and c["nscatt"] == 0 and out["absorb"].sum() == 0
+    path_g = out["jmean"].astype(np.float64).sum() / N
+    o = oracle.OracleScene.from_toml(RES / "lens.toml").run(200_000, 11, tally_mode=A.TALLY_PATHLENGTH)
+    path_o = o["jmean"].astype(np.float64).sum() / 200_000
+    assert abs(path_g - path_o) < 2e-3 * path_o, (path_g, path_o)
+    assert abs(c["bounces"] / N - o["counters"]["bounces"] / 200_000) < 0.02 * o["counters"]["bounces"] / 200_000 + 1e-3
+
+
+def test_vessels_1e9_properties(engine, oracle, smcrt, tmp_path):
+    """BASELINE configs[4] scene (vessel tree: 240 capsules in a dermis box; the reference ships no data, tools/make_vessels.py
+    writes a seeded synthetic tree in its file formats) at 1e9 packets on one GPU (the 1e10 job is ten of these: the
+    committed multi-GPU bench lines).  Conservation and oracle agreement of the absorbed fraction, in and out of the vessels."""
+    import sys
+    sys.path.insert(0, str(RES.parent / "tools"))
+    import make_vessels
+    make_vessels.make(tmp_path, 240, 7)
+    cfg = smcrt.Config.load(RES / "vessels.toml", res_dir=tmp_path)
+    engine.apply(cfg)
+    N = 1_000_000_000
+    engine.run(N, cfg.iseed)
+    out = engine.fetch(absorb=True)
+    c = out["counters"]
+    assert c["launched"] == N and c["lost"] == 0
+    a64 = out["absorb"].astype(np.float64)
+    assert (out["absorb"] == np.round(out["absorb"])).all() and out["absorb"].max() < 2 ** 24
+    n_o = 100_000
+    fo, o = _absorbed_fraction_oracle(oracle, "vessels.toml", n_o, tmp_path)
+    fg = a64.sum() / N
+    assert abs(fg - fo) < 3 * np.sqrt(fo * (1 - fo) / n_o) + 1e-4, (fg, fo)
+    so = o["counters"]["nscatt"] / n_o
+    assert abs(c["nscatt"] / N - so) < 0.02 * so

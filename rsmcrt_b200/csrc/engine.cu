@@ -99,6 +99,7 @@ static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
     return h;
 }
 
+constexpr int SEG_MAX_SHARES = 148 * 8;  // CTAs of a trace launch (<= SMs x resident CTAs): shares of the segment buffer
 constexpr int NVAR_MAX = 8;  // kernel variants a trial can cover (events / time stamps are sized for it)
 static bool create_events(cudaEvent_t* ev, int n) {
     for (int i = 0; i < n; ++i) if (cudaEventCreate(&ev[i]) != cudaSuccess) return false;
@@ -898,7 +899,7 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
         P.jfix[a] = (float)(268435456.0 /* 2^28 */ * nn[a] / (2.0 * c->gmax[a]));
     }
     P.jdiff_used = D.jdiff_used;
-    P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
+    P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total; P.seg_work = D.seg_count ? D.seg_count + SEG_MAX_SHARES : nullptr;
     if (c->any_track) { P.hist_ids = D.hist_ids; P.hist_det = D.hist_det; P.hist_n = D.hist_n; P.hist_cap = HIST_CAP; }
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     static const char* wd_env = getenv("SMCRT_WATCHDOG_MS");  // (tests trip the watchdog with a tiny period)
@@ -907,7 +908,6 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     return 0;
 }
 
-constexpr int SEG_MAX_SHARES = 148 * 8;  // CTAs of a trace launch (<= SMs x resident CTAs)
 static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D, int smem_bytes, bool dry, bool seg_inline) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
@@ -928,8 +928,9 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D,
     kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, D.stream>>>(P);
     CU(cudaGetLastError());
     if (pathlen && !seg_inline) {  // walk what the launch recorded, then clear the shares for the next launch
-        deposit_segments_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(P, (int)blocks);
-        clear_segment_counts_kernel<<<1, 256, 0, D.stream>>>(D.seg_count, (int)blocks);
+        CU(cudaFuncSetAttribute(deposit_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HotTable)));
+        deposit_segments_kernel<<<D.sm_count * 3, 256, sizeof(HotTable), D.stream>>>(P, (int)blocks);  // 3 CTAs of 64 KB per SM
+        clear_segment_counts_kernel<<<1, 256, 0, D.stream>>>(D.seg_count, (int)blocks, D.seg_count + SEG_MAX_SHARES);
         CU(cudaGetLastError());
     }
     return 0;
@@ -1001,11 +1002,11 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
             if (const char* e = getenv("SMCRT_SEG_MB")) bytes = std::max<size_t>((size_t)atoll(e), 1) << 20;
             CU(cudaMalloc(&D.seg_buf, bytes));
             D.seg_records = bytes / 32;
-            CU(cudaMalloc(&D.seg_count, sizeof(unsigned int) * SEG_MAX_SHARES));
-            CU(cudaMemsetAsync(D.seg_count, 0, sizeof(unsigned int) * SEG_MAX_SHARES, D.stream));
+            CU(cudaMalloc(&D.seg_count, sizeof(unsigned int) * (SEG_MAX_SHARES + 1)));  // + the deposit kernel's work counter
+            CU(cudaMemsetAsync(D.seg_count, 0, sizeof(unsigned int) * (SEG_MAX_SHARES + 1), D.stream));
             CU(cudaMalloc(&D.seg_total, 8));
             CU(cudaMemsetAsync(D.seg_total, 0, 8, D.stream));
-            P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total;
+            P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total; P.seg_work = D.seg_count + SEG_MAX_SHARES;
         }
         // an entry of a difference grid holds < 2^63 for 2^32 full-chord deposits (2^28 units each, weights <= 1/chance)
         if (D.jdiff_packets + nphotons > (1ll << 32)) { int rc = scan_pathlength(c, D); if (rc) return rc; }

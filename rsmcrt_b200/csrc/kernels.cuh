@@ -88,6 +88,7 @@ struct KParams {
     unsigned int* seg_count;
     unsigned int seg_cap;
     int seg_off;
+    unsigned int* seg_work;         // work counter of deposit_segments_kernel (cleared with the shares)
     unsigned long long* seg_total;  // all segments produced (recorded or, when a CTA's share was full, walked inline)
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
@@ -553,8 +554,57 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
 // full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
 __device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+// The same, summed first over the lanes of the warp that update the SAME entry right now (integer adds: exact in any order).  The
+// deposit kernel walks 32 segments of one scene side by side, and a source sends them through the same voxels: every first
+// segment of a pencil beam starts in one voxel, 1e8 updates of two addresses that the L2 atomic unit would take one by one.
+__device__ __forceinline__ void red_i64_warp(long long* p, long long v) {
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, (unsigned long long)p);
+    if (peers == (1u << (threadIdx.x & 31))) { red_i64(p, v); return; }
+    // sum over the peers with the warp's integer reduction unit (redux.sync, 32-bit): the value, made non-negative by a bias of
+    // 2^62, goes in three 21-bit limbs whose sums over <= 32 lanes cannot overflow; the bias comes off again afterwards
+    const unsigned long long b = (unsigned long long)v + (1ull << 62);
+    const unsigned int s0 = __reduce_add_sync(peers, (unsigned int)(b & 0x1fffffull));
+    const unsigned int s1 = __reduce_add_sync(peers, (unsigned int)((b >> 21) & 0x1fffffull));
+    const unsigned int s2 = __reduce_add_sync(peers, (unsigned int)(b >> 42));
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        const unsigned long long sum = (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42) -
+                                       ((unsigned long long)__popc(peers) << 62);
+        red_i64(p, (long long)sum);
+    }
+}
 // -> (voxels crossed, atomics issued) for the counters
-static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+// CTA-private accumulator of the deposit kernel for HOT difference-grid entries ("per-CTA shared-memory tile for the
+// beam column", generalised).  A pencil beam sends 1e9 range updates per 1e8 packets into the ~1300 entries of four voxel columns,
+// and L2 takes same-entry atomics one by one (2.5e10/s measured: the ceiling of r01_red_peaks.json for one column).  An open-
+// addressing table in shared memory -- key = the entry's address, first come first kept, at most HOT_PROBES probes -- takes the
+// updates of the entries it holds (two native 32-bit shared adds with carry) and is flushed once per CTA; an entry that found no
+// slot goes to L2 as before, so a diffuse scene (millions of distinct entries) loses only the probes.
+constexpr int HOT_SLOTS = 4096, HOT_PROBES = 3;
+struct HotTable {
+    unsigned long long key[HOT_SLOTS];
+    unsigned int lo[HOT_SLOTS], hi[HOT_SLOTS];
+};
+__device__ __forceinline__ void red_i64_hot(HotTable* T, long long* p, long long v) {
+    const unsigned long long k = (unsigned long long)p;
+    unsigned int h = (unsigned int)((k >> 3) * 0x9E3779B97F4A7C15ull >> 52);
+#pragma unroll
+    for (int probe = 0; probe < HOT_PROBES; ++probe) {
+        unsigned long long cur = T->key[h];
+        if (cur == 0ull) cur = atomicCAS(&T->key[h], 0ull, k), cur = cur ? cur : k;
+        if (cur == k) {
+            const unsigned int vl = (unsigned int)(unsigned long long)v, vh = (unsigned int)((unsigned long long)v >> 32);
+            const unsigned int old = atomicAdd(&T->lo[h], vl);
+            atomicAdd(&T->hi[h], vh + ((old + vl < old) ? 1u : 0u));
+            return;
+        }
+        h = (h + 1u) & (HOT_SLOTS - 1);
+    }
+    red_i64(p, v);
+}
+// `hot`: the deposit kernel's table (nullptr: every range update goes straight to L2)
+static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
+                                                  HotTable* hot = nullptr) {
     if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
     const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
@@ -643,10 +693,17 @@ static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, fl
                 const long long q_lo = fwd ? q_in : q_out, q_hi = fwd ? q_out : q_in;
                 long long* lo = D + (fwd ? off : off - (long long)m * stra);
                 const int hi_idx = fwd ? ia + m : ia;
-                red_i64(lo, q_lo);
-                red_i64(lo + stra, qc - q_lo);
-                red_i64(lo + (long long)m * stra, q_hi - qc);
-                if (hi_idx + 1 < na) red_i64(lo + (long long)(m + 1) * stra, -q_hi);
+                if (hot) {
+                    red_i64_hot(hot, lo, q_lo);
+                    red_i64_hot(hot, lo + stra, qc - q_lo);
+                    red_i64_hot(hot, lo + (long long)m * stra, q_hi - qc);
+                    if (hi_idx + 1 < na) red_i64_hot(hot, lo + (long long)(m + 1) * stra, -q_hi);
+                } else {
+                    red_i64(lo, q_lo);
+                    red_i64(lo + stra, qc - q_lo);
+                    red_i64(lo + (long long)m * stra, q_hi - qc);
+                    if (hi_idx + 1 < na) red_i64(lo + (long long)(m + 1) * stra, -q_hi);
+                }
                 nred += 4u;
                 used = true;
             }
@@ -737,10 +794,28 @@ __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* s
 __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     unsigned long long c_vox = 0ull, c_red = 0ull;
-    for (int sh = blockIdx.x; sh < n_shares; sh += gridDim.x) {
-        const unsigned int n = min(P.seg_count[sh], P.seg_cap);
+    extern __shared__ __align__(16) unsigned char dsm[];
+    HotTable* hot = reinterpret_cast<HotTable*>(dsm);
+    for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x) { hot->key[i] = 0ull; hot->lo[i] = 0u; hot->hi[i] = 0u; }
+    __syncthreads();
+    // work items = (share, eighth of the share), handed out by a global counter: the CTAs of this launch are persistent (as many as
+    // fit beside their 64-KB tables) and stay busy until the last record
+    __shared__ unsigned int item_s;
+    constexpr unsigned int PARTS = 8u;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) item_s = atomicAdd(P.seg_work, 1u);
+        __syncthreads();
+        const unsigned int item = item_s;
+        if (item >= (unsigned int)n_shares * PARTS) break;
+        const int sh = (int)(item / PARTS);
+        const unsigned int part = item % PARTS;
+        const unsigned int n_all = min(P.seg_count[sh], P.seg_cap);
+        const unsigned int r0 = (unsigned int)(((unsigned long long)n_all * part / PARTS + 31ull) & ~31ull),
+                           r1 = part + 1u == PARTS ? n_all : (unsigned int)(((unsigned long long)n_all * (part + 1u) / PARTS + 31ull) & ~31ull);
+        const unsigned int n = min(r1, n_all);
         const float4* recs = P.seg_buf + 2ull * (unsigned long long)sh * P.seg_cap;
-        for (unsigned int base = warp * 32u; base < n; base += nwarp * 32u) {
+        for (unsigned int base = r0 + warp * 32u; base < n; base += nwarp * 32u) {
             const unsigned int i = base + lane;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f);
             float work = 0.f;
@@ -755,7 +830,7 @@ __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_cons
             }
             const bool share = work >= 96.0f;
             if (work > 0.f && !share) {
-                const uint2 w = walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
+                const uint2 w = walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, hot);
                 c_vox += w.x; c_red += w.y;
             }
             unsigned pend = __ballot_sync(0xffffffffu, share);
@@ -771,13 +846,20 @@ __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_cons
             }
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x)  // flush the table: one L2 atomic per entry held
+        if (hot->key[i]) {
+            const long long v = (long long)(((unsigned long long)hot->hi[i] << 32) | (unsigned long long)hot->lo[i]);
+            if (v) red_i64(reinterpret_cast<long long*>(hot->key[i]), v);
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { c_vox += __shfl_xor_sync(0xffffffffu, c_vox, o); c_red += __shfl_xor_sync(0xffffffffu, c_red, o); }
     if (lane == 0 && c_vox) { atomicAdd(&P.counters[C_VOXELS], c_vox); atomicAdd(&P.counters[C_REDS], c_red); }
 }
 // (the shares are cleared for the next launch by a second tiny kernel: a CTA of the deposit kernel may still be reading a count)
-__global__ void clear_segment_counts_kernel(unsigned int* cnt, int n) {
+__global__ void clear_segment_counts_kernel(unsigned int* cnt, int n, unsigned int* work) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cnt[i] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work = 0u;
 }
 
 #endif  // SMCRT_TRACE_TU

@@ -492,7 +492,9 @@ def main():
                              f"frac_executed = the same op table on the ENGINE's own counters ({w_flop_exec:.0f} flops/packet: its directional "
                              "step bounds need ~6 sweeps): what the FMA pipes actually execute.  issue_slot_utilisation / lanes_per_instruction: "
                              "ncu on this command and kernel variant (profiles/bench_ncu.json; null when that variant has no capture).  "
-                             f"peak = {world} GPU(s) x 148 SM x 128 lanes x 2 x sm_max_mhz (nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)",
+                             f"peak = {world} GPU(s) x 148 SM x 128 lanes x 2 x sm_max_mhz (nominal FP32 FMA; MEASURED_PEAKS.json has no FP32 entry)"
+                             + ("" if scene.n_top < 8 else ".  NB this scene has a culling grid: a sweep evaluates only its cell's candidate list, while "
+                                "the flop figures count every top-level SDF per sweep (what the reference evaluates) -- an upper bound on the executed work"),
                      "flops_per_packet": w_flop, "flops_per_packet_executed": w_flop_exec,
                      "engine_sweeps_per_packet": c["sweeps"] / n_run, "engine_nscatt_per_packet": c["nscatt"] / n_run,
                      "engine_lost_fraction": c["lost"] / n_run},

@@ -554,26 +554,6 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
 // full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
 __device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-// The same, summed first over the lanes of the warp that update the SAME entry right now (integer adds: exact in any order).  The
-// deposit kernel walks 32 segments of one scene side by side, and a source sends them through the same voxels: every first
-// segment of a pencil beam starts in one voxel, 1e8 updates of two addresses that the L2 atomic unit would take one by one.
-__device__ __forceinline__ void red_i64_warp(long long* p, long long v) {
-    const unsigned act = __activemask();
-    const unsigned peers = __match_any_sync(act, (unsigned long long)p);
-    if (peers == (1u << (threadIdx.x & 31))) { red_i64(p, v); return; }
-    // sum over the peers with the warp's integer reduction unit (redux.sync, 32-bit): the value, made non-negative by a bias of
-    // 2^62, goes in three 21-bit limbs whose sums over <= 32 lanes cannot overflow; the bias comes off again afterwards
-    const unsigned long long b = (unsigned long long)v + (1ull << 62);
-    const unsigned int s0 = __reduce_add_sync(peers, (unsigned int)(b & 0x1fffffull));
-    const unsigned int s1 = __reduce_add_sync(peers, (unsigned int)((b >> 21) & 0x1fffffull));
-    const unsigned int s2 = __reduce_add_sync(peers, (unsigned int)(b >> 42));
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-        const unsigned long long sum = (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42) -
-                                       ((unsigned long long)__popc(peers) << 62);
-        red_i64(p, (long long)sum);
-    }
-}
-// -> (voxels crossed, atomics issued) for the counters
 // CTA-private accumulator of the deposit kernel for HOT difference-grid entries ("per-CTA shared-memory tile for the
 // beam column", generalised).  A pencil beam sends 1e9 range updates per 1e8 packets into the ~1300 entries of four voxel columns,
 // and L2 takes same-entry atomics one by one (2.5e10/s measured: the ceiling of r01_red_peaks.json for one column).  An open-

@@ -130,6 +130,10 @@ struct DeviceState {
     unsigned long long* hist_ids = nullptr;
     int* hist_det = nullptr;
     unsigned long long* hist_n = nullptr;
+    // A path-length run of several chunks alternates between two lanes: a stream, a half of the segment buffer and a packet counter
+    // each, so that a chunk's trace kernel starts while the last histories of the chunk before are still running (see run_on_device)
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_lane[2] = {nullptr, nullptr};
     // segment buffer of the path-length mode: seg_records records of 32 bytes, split evenly between the CTAs of a trace launch
     float4* seg_buf = nullptr;
     unsigned int* seg_count = nullptr;   // [SEG_MAX_SHARES]
@@ -266,8 +270,8 @@ extern "C" int smcrt_create(smcrt_ctx** out, int n_gpus, const int* device_ids) 
         if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&D.ev0) != cudaSuccess || cudaEventCreate(&D.ev1) != cudaSuccess ||
             !create_events(D.tune_ev, NVAR_MAX + 1) ||
-            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess ||
-            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 16)) != cudaSuccess) {
+            cudaMalloc(&D.counters, sizeof(unsigned long long) * (C_COUNT + 1 + 16 + 2)) != cudaSuccess ||  // counters, next, 16 time stamps, the lanes' next
+            cudaMemset(D.counters, 0, sizeof(unsigned long long) * (C_COUNT + 1 + 16 + 2)) != cudaSuccess) {
             delete c;
             return set_err("smcrt_create: resource allocation failed on device %d: %s", D.dev, cudaGetErrorString(cudaGetLastError()));
         }
@@ -298,6 +302,8 @@ extern "C" void smcrt_destroy(smcrt_ctx* c) {
         if (D.ev0) cudaEventDestroy(D.ev0);
         if (D.ev1) cudaEventDestroy(D.ev1);
         for (cudaEvent_t e : D.tune_ev) if (e) cudaEventDestroy(e);
+        for (cudaStream_t s : D.lane_stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        for (cudaEvent_t ev : {D.ev_fork, D.ev_lane[0], D.ev_lane[1]}) if (ev) cudaEventDestroy(ev);
         if (D.stream) cudaStreamDestroy(D.stream);
     }
     delete c;
@@ -900,6 +906,10 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     }
     P.jdiff_used = D.jdiff_used;
     P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total; P.seg_work = D.seg_count ? D.seg_count + SEG_MAX_SHARES : nullptr;
+    static const float piece = getenv("SMCRT_SEG_PIECE") ? std::max((float)atof(getenv("SMCRT_SEG_PIECE")), 1.0f) : 64.0f;  // (experiments)
+    P.seg_piece = piece;
+    static const int defer = getenv("SMCRT_SEG_DEFER") ? atoi(getenv("SMCRT_SEG_DEFER")) : 1;
+    P.seg_defer = defer;
     if (c->any_track) { P.hist_ids = D.hist_ids; P.hist_det = D.hist_det; P.hist_n = D.hist_n; P.hist_cap = HIST_CAP; }
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     static const char* wd_env = getenv("SMCRT_WATCHDOG_MS");  // (tests trip the watchdog with a tiny period)
@@ -908,7 +918,9 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     return 0;
 }
 
-static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D, int smem_bytes, bool dry, bool seg_inline) {
+// lane < 0: on the device's main stream, with the whole segment buffer; lane 0 / 1: on that lane's stream, with its half of the
+// buffer and its own packet counter
+static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D, int smem_bytes, bool dry, bool seg_inline, int lane) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMCRT_BLOCK, smem_bytes));
@@ -923,14 +935,27 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D,
     if (pathlen) {
         if (blocks > SEG_MAX_SHARES) return set_err("trace launch of %lld CTAs exceeds the segment buffer's %d shares", blocks, SEG_MAX_SHARES);
         // seg_cap = 0: every segment is walked by the lane that made it (the fallback of a full share, for all of them)
-        P.seg_cap = seg_inline ? 0u : (unsigned int)std::min<size_t>(D.seg_records / (size_t)blocks, 0x7fffffffu);
+        P.seg_cap = seg_inline ? 0u : (unsigned int)std::min<size_t>(D.seg_records / (lane < 0 ? 1 : 2) / (size_t)blocks, 0x7fffffffu);
     }
-    kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, D.stream>>>(P);
+    cudaStream_t st = D.stream;
+    if (lane >= 0) {
+        st = D.lane_stream[lane];
+        P.seg_buf = D.seg_buf + (size_t)lane * (D.seg_records / 2) * 2;  // (2 x float4 per record)
+        P.seg_count = D.seg_count + (size_t)lane * (SEG_MAX_SHARES + 1);
+        P.seg_work = P.seg_count + SEG_MAX_SHARES;
+        P.next = D.counters + C_COUNT + 17 + lane;
+        CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), st));
+    }
+    kern<<<(unsigned)blocks, SMCRT_BLOCK, smem_bytes, st>>>(P);
     CU(cudaGetLastError());
     if (pathlen && !seg_inline) {  // walk what the launch recorded, then clear the shares for the next launch
-        CU(cudaFuncSetAttribute(deposit_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HotTable)));
-        deposit_segments_kernel<<<D.sm_count * 3, 256, sizeof(HotTable), D.stream>>>(P, (int)blocks);  // 3 CTAs of 64 KB per SM
-        clear_segment_counts_kernel<<<1, 256, 0, D.stream>>>(D.seg_count, (int)blocks, D.seg_count + SEG_MAX_SHARES);
+        // 2 CTAs of 512 threads per SM (64 registers): a third more warps than 3 x 256 at 80 registers, +7 % on sphere.toml / skin
+        // 2 CTAs of 512 threads per SM at 64 registers: a third more warps than 3 x 256 at 80 registers (+7 % on sphere.toml and skin)
+        constexpr int DEP_THREADS = 512, DEP_CTAS = 2;
+        const int dep_smem = (int)sizeof(HotTable) + (DEP_THREADS / 32) * RUNQ_CAP * 2 * (int)sizeof(float4);  // the table + the warps' run queues
+        CU(cudaFuncSetAttribute(deposit_segments_kernel<DEP_THREADS, DEP_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dep_smem));
+        deposit_segments_kernel<DEP_THREADS, DEP_CTAS><<<D.sm_count * DEP_CTAS, DEP_THREADS, dep_smem, st>>>(P, (int)blocks);
+        clear_segment_counts_kernel<<<1, 256, 0, st>>>(P.seg_count, (int)blocks, P.seg_work);
         CU(cudaGetLastError());
     }
     return 0;
@@ -938,14 +963,14 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D,
 struct Variant { int sched; int mb; };
 constexpr int NVAR = 6;
 static const Variant VARIANTS[NVAR] = {{SCHED_PLAIN, 2}, {SCHED_PLAIN, 3}, {SCHED_PLAIN, 4}, {SCHED_COMPACT, 2}, {SCHED_QUEUED, 2}, {SCHED_QUEUED, 3}};
-static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false, bool seg_inline = false) {
+static int launch_variant(bool pl, bool hd, int var, const KParams& P, DeviceState& D, const int smem_bytes[3], bool dry = false, bool seg_inline = false, int lane = -1) {
     const Variant v = VARIANTS[var];
     const bool need = P.has_capsule != 0, simple = P.simple_scene != 0;
     // LEAN: nothing optional asked of this run (no per-packet records, diagnostics, batched sources, survival biasing)
     const bool lean = !P.out_fate && !P.out_nscatt && !P.out_dbg && !P.dbg_log && !P.src_table && !P.src_tot && !P.survival && !P.out_vert && !P.id_list;
     trace_kernel_t k = pl ? (hd ? pick_kernel_pl1_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl1_hd0(v.sched, v.mb, need, simple, lean))
                           : (hd ? pick_kernel_pl0_hd1(v.sched, v.mb, need, simple, lean) : pick_kernel_pl0_hd0(v.sched, v.mb, need, simple, lean));
-    return launch_kernel(k, P, D, smem_bytes[v.sched], dry, seg_inline);
+    return launch_kernel(k, P, D, smem_bytes[v.sched], dry, seg_inline, lane);
 }
 
 // Path-length deposits waiting in the difference grids -> jmean (prefix sums along each touched axis; the grids come back zero).
@@ -1002,8 +1027,10 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
             if (const char* e = getenv("SMCRT_SEG_MB")) bytes = std::max<size_t>((size_t)atoll(e), 1) << 20;
             CU(cudaMalloc(&D.seg_buf, bytes));
             D.seg_records = bytes / 32;
-            CU(cudaMalloc(&D.seg_count, sizeof(unsigned int) * (SEG_MAX_SHARES + 1)));  // + the deposit kernel's work counter
-            CU(cudaMemsetAsync(D.seg_count, 0, sizeof(unsigned int) * (SEG_MAX_SHARES + 1), D.stream));
+            CU(cudaMalloc(&D.seg_count, sizeof(unsigned int) * 2 * (SEG_MAX_SHARES + 1)));  // per lane: the shares' counts + the deposit kernel's work counter
+            CU(cudaMemsetAsync(D.seg_count, 0, sizeof(unsigned int) * 2 * (SEG_MAX_SHARES + 1), D.stream));
+            for (cudaStream_t& s : D.lane_stream) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            for (cudaEvent_t* ev : {&D.ev_fork, &D.ev_lane[0], &D.ev_lane[1]}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
             CU(cudaMalloc(&D.seg_total, 8));
             CU(cudaMemsetAsync(D.seg_total, 0, 8, D.stream));
             P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total; P.seg_work = D.seg_count + SEG_MAX_SHARES;
@@ -1101,18 +1128,36 @@ static int run_on_device(smcrt_ctx* c, DeviceState& D, long long nphotons, uint6
     // Path-length mode: a launch may produce no more segments than the segment buffer holds (a CTA whose share is full walks its
     // segments inline: correct, but slow), so the run is cut into chunks of packets sized from the scene's measured segments per
     // packet, with a margin for the spread between CTAs.
+    // A run of several chunks alternates between the two lanes (chunks of half the buffer, of equal size).  A launch ends with its
+    // slowest history -- ~10 ms for a packet of sphere.toml that is reflected 1000 times inside a sphere, whatever the chunk -- and on
+    // ONE stream the next trace kernel and the deposit kernel would wait for it with the machine empty.  On two streams the next
+    // chunk's CTAs move in as this chunk's CTAs leave, and each lane's deposit kernel follows its trace kernel in stream order.
     long long left = P.nphotons;
-    while (left > 0) {
+    static const bool no_lanes = getenv("SMCRT_PL_LANES") && atoi(getenv("SMCRT_PL_LANES")) == 0;  // A/B switch
+    const bool lanes = pl && c->seg_inline != 1 && left > chunk_max && !no_lanes;
+    if (lanes) {
+        const long long half_max = std::max<long long>(chunk_max / 2, 1ll << 15);
+        const long long n_chunks = (left + half_max - 1) / half_max;
+        chunk_max = (left + n_chunks - 1) / n_chunks;
+        CU(cudaEventRecord(D.ev_fork, D.stream));
+        for (cudaStream_t s : D.lane_stream) CU(cudaStreamWaitEvent(s, D.ev_fork, 0));
+    }
+    for (int k = 0; left > 0; ++k) {
         const long long chunk = std::min(left, chunk_max);
         KParams Q = P;
         Q.nphotons = chunk;
-        int rc = launch_variant(pl, hd, var, Q, D, smem_bytes, false, c->seg_inline == 1);
+        int rc = launch_variant(pl, hd, var, Q, D, smem_bytes, false, c->seg_inline == 1, lanes ? (k & 1) : -1);
         if (rc) return rc;
         P.id_offset += (unsigned long long)chunk;
         left -= chunk;
         ++n_launch;
-        if (left > 0) CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
+        if (left > 0 && !lanes) CU(cudaMemsetAsync(P.next, 0, sizeof(unsigned long long), D.stream));
     }
+    if (lanes)
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventRecord(D.ev_lane[b], D.lane_stream[b]));
+            CU(cudaStreamWaitEvent(D.stream, D.ev_lane[b], 0));
+        }
     CU(cudaEventRecord(D.ev1, D.stream));
     D.ran = true;
     c->launches += (pl ? 3 : 1) * n_launch;

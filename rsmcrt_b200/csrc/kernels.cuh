@@ -89,6 +89,8 @@ struct KParams {
     unsigned int seg_cap;
     int seg_off;
     unsigned int* seg_work;         // work counter of deposit_segments_kernel (cleared with the shares)
+    int seg_defer;                  // (experiments) 0: run-walk segments are walked where they turn up
+    float seg_piece;                // the deposit kernel cuts segments into pieces of about this many voxel visits, one piece per lane
     unsigned long long* seg_total;  // all segments produced (recorded or, when a CTA's share was full, walked inline)
     // optional per-packet outputs (smcrt_trace_packets)
     int* out_fate;
@@ -561,6 +563,7 @@ __device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(r
 // updates of the entries it holds (two native 32-bit shared adds with carry) and is flushed once per CTA; an entry that found no
 // slot goes to L2 as before, so a diffuse scene (millions of distinct entries) loses only the probes.
 constexpr int HOT_SLOTS = 4096, HOT_PROBES = 3;
+constexpr int RUNQ_CAP = 64;  // records in a warp's run-walk queue of the deposit kernel (2 x float4 each)
 struct HotTable {
     unsigned long long key[HOT_SLOTS];
     unsigned int lo[HOT_SLOTS], hi[HOT_SLOTS];
@@ -582,9 +585,43 @@ __device__ __forceinline__ void red_i64_hot(HotTable* T, long long* p, long long
     }
     red_i64(p, v);
 }
-// `hot`: the deposit kernel's table (nullptr: every range update goes straight to L2)
-static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
-                                                  HotTable* hot = nullptr) {
+// Two functions (the deposit kernel knows which one a segment takes and calls it directly: each gets its own register allocation).
+// walk_voxels: the voxel walk.  Returns (voxels visited, atomics issued).
+static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+    if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
+    const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
+    const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
+    const long long off = (long long)S.c[0] + vy * (long long)S.c[1] + vz * (long long)S.c[2];
+    // faces that can still be crossed along each axis before the walk leaves the grid
+    int rx = dx > 0.f ? P.nxg - 1 - S.c[0] : S.c[0], ry = dy > 0.f ? P.nyg - 1 - S.c[1] : S.c[1], rz = dz > 0.f ? P.nzg - 1 - S.c[2] : S.c[2];
+    float tx = S.t[0], ty = S.t[1], tz = S.t[2];
+    const float dtx = S.dt[0], dty = S.dt[1], dtz = S.dt[2];
+    float t = 0.f;
+    // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
+    const long long svx = dx > 0.f ? 1ll : -1ll, svy = dy > 0.f ? vy : -vy, svz = dz > 0.f ? vz : -vz;
+    float* cell = P.jmean + off;
+    unsigned int nvox = 0u;
+    for (;;) {
+        const float tn = fminf(tx, fminf(ty, tz));
+        ++nvox;
+        if (tn >= len) {
+            atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
+            break;
+        }
+        atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
+        t = tn;
+        // which face: x before y before z on a tie.  Selects, not branches: the lanes of a warp walk different rays
+        const bool stx = tx <= ty && tx <= tz, sty = !stx && ty <= tz, stz = !stx && !sty;
+        cell += stx ? svx : (sty ? svy : svz);
+        tx += stx ? dtx : 0.f; ty += sty ? dty : 0.f; tz += stz ? dtz : 0.f;
+        rx -= stx ? 1 : 0; ry -= sty ? 1 : 0; rz -= stz ? 1 : 0;
+        if ((rx | ry | rz) < 0) break;  // :437-440
+    }
+    return make_uint2(nvox, nvox);
+}
+// walk_runs: the run walk.  `hot`: the deposit kernel's table (nullptr: every range update goes straight to L2)
+static __device__ __noinline__ uint2 walk_runs(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
+                                               HotTable* hot) {
     if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
     const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
@@ -594,35 +631,6 @@ static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, fl
     const bool a0 = a == 0, a1 = a == 1, a2 = a == 2;
     const float dta = a0 ? S.dt[0] : (a1 ? S.dt[1] : S.dt[2]);
     const float dtb = a0 ? S.dt[1] : S.dt[0], dtc = a2 ? S.dt[1] : S.dt[2];
-    if (P.dda_legacy || len < 6.0f * dta || fminf(dtb, dtc) < 4.0f * dta) {
-        // ---- voxel walk
-        int i = S.c[0], j = S.c[1], k = S.c[2];
-        const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
-        float tx = S.t[0], ty = S.t[1], tz = S.t[2];
-        const float dtx = S.dt[0], dty = S.dt[1], dtz = S.dt[2];
-        float t = 0.f;
-        // the voxel's flat index is carried along (one 64-bit add per crossing instead of two 64-bit multiply-adds)
-        const long long svx = sx, svy = sy > 0 ? vy : -vy, svz = sz > 0 ? vz : -vz;
-        float* cell = P.jmean + off;
-        unsigned int nvox = 0u;
-        for (;;) {
-            const float tn = fminf(tx, fminf(ty, tz));
-            ++nvox;
-            if (tn >= len) {
-                atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
-                break;
-            }
-            atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
-            t = tn;
-            bool out;  // (unsigned)index >= n  <=>  index < 0 or index >= n
-            if (tx <= ty && tx <= tz) { i += sx; cell += svx; tx += dtx; out = (unsigned)i >= (unsigned)P.nxg; }
-            else if (ty <= tz)        { j += sy; cell += svy; ty += dty; out = (unsigned)j >= (unsigned)P.nyg; }
-            else                      { k += sz; cell += svz; tz += dtz; out = (unsigned)k >= (unsigned)P.nzg; }
-            if (out) break;  // :437-440
-        }
-        return make_uint2(nvox, nvox);
-    }
-    // ---- run walk
     float ta = a0 ? S.t[0] : (a1 ? S.t[1] : S.t[2]);
     int ia = a0 ? S.c[0] : (a1 ? S.c[1] : S.c[2]);
     const int na = a0 ? P.nxg : (a1 ? P.nyg : P.nzg);
@@ -701,6 +709,21 @@ static __device__ __noinline__ uint2 walk_segment(const KParams& P, float fx, fl
     if (used) P.jdiff_used[a] = 1u;
     return make_uint2(nvox, nred);
 }
+// Does the run walk pay for this segment?  Only if it is at least 6 voxels long along its dominant axis and steep enough that a
+// column lasts 4 voxels (faces crossed per unit length along each axis: r = |u| / vox).
+__device__ __forceinline__ bool takes_run_walk(const KParams& P, float dx, float dy, float dz, float len, float& work) {
+    const float rx = fabsf(dx) * P.inv_vox[0], ry = fabsf(dy) * P.inv_vox[1], rz = fabsf(dz) * P.inv_vox[2];
+    const float rmax = fmaxf(rx, fmaxf(ry, rz)), rsum = rx + ry + rz;
+    const float rmid = fmaxf(fminf(rx, ry), fminf(fmaxf(rx, ry), rz));
+    const bool runs = !P.dda_legacy && len * rmax > 6.0f && rmax > 4.0f * rmid;
+    work = 1.0f + len * (runs ? 2.0f * (rsum - rmax) : rsum);  // a segment the run walker takes only works per COLUMN change
+    return runs;
+}
+static __device__ __forceinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
+                                                     HotTable* hot = nullptr) {
+    float work;
+    return takes_run_walk(P, dx, dy, dz, len, work) ? walk_runs(P, fx, fy, fz, dx, dy, dz, len, weight, hot) : walk_voxels(P, fx, fy, fz, dx, dy, dz, len, weight);
+}
 
 // Prefix sum of one difference grid along its axis, added to jmean; the grid is cleared on the way.
 //   AXIS 0 (x, contiguous): one warp per row, 32 entries per step (shuffle scan + carry)
@@ -766,18 +789,26 @@ __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* s
 
 #ifndef SMCRT_TRACE_TU  // (engine.cu only)
 // The deposit kernel: walks the recorded segments.  One warp takes 32 records of a CTA's share at a time (two coalesced 16-byte
-// loads per lane).  Segments with little work -- the free paths of a turbid medium, anything the run walker takes -- are walked
-// by their own lanes, all at once; a segment that crosses many voxels obliquely (a refracted ray through the 200^3 grid of
-// sphere.toml) is SHARED: lane j walks the j-th 32nd of it (a voxel that holds a cut point gets its length in two deposits).
+// loads per lane) and sorts them by the work they are: short segments for the voxel walk -- the free paths of a turbid medium --
+// are walked by their own lanes, all at once; segments for the run walker wait in the warp's queue until a warp's worth has
+// gathered; and a long segment (the 300-voxel flight of an escaping packet, a refracted ray through the 200^3 grid of sphere.toml)
+// is cut into pieces of seg_piece voxel visits that are dealt out to the lanes.
 // A small kernel with a small loop: the voxel walk does not compete with the transport code for the instruction cache (in one
 // kernel the hot code was 39 KB, beyond the 32 KB L1.5 I-cache: 6 stall cycles per issue waiting for instructions).
-__global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     unsigned long long c_vox = 0ull, c_red = 0ull;
     extern __shared__ __align__(16) unsigned char dsm[];
     HotTable* hot = reinterpret_cast<HotTable*>(dsm);
     for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x) { hot->key[i] = 0ull; hot->lo[i] = 0u; hot->hi[i] = 0u; }
     __syncthreads();
+    // The warp's queue of segments for the RUN walker (behind the table in shared memory, 64 records).  A batch of a turbid scene
+    // holds one or two of them -- the beam's first flight, a long free path along an axis -- and the run walk is long straight-line
+    // code: taken where they turn up, it ran on 1.3 lanes of 32 and was 28 % of the kernel's instructions on skin_b200.toml.  They
+    // wait here until 32 have gathered and are then walked one per lane.
+    float4* const runq = reinterpret_cast<float4*>(dsm + sizeof(HotTable)) + warp * (2 * RUNQ_CAP);
+    int n_runq = 0;  // (warp-uniform)
     // work items = (share, eighth of the share), handed out by a global counter: the CTAs of this launch are persistent (as many as
     // fit beside their 64-KB tables) and stay busy until the last record
     __shared__ unsigned int item_s;
@@ -799,32 +830,73 @@ __global__ void __launch_bounds__(256) deposit_segments_kernel(const __grid_cons
             const unsigned int i = base + lane;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f);
             float work = 0.f;
+            bool runs = false;
             if (i < n) {
                 a = recs[2u * i]; b = recs[2u * i + 1u];
-                // faces crossed per unit length along each axis; a segment the run walker takes only works per COLUMN change
-                const float rx = fabsf(b.x) * P.inv_vox[0], ry = fabsf(b.y) * P.inv_vox[1], rz = fabsf(b.z) * P.inv_vox[2];
-                const float rmax = fmaxf(rx, fmaxf(ry, rz)), rsum = rx + ry + rz;
-                const float rmid = fmaxf(fminf(rx, ry), fminf(fmaxf(rx, ry), rz));
-                const bool runs = !P.dda_legacy && a.w * rmax > 6.0f && rmax > 4.0f * rmid;
-                work = 1.0f + a.w * (runs ? 2.0f * (rsum - rmax) : rsum);
+                runs = takes_run_walk(P, b.x, b.y, b.z, a.w, work);
             }
-            const bool share = work >= 96.0f;
-            if (work > 0.f && !share) {
-                const uint2 w = walk_segment(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, hot);
+            // The 32 segments of a batch are of very different lengths (a free path of two voxels next to the 300-voxel flight of an
+            // escaping packet): walked one per lane, the warp waits for its longest with 3-7 lanes of 32 busy (ncu:
+            // profiles/r02_skin_deposit_kernel.txt).  So every segment is cut into PIECES of about seg_piece voxel visits, the pieces
+            // of the batch are numbered through (a warp prefix sum), and lane j of pass p walks piece 32 p + j of whichever segment
+            // it belongs to (its record fetched by shuffle): equal work per lane.  A voxel that holds a cut gets its length in two
+            // deposits.  The short segments (one piece) go first, each on its own lane, so that they do not wait for longer pieces.
+            const bool brief = work > 0.f && work <= P.seg_piece;
+            const bool defer = brief && runs && P.seg_defer;
+            const unsigned dm = __ballot_sync(0xffffffffu, defer);
+            if (dm) {
+                if (defer) {
+                    const int at = n_runq + __popc(dm & ((1u << lane) - 1u));
+                    runq[2 * at] = a; runq[2 * at + 1] = b;
+                }
+                n_runq += __popc(dm);
+                __syncwarp();
+            }
+            if (brief && !defer) {
+                const uint2 w = runs ? walk_runs(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, hot) : walk_voxels(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
                 c_vox += w.x; c_red += w.y;
             }
-            unsigned pend = __ballot_sync(0xffffffffu, share);
-            while (pend) {
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1u;
-                const float L = __shfl_sync(0xffffffffu, a.w, src), w = __shfl_sync(0xffffffffu, b.w, src);
-                const float ax = __shfl_sync(0xffffffffu, a.x, src), ay = __shfl_sync(0xffffffffu, a.y, src), az = __shfl_sync(0xffffffffu, a.z, src);
-                const float vx = __shfl_sync(0xffffffffu, b.x, src), vy = __shfl_sync(0xffffffffu, b.y, src), vz = __shfl_sync(0xffffffffu, b.z, src);
-                const float t0 = L * ((float)lane * 0.03125f), t1 = lane == 31 ? L : L * ((float)(lane + 1) * 0.03125f);
-                const uint2 wk = walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w);
-                c_vox += wk.x; c_red += wk.y;
+            const int np = (work > 0.f && !brief) ? (int)fminf(ceilf(work / P.seg_piece), 65536.f) : 0;
+            int incl = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int g0 = 0; g0 < total; g0 += 32) {
+                const int g = min(g0 + lane, total - 1);
+                int own = 0;  // the segment piece g belongs to: the number of lanes whose pieces all come before it
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, own + s - 1);
+                    if (v <= g) own += s;
+                }
+                const int npo = __shfl_sync(0xffffffffu, np, own), first = __shfl_sync(0xffffffffu, incl, own) - npo;
+                const float L = __shfl_sync(0xffffffffu, a.w, own), w = __shfl_sync(0xffffffffu, b.w, own);
+                const float ax = __shfl_sync(0xffffffffu, a.x, own), ay = __shfl_sync(0xffffffffu, a.y, own), az = __shfl_sync(0xffffffffu, a.z, own);
+                const float vx = __shfl_sync(0xffffffffu, b.x, own), vy = __shfl_sync(0xffffffffu, b.y, own), vz = __shfl_sync(0xffffffffu, b.z, own);
+                if (g0 + lane < total) {
+                    const int q = g - first;
+                    const float inv = 1.0f / (float)npo;
+                    const float t0 = L * ((float)q * inv), t1 = q + 1 == npo ? L : L * ((float)(q + 1) * inv);
+                    const uint2 wk = walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w, hot);
+                    c_vox += wk.x; c_red += wk.y;
+                }
+            }
+            if (n_runq >= 32) {  // (last: the batch's own records are no longer live across this call)
+                n_runq -= 32;
+                const float4 qa = runq[2 * (n_runq + lane)], qb = runq[2 * (n_runq + lane) + 1];
+                __syncwarp();
+                const uint2 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, hot);
+                c_vox += w.x; c_red += w.y;
             }
         }
+    }
+    if (lane < n_runq) {  // what is left in the warp's queue
+        const float4 qa = runq[2 * lane], qb = runq[2 * lane + 1];
+        const uint2 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, hot);
+        c_vox += w.x; c_red += w.y;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x)  // flush the table: one L2 atomic per entry held
@@ -1402,6 +1474,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     unsigned int slot = 0;
     bool has = false;  // this lane holds a packet (slot `slot`) in registers
     int wc = -1;       // class of the warp's previous iteration (warp-uniform)
+    bool draining = false;  // a slot of this warp has found the packet pool empty (warp-uniform)
     for (;;) {
         // ---- which class does the warp work on next
         const int cls = !has ? -1 : (state <= ST_CROSS ? Q_SWEEP : (state == ST_FRESNEL ? Q_FRESNEL : (state == ST_INTERACT ? Q_INTERACT : Q_EMIT)));
@@ -1409,7 +1482,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         unsigned keep = 0u;
         // usual case: enough lanes are still in the class the warp worked on last time (one ballot instead of four)
         const unsigned stay = wc >= 0 ? __ballot_sync(full, cls == wc) : 0u;
-        if (__popc(stay) >= KEEP_MIN) { c = wc; keep = stay; }
+        if (__popc(stay) >= (draining ? 1 : KEEP_MIN)) { c = wc; keep = stay; }
         else {
             int bestn = 0;
 #pragma unroll
@@ -1418,7 +1491,11 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                 const int k = __popc(m);
                 if (k > bestn) { bestn = k; c = q; keep = m; }
             }
-            if (bestn < KEEP_MIN) { c = -1; keep = 0u; }
+            // Few packets held: they are all queued and the warp takes a batch of the fullest class, which gathers the stragglers
+            // of the CTA's warps.  Not at the END of a launch (one packet is enough once a slot of this warp has found the packet pool
+            // empty): there is less and less to gather then, and the last histories (a packet on its 1000 reflections inside a
+            // sphere of sphere.toml: 10 ms alone) would be stored and reloaded at every step.  They stay in registers.
+            if (bestn < (draining ? 1 : KEEP_MIN)) { c = -1; keep = 0u; }
         }
         // ---- store and queue the packets that leave (all of them when no class is kept)
         const bool push = has && cls != c;
@@ -1552,6 +1629,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         if (gone) {
             if (lane == 0) atomicAdd(&qc->retired, (unsigned int)__popc(gone));
             if (state == ST_DONE) has = false;
+            draining = true;
         }
     }
 #include "step_macros_undef.inc"

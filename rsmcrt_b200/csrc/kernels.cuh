@@ -1429,7 +1429,9 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     const int M = blockDim.x * QSLOTS_PER_THREAD;  // packets in flight per CTA (power of two: the rings wrap with a mask)
     QueueCtl* qc = reinterpret_cast<QueueCtl*>(smem + P.xchg_off);
     unsigned short* ring = reinterpret_cast<unsigned short*>(qc + 1);                  // [Q_COUNT][M]
-    uint4* slots = reinterpret_cast<uint4*>(ring + Q_COUNT * M);                         // [M][6]
+    // [6][M]: word k of every slot in one plane, so that the lanes of a warp (different slots, same word) spread over the banks --
+    // slot-major (96-byte stride) put them on four of the eight 16-byte columns: 3.5 wavefronts per access where 1 is ideal
+    uint4* slots = reinterpret_cast<uint4*>(ring + Q_COUNT * M);
     volatile QueueCtl* vq = qc;
     if (threadIdx.x < Q_COUNT) {
         const unsigned int n0 = threadIdx.x == Q_EMIT ? (unsigned int)M : 0u;          // every slot starts free
@@ -1438,7 +1440,7 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
     if (threadIdx.x == 0) qc->retired = 0u;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         ring[Q_EMIT * M + i] = (unsigned short)i;
-        slots[6 * i + 3] = make_uint4(0u, 0u, (uint32_t)ST_EMIT, 0u);                    // w[14]: state EMIT, no packet id yet
+        slots[3 * M + i] = make_uint4(0u, 0u, (uint32_t)ST_EMIT, 0u);                    // w[14]: state EMIT, no packet id yet
     }
     if (HASDET && P.det_in_smem)
         for (int i = threadIdx.x; i < P.det_total; i += blockDim.x) sbins[i] = 0ull;
@@ -1501,15 +1503,15 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
         const bool push = has && cls != c;
         const unsigned pm = __ballot_sync(full, push);
         if (push) {
-            uint4* w = slots + 6 * slot;
+            uint4* w = slots + slot;
             w[0] = make_uint4((uint32_t)__double2loint(pxd), (uint32_t)__double2hiint(pxd), (uint32_t)__double2loint(pyd), (uint32_t)__double2hiint(pyd));
-            w[1] = make_uint4((uint32_t)__double2loint(pzd), (uint32_t)__double2hiint(pzd), __float_as_uint(ux), __float_as_uint(uy));
-            w[2] = make_uint4(__float_as_uint(uz), __float_as_uint(tau), __float_as_uint(taurun), __float_as_uint(dstep));
-            w[3] = make_uint4(__float_as_uint(dlast), (uint32_t)layer | ((uint32_t)new_layer << 16),
-                              (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u) | (ev << 11),
-                              (uint32_t)steps | ((uint32_t)bounces << 21));
-            w[4] = make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), __float_as_uint(sx), __float_as_uint(sy));
-            w[5] = make_uint4(__float_as_uint(sz), __float_as_uint(weight), 0u, 0u);
+            w[M] = make_uint4((uint32_t)__double2loint(pzd), (uint32_t)__double2hiint(pzd), __float_as_uint(ux), __float_as_uint(uy));
+            w[2 * M] = make_uint4(__float_as_uint(uz), __float_as_uint(tau), __float_as_uint(taurun), __float_as_uint(dstep));
+            w[3 * M] = make_uint4(__float_as_uint(dlast), (uint32_t)layer | ((uint32_t)new_layer << 16),
+                                  (uint32_t)state | ((uint32_t)phase << 4) | (tflag ? 256u : 0u) | (launch ? 512u : 0u) | (have_pid ? 1024u : 0u) | (ev << 11),
+                                  (uint32_t)steps | ((uint32_t)bounces << 21));
+            w[4 * M] = make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), __float_as_uint(sx), __float_as_uint(sy));
+            w[5 * M] = make_uint4(__float_as_uint(sz), __float_as_uint(weight), 0u, 0u);
             const unsigned grp = __match_any_sync(pm, cls);
             const int cnt = __popc(grp), lead = __ffs(grp) - 1;
             unsigned int start = 0;
@@ -1568,8 +1570,8 @@ __global__ void __launch_bounds__(SMCRT_BLOCK, (MINBLOCKS * 256) / SMCRT_BLOCK) 
                 const unsigned int rank = (unsigned int)__popc(freem & ((1u << lane) - 1u));
                 if (((freem >> lane) & 1u) && rank < n) {
                     slot = ring[q * M + ((h0 + rank) & mask)];
-                    const uint4* r = slots + 6 * slot;
-                    const uint4 a = r[0], b = r[1], cc = r[2], d = r[3], e = r[4], f = r[5];
+                    const uint4* r = slots + slot;
+                    const uint4 a = r[0], b = r[M], cc = r[2 * M], d = r[3 * M], e = r[4 * M], f = r[5 * M];
                     pxd = __hiloint2double((int)a.y, (int)a.x); pyd = __hiloint2double((int)a.w, (int)a.z); pzd = __hiloint2double((int)b.y, (int)b.x);
                     px = (float)pxd; py = (float)pyd; pz = (float)pzd;
                     ux = __uint_as_float(b.z); uy = __uint_as_float(b.w); uz = __uint_as_float(cc.x);

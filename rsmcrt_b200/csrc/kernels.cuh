@@ -568,7 +568,7 @@ struct HotTable {
     unsigned long long key[HOT_SLOTS];
     unsigned int lo[HOT_SLOTS], hi[HOT_SLOTS];
 };
-__device__ __forceinline__ void red_i64_hot(HotTable* T, long long* p, long long v) {
+__device__ __forceinline__ bool red_i64_hot(HotTable* T, long long* p, long long v) {  // true: the table took it
     const unsigned long long k = (unsigned long long)p;
     unsigned int h = (unsigned int)((k >> 3) * 0x9E3779B97F4A7C15ull >> 52);
 #pragma unroll
@@ -579,11 +579,12 @@ __device__ __forceinline__ void red_i64_hot(HotTable* T, long long* p, long long
             const unsigned int vl = (unsigned int)(unsigned long long)v, vh = (unsigned int)((unsigned long long)v >> 32);
             const unsigned int old = atomicAdd(&T->lo[h], vl);
             atomicAdd(&T->hi[h], vh + ((old + vl < old) ? 1u : 0u));
-            return;
+            return true;
         }
         h = (h + 1u) & (HOT_SLOTS - 1);
     }
     red_i64(p, v);
+    return false;
 }
 // Two functions (the deposit kernel knows which one a segment takes and calls it directly: each gets its own register allocation).
 // walk_voxels: the voxel walk.  Returns (voxels visited, atomics issued).
@@ -620,9 +621,10 @@ static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, flo
     return make_uint2(nvox, nvox);
 }
 // walk_runs: the run walk.  `hot`: the deposit kernel's table (nullptr: every range update goes straight to L2)
-static __device__ __noinline__ uint2 walk_runs(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
+// Returns (voxels visited, atomics issued, range-update entries offered to the table, entries it took).
+static __device__ __noinline__ uint4 walk_runs(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
                                                HotTable* hot) {
-    if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
+    if (!in_grid(P, fx, fy, fz)) return make_uint4(0u, 0u, 0u, 0u);  // :411-415
     const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
     long long off = (long long)S.c[0] + vy * (long long)S.c[1] + vz * (long long)S.c[2];
@@ -648,7 +650,7 @@ static __device__ __noinline__ uint2 walk_runs(const KParams& P, float fx, float
     const float fix = (a0 ? P.jfix[0] : (a1 ? P.jfix[1] : P.jfix[2])) * weight;
     float t = 0.f;
     bool used = false;
-    unsigned int nvox = 0u, nred = 0u;
+    unsigned int nvox = 0u, nred = 0u, n_try = 0u, n_hit = 0u;
     for (;;) {
         const float tcol = fminf(tb, tc);        // the ray leaves this column (or never: BIG)
         const float tend = fminf(tcol, len);
@@ -682,10 +684,11 @@ static __device__ __noinline__ uint2 walk_runs(const KParams& P, float fx, float
                 long long* lo = D + (fwd ? off : off - (long long)m * stra);
                 const int hi_idx = fwd ? ia + m : ia;
                 if (hot) {
-                    red_i64_hot(hot, lo, q_lo);
-                    red_i64_hot(hot, lo + stra, qc - q_lo);
-                    red_i64_hot(hot, lo + (long long)m * stra, q_hi - qc);
-                    if (hi_idx + 1 < na) red_i64_hot(hot, lo + (long long)(m + 1) * stra, -q_hi);
+                    n_hit += red_i64_hot(hot, lo, q_lo) ? 1u : 0u;
+                    n_hit += red_i64_hot(hot, lo + stra, qc - q_lo) ? 1u : 0u;
+                    n_hit += red_i64_hot(hot, lo + (long long)m * stra, q_hi - qc) ? 1u : 0u;
+                    if (hi_idx + 1 < na) n_hit += red_i64_hot(hot, lo + (long long)(m + 1) * stra, -q_hi) ? 1u : 0u;
+                    n_try += 4u;
                 } else {
                     red_i64(lo, q_lo);
                     red_i64(lo + stra, qc - q_lo);
@@ -707,7 +710,7 @@ static __device__ __noinline__ uint2 walk_runs(const KParams& P, float fx, float
         if (out) break;
     }
     if (used) P.jdiff_used[a] = 1u;
-    return make_uint2(nvox, nred);
+    return make_uint4(nvox, nred, n_try, n_hit);
 }
 // Does the run walk pay for this segment?  Only if it is at least 6 voxels long along its dominant axis and steep enough that a
 // column lasts 4 voxels (faces crossed per unit length along each axis: r = |u| / vox).
@@ -722,7 +725,11 @@ __device__ __forceinline__ bool takes_run_walk(const KParams& P, float dx, float
 static __device__ __forceinline__ uint2 walk_segment(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight,
                                                      HotTable* hot = nullptr) {
     float work;
-    return takes_run_walk(P, dx, dy, dz, len, work) ? walk_runs(P, fx, fy, fz, dx, dy, dz, len, weight, hot) : walk_voxels(P, fx, fy, fz, dx, dy, dz, len, weight);
+    if (takes_run_walk(P, dx, dy, dz, len, work)) {
+        const uint4 w = walk_runs(P, fx, fy, fz, dx, dy, dz, len, weight, hot);
+        return make_uint2(w.x, w.y);
+    }
+    return walk_voxels(P, fx, fy, fz, dx, dy, dz, len, weight);
 }
 
 // Prefix sum of one difference grid along its axis, added to jmean; the grid is cleared on the way.
@@ -809,8 +816,11 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
     // wait here until 32 have gathered and are then walked one per lane.
     float4* const runq = reinterpret_cast<float4*>(dsm + sizeof(HotTable)) + warp * (2 * RUNQ_CAP);
     int n_runq = 0;  // (warp-uniform)
+    bool use_hot = true;  // (warp-uniform) the table still takes a fair share of what this warp offers it
+    unsigned int hot_try = 0u, hot_hit = 0u;
     // work items = (share, eighth of the share), handed out by a global counter: the CTAs of this launch are persistent (as many as
-    // fit beside their 64-KB tables) and stay busy until the last record
+    // fit beside their 64-KB tables) and stay busy until the last record.  (Handed out to single warps, a 64th of a share at a
+    // time and no barrier, the kernel was 1-3 % slower: the warps of a CTA no longer read neighbouring records.)
     __shared__ unsigned int item_s;
     constexpr unsigned int PARTS = 8u;
     for (;;) {
@@ -853,8 +863,13 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                 __syncwarp();
             }
             if (brief && !defer) {
-                const uint2 w = runs ? walk_runs(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, hot) : walk_voxels(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
-                c_vox += w.x; c_red += w.y;
+                if (runs) {  // (only with the queue switched off)
+                    const uint4 w = walk_runs(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, use_hot ? hot : nullptr);
+                    c_vox += w.x; c_red += w.y;
+                } else {
+                    const uint2 w = walk_voxels(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
+                    c_vox += w.x; c_red += w.y;
+                }
             }
             const int np = (work > 0.f && !brief) ? (int)fminf(ceilf(work / P.seg_piece), 65536.f) : 0;
             int incl = np;
@@ -880,7 +895,7 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                     const int q = g - first;
                     const float inv = 1.0f / (float)npo;
                     const float t0 = L * ((float)q * inv), t1 = q + 1 == npo ? L : L * ((float)(q + 1) * inv);
-                    const uint2 wk = walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w, hot);
+                    const uint2 wk = walk_segment(P, fmaf(t0, vx, ax), fmaf(t0, vy, ay), fmaf(t0, vz, az), vx, vy, vz, t1 - t0, w, use_hot ? hot : nullptr);
                     c_vox += wk.x; c_red += wk.y;
                 }
             }
@@ -888,14 +903,24 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                 n_runq -= 32;
                 const float4 qa = runq[2 * (n_runq + lane)], qb = runq[2 * (n_runq + lane) + 1];
                 __syncwarp();
-                const uint2 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, hot);
+                const uint4 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, use_hot ? hot : nullptr);
                 c_vox += w.x; c_red += w.y;
+                // Does the table earn its probes?  On a pencil beam nearly every entry is one of the ~1300 it holds; on a diffuse scene
+                // (sphere.toml) it fills with entries that never come back and every update pays three probes for nothing -- a third
+                // of this kernel's instructions (profiles/r02_sphere_deposit_kernel.txt).  The warp counts, and stops offering.
+                if (use_hot) {
+                    hot_try += __reduce_add_sync(0xffffffffu, w.z); hot_hit += __reduce_add_sync(0xffffffffu, w.w);
+                    if (hot_try >= 1024u) {
+                        if (4u * hot_hit < hot_try) use_hot = false;
+                        hot_try = 0u; hot_hit = 0u;
+                    }
+                }
             }
         }
     }
     if (lane < n_runq) {  // what is left in the warp's queue
         const float4 qa = runq[2 * lane], qb = runq[2 * lane + 1];
-        const uint2 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, hot);
+        const uint4 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, use_hot ? hot : nullptr);
         c_vox += w.x; c_red += w.y;
     }
     __syncthreads();

@@ -908,8 +908,6 @@ static int fill_params(smcrt_ctx* c, DeviceState& D, KParams& P) {
     P.seg_buf = D.seg_buf; P.seg_count = D.seg_count; P.seg_total = D.seg_total; P.seg_work = D.seg_count ? D.seg_count + SEG_MAX_SHARES : nullptr;
     static const float piece = getenv("SMCRT_SEG_PIECE") ? std::max((float)atof(getenv("SMCRT_SEG_PIECE")), 1.0f) : 64.0f;  // (experiments)
     P.seg_piece = piece;
-    static const int defer = getenv("SMCRT_SEG_DEFER") ? atoi(getenv("SMCRT_SEG_DEFER")) : 1;
-    P.seg_defer = defer;
     if (c->any_track) { P.hist_ids = D.hist_ids; P.hist_det = D.hist_det; P.hist_n = D.hist_n; P.hist_cap = HIST_CAP; }
     P.eps0 = (float)c->eps0; P.eps_rel = (float)c->eps_rel;
     static const char* wd_env = getenv("SMCRT_WATCHDOG_MS");  // (tests trip the watchdog with a tiny period)
@@ -952,7 +950,7 @@ static int launch_kernel(trace_kernel_t kern, const KParams& P0, DeviceState& D,
         // 2 CTAs of 512 threads per SM (64 registers): a third more warps than 3 x 256 at 80 registers, +7 % on sphere.toml / skin
         // 2 CTAs of 512 threads per SM at 64 registers: a third more warps than 3 x 256 at 80 registers (+7 % on sphere.toml and skin)
         constexpr int DEP_THREADS = 512, DEP_CTAS = 2;
-        const int dep_smem = (int)sizeof(HotTable) + (DEP_THREADS / 32) * RUNQ_CAP * 2 * (int)sizeof(float4);  // the table + the warps' run queues
+        const int dep_smem = (int)sizeof(HotTable) + (DEP_THREADS / 32) * 2 * WARPQ_CAP * 2 * (int)sizeof(float4);  // the table + the warps' two queues
         CU(cudaFuncSetAttribute(deposit_segments_kernel<DEP_THREADS, DEP_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dep_smem));
         deposit_segments_kernel<DEP_THREADS, DEP_CTAS><<<D.sm_count * DEP_CTAS, DEP_THREADS, dep_smem, st>>>(P, (int)blocks);
         clear_segment_counts_kernel<<<1, 256, 0, st>>>(P.seg_count, (int)blocks, P.seg_work);

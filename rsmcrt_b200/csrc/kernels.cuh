@@ -89,7 +89,6 @@ struct KParams {
     unsigned int seg_cap;
     int seg_off;
     unsigned int* seg_work;         // work counter of deposit_segments_kernel (cleared with the shares)
-    int seg_defer;                  // (experiments) 0: run-walk segments are walked where they turn up
     float seg_piece;                // the deposit kernel cuts segments into pieces of about this many voxel visits, one piece per lane
     unsigned long long* seg_total;  // all segments produced (recorded or, when a CTA's share was full, walked inline)
     // optional per-packet outputs (smcrt_trace_packets)
@@ -555,7 +554,16 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // voxel walk up to the rounding of a face time (ta + j dta by one fma instead of j additions).
 // Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
 // full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
-__device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+// The deposits are reductions into GLOBAL memory whose result nobody reads: red.global.  Said in PTX, because in the walkers (not
+// inlined, the grids reached through a KParams reference) the compiler cannot prove the address space, and atomicAdd() then becomes
+// a generic ATOM -- a shared-window test with a CAS loop beside it, and an atomic WITH a reply, which the warp's scoreboard waits
+// for (long-scoreboard stall 5.9 per issued instruction in the deposit kernel on skin_b200.toml; lts op_atom, not op_red).
+__device__ __forceinline__ void red_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_i64(long long* p, long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
 // CTA-private accumulator of the deposit kernel for HOT difference-grid entries ("per-CTA shared-memory tile for the
 // beam column", generalised).  A pencil beam sends 1e9 range updates per 1e8 packets into the ~1300 entries of four voxel columns,
 // and L2 takes same-entry atomics one by one (2.5e10/s measured: the ceiling of r01_red_peaks.json for one column).  An open-
@@ -563,7 +571,7 @@ __device__ __forceinline__ void red_i64(long long* p, long long v) { atomicAdd(r
 // updates of the entries it holds (two native 32-bit shared adds with carry) and is flushed once per CTA; an entry that found no
 // slot goes to L2 as before, so a diffuse scene (millions of distinct entries) loses only the probes.
 constexpr int HOT_SLOTS = 4096, HOT_PROBES = 3;
-constexpr int RUNQ_CAP = 64;  // records in a warp's run-walk queue of the deposit kernel (2 x float4 each)
+constexpr int WARPQ_CAP = 32;  // records in each of a warp's two queues of the deposit kernel (2 x float4 per record)
 struct HotTable {
     unsigned long long key[HOT_SLOTS];
     unsigned int lo[HOT_SLOTS], hi[HOT_SLOTS];
@@ -606,10 +614,10 @@ static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, flo
         const float tn = fminf(tx, fminf(ty, tz));
         ++nvox;
         if (tn >= len) {
-            atomicAdd(cell, fmaxf(len - t, 0.f) * weight);
+            red_f32(cell, fmaxf(len - t, 0.f) * weight);
             break;
         }
-        atomicAdd(cell, fmaxf(tn - t, 0.f) * weight);
+        red_f32(cell, fmaxf(tn - t, 0.f) * weight);
         t = tn;
         // which face: x before y before z on a tie.  Selects, not branches: the lanes of a warp walk different rays
         const bool stx = tx <= ty && tx <= tz, sty = !stx && ty <= tz, stz = !stx && !sty;
@@ -666,16 +674,16 @@ static __device__ __noinline__ uint4 walk_runs(const KParams& P, float fx, float
         if (leave) m = room;
         nvox += (unsigned int)m + 1u;
         if (m == 0) {
-            atomicAdd(P.jmean + off, fmaxf((leave ? ta : tend) - t, 0.f) * weight);
+            red_f32(P.jmean + off, fmaxf((leave ? ta : tend) - t, 0.f) * weight);
             ++nred;
         } else {
             const float p_in = fmaxf(ta - t, 0.f);
             // the last voxel of a run that leaves the grid is crossed whole
             const float p_out = leave ? dta : fmaxf(tend - fmaf((float)(m - 1), dta, ta), 0.f);
             if (m < 3) {  // 2 or 3 voxels: direct deposits are no more atomics than the range update
-                atomicAdd(P.jmean + off, p_in * weight);
-                if (m == 2) atomicAdd(P.jmean + off + sva, dta * weight);
-                atomicAdd(P.jmean + off + (long long)m * sva, p_out * weight);
+                red_f32(P.jmean + off, p_in * weight);
+                if (m == 2) red_f32(P.jmean + off + sva, dta * weight);
+                red_f32(P.jmean + off + (long long)m * sva, p_out * weight);
                 nred += (unsigned int)m + 1u;
             } else {
                 const long long qc = __float2ll_rn(dta * fix);
@@ -796,27 +804,45 @@ __device__ __forceinline__ void record_segment(const KParams& P, unsigned int* s
 
 #ifndef SMCRT_TRACE_TU  // (engine.cu only)
 // The deposit kernel: walks the recorded segments.  One warp takes 32 records of a CTA's share at a time (two coalesced 16-byte
-// loads per lane) and sorts them by the work they are: short segments for the voxel walk -- the free paths of a turbid medium --
-// are walked by their own lanes, all at once; segments for the run walker wait in the warp's queue until a warp's worth has
-// gathered; and a long segment (the 300-voxel flight of an escaping packet, a refracted ray through the 200^3 grid of sphere.toml)
-// is cut into pieces of seg_piece voxel visits that are dealt out to the lanes.
+// loads per lane) and sorts them by the work they are:
+//   * a segment that stays inside ONE voxel -- half the free paths of a turbid medium -- is one atomic, issued at once;
+//   * a short segment for the voxel walk, and one for the run walker (the beam's first flight, a long free path along an axis),
+//     go to the warp's two queues in shared memory and are walked when 32 of a kind have gathered, one per lane: every lane of
+//     the walk is busy.  (Walked where they turned up, the run walk ran on 1.3 lanes of 32 and was 28 % of the kernel's
+//     instructions on skin_b200.toml; the voxel walk's set-up, ~130 instructions, ran for whatever lanes were not single-voxel.)
+//   * a long segment (the 300-voxel flight of an escaping packet, a refracted ray through the 200^3 grid of sphere.toml) is cut
+//     into pieces of seg_piece voxel visits that are dealt out to the lanes.
 // A small kernel with a small loop: the voxel walk does not compete with the transport code for the instruction cache (in one
 // kernel the hot code was 39 KB, beyond the 32 KB L1.5 I-cache: 6 stall cycles per issue waiting for instructions).
+//
+// A warp's queue: 32 records (2 x float4).  Lanes with `pred` append theirs; when that makes 32, the full queue is taken (one
+// record per lane, returned in qa / qb with `full`), and the records that did not fit start the next filling.
+__device__ __forceinline__ bool warp_queue_push(float4* q, int& n, bool pred, const float4& a, const float4& b, int lane, float4& qa, float4& qb) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return false;
+    const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u)), room = 32 - n;
+    if (pred && rank < room) { q[2 * (n + rank)] = a; q[2 * (n + rank) + 1] = b; }
+    __syncwarp();
+    if (n + cnt < 32) { n += cnt; return false; }
+    qa = q[2 * lane]; qb = q[2 * lane + 1];
+    __syncwarp();
+    if (pred && rank >= room) { q[2 * (rank - room)] = a; q[2 * (rank - room) + 1] = b; }
+    n += cnt - 32;
+    __syncwarp();
+    return true;
+}
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const __grid_constant__ KParams P, int n_shares) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    unsigned long long c_vox = 0ull, c_red = 0ull;
+    unsigned int c_vox = 0u, c_red = 0u;  // (per thread: < 2^32 in any launch)
     extern __shared__ __align__(16) unsigned char dsm[];
     HotTable* hot = reinterpret_cast<HotTable*>(dsm);
     for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x) { hot->key[i] = 0ull; hot->lo[i] = 0u; hot->hi[i] = 0u; }
     __syncthreads();
-    // The warp's queue of segments for the RUN walker (behind the table in shared memory, 64 records).  A batch of a turbid scene
-    // holds one or two of them -- the beam's first flight, a long free path along an axis -- and the run walk is long straight-line
-    // code: taken where they turn up, it ran on 1.3 lanes of 32 and was 28 % of the kernel's instructions on skin_b200.toml.  They
-    // wait here until 32 have gathered and are then walked one per lane.
-    float4* const runq = reinterpret_cast<float4*>(dsm + sizeof(HotTable)) + warp * (2 * RUNQ_CAP);
-    int n_runq = 0;  // (warp-uniform)
-    bool use_hot = true;  // (warp-uniform) the table still takes a fair share of what this warp offers it
+    float4* const runq = reinterpret_cast<float4*>(dsm + sizeof(HotTable)) + warp * (4 * WARPQ_CAP);  // the warp's two queues
+    float4* const voxq = runq + 2 * WARPQ_CAP;
+    int n_runq = 0, n_voxq = 0;  // (warp-uniform)
+    bool use_hot = true;         // (warp-uniform) the table still takes a fair share of what this warp offers it
     unsigned int hot_try = 0u, hot_hit = 0u;
     // work items = (share, eighth of the share), handed out by a global counter: the CTAs of this launch are persistent (as many as
     // fit beside their 64-KB tables) and stay busy until the last record.  (Handed out to single warps, a 64th of a share at a
@@ -845,32 +871,27 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                 a = recs[2u * i]; b = recs[2u * i + 1u];
                 runs = takes_run_walk(P, b.x, b.y, b.z, a.w, work);
             }
-            // The 32 segments of a batch are of very different lengths (a free path of two voxels next to the 300-voxel flight of an
-            // escaping packet): walked one per lane, the warp waits for its longest with 3-7 lanes of 32 busy (ncu:
-            // profiles/r02_skin_deposit_kernel.txt).  So every segment is cut into PIECES of about seg_piece voxel visits, the pieces
-            // of the batch are numbered through (a warp prefix sum), and lane j of pass p walks piece 32 p + j of whichever segment
-            // it belongs to (its record fetched by shuffle): equal work per lane.  A voxel that holds a cut gets its length in two
-            // deposits.  The short segments (one piece) go first, each on its own lane, so that they do not wait for longer pieces.
+            // ---- inside one voxel?  Start and end in voxel units, both well inside the same cell (the margin covers the rounding
+            // of these few operations: the walk's own cell and face arithmetic is not needed to know that no face is crossed).
+            // The walk would deposit len * weight into the start cell; so does this.
+            if (work > 0.f && work < 4.0f && !P.dda_legacy) {
+                const float s0 = fmaf(a.x, P.inv_vox[0], 0.5f * (float)P.nxg), s1 = fmaf(a.y, P.inv_vox[1], 0.5f * (float)P.nyg),
+                            s2 = fmaf(a.z, P.inv_vox[2], 0.5f * (float)P.nzg);
+                const float e0 = fmaf(a.w * b.x, P.inv_vox[0], s0), e1 = fmaf(a.w * b.y, P.inv_vox[1], s1), e2 = fmaf(a.w * b.z, P.inv_vox[2], s2);
+                const float c0 = floorf(s0), c1 = floorf(s1), c2 = floorf(s2);
+                constexpr float MG = 2.0e-3f;
+                const float lo = fminf(fminf(fminf(s0 - c0, e0 - c0), fminf(s1 - c1, e1 - c1)), fminf(s2 - c2, e2 - c2));
+                const float hi = fmaxf(fmaxf(fmaxf(s0 - c0, e0 - c0), fmaxf(s1 - c1, e1 - c1)), fmaxf(s2 - c2, e2 - c2));
+                if (lo > MG && hi < 1.0f - MG && c0 >= 0.f && c1 >= 0.f && c2 >= 0.f && c0 < (float)P.nxg && c1 < (float)P.nyg && c2 < (float)P.nzg) {
+                    red_f32(P.jmean + ((long long)c0 + (long long)P.nxg * ((long long)c1 + (long long)P.nyg * (long long)c2)), a.w * b.w);
+                    ++c_vox; ++c_red;
+                    work = 0.f;  // done
+                }
+            }
+            // ---- long segments: cut into PIECES of about seg_piece voxel visits, numbered through the batch (a warp prefix sum);
+            // lane j of pass p walks piece 32 p + j of whichever segment it belongs to (its record fetched by shuffle): equal work
+            // per lane.  A voxel that holds a cut gets its length in two deposits.
             const bool brief = work > 0.f && work <= P.seg_piece;
-            const bool defer = brief && runs && P.seg_defer;
-            const unsigned dm = __ballot_sync(0xffffffffu, defer);
-            if (dm) {
-                if (defer) {
-                    const int at = n_runq + __popc(dm & ((1u << lane) - 1u));
-                    runq[2 * at] = a; runq[2 * at + 1] = b;
-                }
-                n_runq += __popc(dm);
-                __syncwarp();
-            }
-            if (brief && !defer) {
-                if (runs) {  // (only with the queue switched off)
-                    const uint4 w = walk_runs(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w, use_hot ? hot : nullptr);
-                    c_vox += w.x; c_red += w.y;
-                } else {
-                    const uint2 w = walk_voxels(P, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w);
-                    c_vox += w.x; c_red += w.y;
-                }
-            }
             const int np = (work > 0.f && !brief) ? (int)fminf(ceilf(work / P.seg_piece), 65536.f) : 0;
             int incl = np;
 #pragma unroll
@@ -883,9 +904,9 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                 const int g = min(g0 + lane, total - 1);
                 int own = 0;  // the segment piece g belongs to: the number of lanes whose pieces all come before it
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, incl, own + s - 1);
-                    if (v <= g) own += s;
+                for (int st = 16; st > 0; st >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, own + st - 1);
+                    if (v <= g) own += st;
                 }
                 const int npo = __shfl_sync(0xffffffffu, np, own), first = __shfl_sync(0xffffffffu, incl, own) - npo;
                 const float L = __shfl_sync(0xffffffffu, a.w, own), w = __shfl_sync(0xffffffffu, b.w, own);
@@ -899,10 +920,13 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
                     c_vox += wk.x; c_red += wk.y;
                 }
             }
-            if (n_runq >= 32) {  // (last: the batch's own records are no longer live across this call)
-                n_runq -= 32;
-                const float4 qa = runq[2 * (n_runq + lane)], qb = runq[2 * (n_runq + lane) + 1];
-                __syncwarp();
+            // ---- short segments: into the queue of their walker; a full queue is walked, one record per lane
+            float4 qa, qb;
+            if (warp_queue_push(voxq, n_voxq, brief && !runs, a, b, lane, qa, qb)) {
+                const uint2 w = walk_voxels(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w);
+                c_vox += w.x; c_red += w.y;
+            }
+            if (warp_queue_push(runq, n_runq, brief && runs, a, b, lane, qa, qb)) {
                 const uint4 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, use_hot ? hot : nullptr);
                 c_vox += w.x; c_red += w.y;
                 // Does the table earn its probes?  On a pencil beam nearly every entry is one of the ~1300 it holds; on a diffuse scene
@@ -918,7 +942,12 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
             }
         }
     }
-    if (lane < n_runq) {  // what is left in the warp's queue
+    if (lane < n_voxq) {  // what is left in the warp's queues
+        const float4 qa = voxq[2 * lane], qb = voxq[2 * lane + 1];
+        const uint2 w = walk_voxels(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w);
+        c_vox += w.x; c_red += w.y;
+    }
+    if (lane < n_runq) {
         const float4 qa = runq[2 * lane], qb = runq[2 * lane + 1];
         const uint4 w = walk_runs(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w, use_hot ? hot : nullptr);
         c_vox += w.x; c_red += w.y;
@@ -929,9 +958,10 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
             const long long v = (long long)(((unsigned long long)hot->hi[i] << 32) | (unsigned long long)hot->lo[i]);
             if (v) red_i64(reinterpret_cast<long long*>(hot->key[i]), v);
         }
+    unsigned long long t_vox = c_vox, t_red = c_red;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { c_vox += __shfl_xor_sync(0xffffffffu, c_vox, o); c_red += __shfl_xor_sync(0xffffffffu, c_red, o); }
-    if (lane == 0 && c_vox) { atomicAdd(&P.counters[C_VOXELS], c_vox); atomicAdd(&P.counters[C_REDS], c_red); }
+    for (int o = 16; o > 0; o >>= 1) { t_vox += __shfl_xor_sync(0xffffffffu, t_vox, o); t_red += __shfl_xor_sync(0xffffffffu, t_red, o); }
+    if (lane == 0 && t_vox) { atomicAdd(&P.counters[C_VOXELS], t_vox); atomicAdd(&P.counters[C_REDS], t_red); }
 }
 // (the shares are cleared for the next launch by a second tiny kernel: a CTA of the deposit kernel may still be reading a count)
 __global__ void clear_segment_counts_kernel(unsigned int* cnt, int n, unsigned int* work) {

@@ -480,6 +480,16 @@ __device__ __forceinline__ long long voxel_of(const KParams& P, float x, float y
     i = min(max(i, 0), P.nxg - 1); j = min(max(j, 0), P.nyg - 1); k = min(max(k, 0), P.nzg - 1);
     return (long long)i + (long long)P.nxg * ((long long)j + (long long)P.nyg * (long long)k);
 }
+// The deposits are reductions into GLOBAL memory whose result nobody reads: red.global.  Said in PTX, because in the walkers (not
+// inlined, the grids reached through a KParams reference) the compiler cannot prove the address space, and atomicAdd() then becomes
+// a generic ATOM -- a shared-window test with a CAS loop beside it, and an atomic WITH a reply, which the warp's scoreboard waits
+// for (long-scoreboard stall 5.9 per issued instruction in the deposit kernel on skin_b200.toml; lts op_atom, not op_red).
+__device__ __forceinline__ void red_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_i64(long long* p, long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
 // Warp-aggregated deposit: lanes of the converged group that hit the same voxel are summed with shuffles and
 // ONE red.global.add.f32 is issued per distinct voxel.
 // NB must stay inlined: __activemask() inside a called (noinline) function does not name the lanes that called it together,
@@ -499,7 +509,7 @@ __device__ __forceinline__ void deposit(float* grid, long long vox, float w) {
             rem &= rem - 1;
         }
     }
-    if (lane == leader) atomicAdd(grid + vox, sum);  // result unused -> RED.E.ADD.F32
+    if (lane == leader) red_f32(grid + vox, sum);
 }
 
 // update_grids in -Dpathlength mode (src/inttau2.f90:408-445): deposits (segment length * weight) into every voxel the straight
@@ -554,16 +564,6 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // voxel walk up to the rounding of a face time (ta + j dta by one fma instead of j additions).
 // Fixed point: 2^28 units per voxel edge of the run's axis (3.7e-9 relative), weight folded in; |D| < 2^63 holds for 2^32
 // full-chord deposits into one entry, and the engine scans the difference grids at least every 2^32 packets.
-// The deposits are reductions into GLOBAL memory whose result nobody reads: red.global.  Said in PTX, because in the walkers (not
-// inlined, the grids reached through a KParams reference) the compiler cannot prove the address space, and atomicAdd() then becomes
-// a generic ATOM -- a shared-window test with a CAS loop beside it, and an atomic WITH a reply, which the warp's scoreboard waits
-// for (long-scoreboard stall 5.9 per issued instruction in the deposit kernel on skin_b200.toml; lts op_atom, not op_red).
-__device__ __forceinline__ void red_f32(float* p, float v) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
-}
-__device__ __forceinline__ void red_i64(long long* p, long long v) {
-    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
-}
 // CTA-private accumulator of the deposit kernel for HOT difference-grid entries ("per-CTA shared-memory tile for the
 // beam column", generalised).  A pencil beam sends 1e9 range updates per 1e8 packets into the ~1300 entries of four voxel columns,
 // and L2 takes same-entry atomics one by one (2.5e10/s measured: the ceiling of r01_red_peaks.json for one column).  An open-

@@ -349,6 +349,43 @@ def test_kernel_variants_trace_identical_histories_with_fresnel_events(engine, o
     assert np.array_equal(a["absorb"], b["absorb"])
 
 
+def test_pathlength_chunked_run_on_two_lanes_equals_single_launch(engine, smcrt, monkeypatch):
+    """A path-length run whose segments do not fit the segment buffer is cut into chunks of packets that alternate between two
+    stream lanes (half a buffer and a packet counter each), each lane's deposit kernel behind its trace
+    kernel.  Histories depend on (seed, packet id) only, so the chunked run IS the single-launch run: identical counters and
+    absorb counts, fluence equal to the order of the float32 / fixed-point atomics."""
+    cfg = smcrt.Config.load(RES / "skin_b200.toml")
+    n, mode = 400_000, A.TALLY_PATHLENGTH | A.TALLY_ABSORB
+    engine.apply(cfg)
+    l0 = engine.launch_count
+    engine.run(n, 9, tally_mode=mode)
+    single = engine.launch_count - l0
+    a = engine.fetch(jmean=True, absorb=True)
+    monkeypatch.setenv("SMCRT_SEG_MB", "64")
+    # 2 x 1e6 records, 41 segments per packet: the chunks (32 768 packets at least) overflow their shares, so the trace kernel's
+    # inline fallback of a full share is exercised as well
+    e2 = smcrt.Engine(1)
+    try:
+        e2.apply(cfg)
+        l0 = e2.launch_count
+        e2.run(n, 9, tally_mode=mode)
+        chunked = e2.launch_count - l0
+        b = e2.fetch(jmean=True, absorb=True)
+    finally:
+        e2.close()
+    assert chunked >= single + 3 * 3  # (trace + deposit + clear per chunk: several more chunks than the single launch)
+    for k in ("launched", "nscatt", "lost", "bounces"):
+        assert a["counters"][k] == b["counters"][k], k
+    assert a["counters"]["launched"] == n
+    assert np.array_equal(a["absorb"], b["absorb"])
+    ja, jb = a["jmean"].astype(np.float64), b["jmean"].astype(np.float64)
+    assert jb.sum() > 0 and abs(ja.sum() - jb.sum()) < 2e-6 * jb.sum()
+    err = np.abs(ja - jb)
+    # (a long segment is cut into pieces; a chunk boundary does not move the cuts, so only the order of the adds differs)
+    assert err.max() < 1e-4 * jb.max()
+    assert err.sum() < 1e-5 * jb.sum()
+
+
 @pytest.mark.parametrize("deck,n,tol", [("validation1.toml", 20_000, 2e-4), ("sphere.toml", 100_000, 2e-5), ("skin_b200.toml", 50_000, 2e-5),
                                         ("scat_test.toml", 20_000, 2e-5), ("lens.toml", 50_000, 2e-5)])
 def test_pathlength_run_walker_equals_voxel_walker(engine, oracle, smcrt, monkeypatch, deck, n, tol):

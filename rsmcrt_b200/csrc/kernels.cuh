@@ -570,7 +570,9 @@ __device__ __forceinline__ DdaStart dda_start(const KParams& P, float fx, float 
 // addressing table in shared memory -- key = the entry's address, first come first kept, at most HOT_PROBES probes -- takes the
 // updates of the entries it holds (two native 32-bit shared adds with carry) and is flushed once per CTA; an entry that found no
 // slot goes to L2 as before, so a diffuse scene (millions of distinct entries) loses only the probes.
-constexpr int HOT_SLOTS = 4096, HOT_PROBES = 3;
+// 2048 slots = 32 KB: room for the slab's ~1300 hot entries; 4096 slots cost the other scenes 2-3 % (the shared memory comes out of
+// the L1 that serves the kernel's spills and records) and gained the slab 0.6 %
+constexpr int HOT_BITS = 11, HOT_SLOTS = 1 << HOT_BITS, HOT_PROBES = 3;
 constexpr int WARPQ_CAP = 32;  // records in each of a warp's two queues of the deposit kernel (2 x float4 per record)
 struct HotTable {
     unsigned long long key[HOT_SLOTS];
@@ -578,7 +580,7 @@ struct HotTable {
 };
 __device__ __forceinline__ bool red_i64_hot(HotTable* T, long long* p, long long v) {  // true: the table took it
     const unsigned long long k = (unsigned long long)p;
-    unsigned int h = (unsigned int)((k >> 3) * 0x9E3779B97F4A7C15ull >> 52);
+    unsigned int h = (unsigned int)((k >> 3) * 0x9E3779B97F4A7C15ull >> (64 - HOT_BITS));
 #pragma unroll
     for (int probe = 0; probe < HOT_PROBES; ++probe) {
         unsigned long long cur = T->key[h];
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
     bool use_hot = true;         // (warp-uniform) the table still takes a fair share of what this warp offers it
     unsigned int hot_try = 0u, hot_hit = 0u;
     // work items = (share, eighth of the share), handed out by a global counter: the CTAs of this launch are persistent (as many as
-    // fit beside their 64-KB tables) and stay busy until the last record.  (Handed out to single warps, a 64th of a share at a
+    // fit beside their 32-KB tables) and stay busy until the last record.  (Handed out to single warps, a 64th of a share at a
     // time and no barrier, the kernel was 1-3 % slower: the warps of a CTA no longer read neighbouring records.)
     __shared__ unsigned int item_s;
     constexpr unsigned int PARTS = 8u;

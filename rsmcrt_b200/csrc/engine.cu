@@ -1200,6 +1200,8 @@ extern "C" int smcrt_wait(smcrt_ctx* c) {
     for (DeviceState& D : c->devs) {  // every device first: an error below must not leave another device's run in flight
         CU(cudaSetDevice(D.dev));
         CU(cudaStreamSynchronize(D.stream));
+        // (the main stream has joined the chunk lanes of a path-length run; after a launch error it has not)
+        for (cudaStream_t ls : D.lane_stream) if (ls) CU(cudaStreamSynchronize(ls));
     }
     int wd_dev = -1;
     for (DeviceState& D : c->devs) {

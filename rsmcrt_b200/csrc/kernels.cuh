@@ -598,7 +598,7 @@ __device__ __forceinline__ bool red_i64_hot(HotTable* T, long long* p, long long
 }
 // Two functions (the deposit kernel knows which one a segment takes and calls it directly: each gets its own register allocation).
 // walk_voxels: the voxel walk.  Returns (voxels visited, atomics issued).
-static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+__device__ __forceinline__ uint2 walk_voxels_inl(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
     if (!in_grid(P, fx, fy, fz)) return make_uint2(0u, 0u);  // :411-415
     const DdaStart S = dda_start(P, fx, fy, fz, dx, dy, dz);
     const long long vy = (long long)P.nxg, vz = (long long)P.nxg * (long long)P.nyg;
@@ -629,6 +629,11 @@ static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, flo
         if ((rx | ry | rz) < 0) break;  // :437-440
     }
     return make_uint2(nvox, nvox);
+}
+// (called where the walk is not the hot path; the deposit kernel's voxel-walk queue inlines the body: its KParams reads are then
+// constant-bank loads and no registers are saved around a call)
+static __device__ __noinline__ uint2 walk_voxels(const KParams& P, float fx, float fy, float fz, float dx, float dy, float dz, float len, float weight) {
+    return walk_voxels_inl(P, fx, fy, fz, dx, dy, dz, len, weight);
 }
 // walk_runs: the run walk.  `hot`: the deposit kernel's table (nullptr: every range update goes straight to L2)
 // Returns (voxels visited, atomics issued, range-update entries offered to the table, entries it took).
@@ -925,7 +930,7 @@ __global__ void __launch_bounds__(THREADS, MINB) deposit_segments_kernel(const _
             // ---- short segments: into the queue of their walker; a full queue is walked, one record per lane
             float4 qa, qb;
             if (warp_queue_push(voxq, n_voxq, brief && !runs, a, b, lane, qa, qb)) {
-                const uint2 w = walk_voxels(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w);
+                const uint2 w = walk_voxels_inl(P, qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, qa.w, qb.w);
                 c_vox += w.x; c_red += w.y;
             }
             if (warp_queue_push(runq, n_runq, brief && runs, a, b, lane, qa, qb)) {
